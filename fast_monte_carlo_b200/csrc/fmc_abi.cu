@@ -1,0 +1,496 @@
+// C ABI of libfmc_b200.so (include/fmc.h): context, forest specialisation/upload, the tree-predict
+// kernel launch and the persistent simulation kernel launch.  No CPU fallback anywhere: every
+// compute entry point launches a kernel or fails.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "fmc_sim.cuh"
+
+using namespace fmc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(FMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// tree-predict kernel: one lane per row, all lanes of a warp walk the same trees
+// ---------------------------------------------------------------------------------------------
+struct PredictArgs {
+    const double *rows;     // [n][17]
+    double *out;            // [n][n_outputs]
+    long long n;
+    const uint2 *slots;
+    const uint32_t *roots;
+    int n_outputs, rounds_padded, max_depth, n_num;
+    int zero_is_missing;
+    double base[8];
+    int n_scaled;
+    int scaler_cols[16];
+    double scaler_mean[16], scaler_scale[16];
+};
+
+constexpr int kPredThreads = 256;
+
+template <bool SKL>
+__global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs a) {
+    __shared__ float rows[kPredThreads * kPredStride];
+    const int tid = threadIdx.x;
+    const float inf = __int_as_float(0x7f800000);
+    for (long long base = (long long)blockIdx.x * kPredThreads; base < a.n; base += (long long)gridDim.x * kPredThreads) {
+        for (int i = tid; i < kPredThreads * kNumMax; i += kPredThreads) {
+            const int r = i / kNumMax, k = i - r * kNumMax;
+            const long long idx = base + r;
+            if (idx >= a.n || k >= a.n_num) continue;
+            double x = a.rows[idx * kNumMax + k];
+            for (int j = 0; j < a.n_scaled; ++j)
+                if (a.scaler_cols[j] == k) x = (x - a.scaler_mean[j]) / a.scaler_scale[j];
+            const float v = (float)x;
+            const bool flag = (k == 3 || k == 12 || k == 13 || k == 14 || k == 16);
+            float *row = rows + r * kPredStride;
+            if (flag || !a.zero_is_missing) {
+                row[k] = v;
+            } else {
+                // rows of the B views follow the 17 numerics in the order of the non-flag columns
+                int nb = kNumMax;
+                for (int q = 0; q < k; ++q) nb += !(q == 3 || q == 12 || q == 13 || q == 14 || q == 16);
+                row[k] = v == 0.f ? -inf : v;
+                row[nb] = v == 0.f ? inf : v;
+            }
+        }
+        __syncthreads();
+        const bool live = base + tid < a.n;
+        const float *frow = rows + (live ? tid : 0) * kPredStride;
+        for (int o = 0; o < a.n_outputs; ++o) {
+            const uint32_t *roots = a.roots + (size_t)o * a.rounds_padded;
+            double v;
+            if (SKL) {
+                v = (a.max_depth <= 3) ? walk_output<true, 5, true, 3>(a.slots, roots, a.rounds_padded, frow, a.base[o])
+                                       : walk_output<true, 5, true, 99>(a.slots, roots, a.rounds_padded, frow, a.base[o]);
+            } else {
+                v = walk_output<false, 5, true, 99>(a.slots, roots, a.rounds_padded, frow, a.base[o]);
+            }
+            if (live) a.out[(base + tid) * a.n_outputs + o] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct fmc_ctx {
+    int device = 0;
+    cudaDeviceProp prop;
+    HostForest forest[FMC_N_MODELS];
+    fmc_params params;
+    std::vector<fmc_matchup> matchups;
+    bool tables_dirty = true;
+    // device-side state of the last set_matchups
+    uint2 *d_slots = nullptr;
+    uint32_t *d_roots = nullptr;
+    MatchupDev *d_matchups = nullptr;
+    unsigned long long *d_next = nullptr;
+    std::vector<unsigned long long> h_next;
+    std::vector<int32_t> packed_slots;   // [n_matchups][FMC_N_MODELS][2]
+    // predict scratch
+    uint2 *p_slots = nullptr;
+    uint32_t *p_roots = nullptr;
+    size_t p_slots_cap = 0, p_roots_cap = 0;
+};
+
+extern "C" const char *fmc_last_error(void) { return g_err.c_str(); }
+extern "C" int fmc_abi_version(void) { return FMC_ABI_VERSION; }
+
+extern "C" int fmc_create(int device, fmc_ctx **out) {
+    if (!out) return fail(FMC_ERR_INVALID, "fmc_create: out is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0)
+        return fail(FMC_ERR_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                           " (libfmc_b200 has no CPU fallback)");
+    if (device < 0 || device >= n) return fail(FMC_ERR_INVALID, "fmc_create: bad device index");
+    fmc_ctx *c = new fmc_ctx();
+    c->device = device;
+    CK(cudaSetDevice(device));
+    CK(cudaGetDeviceProperties(&c->prop, device));
+    if (c->prop.major != 10) {
+        std::string nm = c->prop.name;
+        delete c;
+        return fail(FMC_ERR_NO_DEVICE, "device '" + nm + "' is not sm_100 (this library is built for sm_100a only)");
+    }
+    std::memset(&c->params, 0, sizeof(c->params));
+    c->params.play_temp = 1.0;
+    c->params.qy_noise = 0.5;
+    c->params.stage2_standin[0] = (double)0.78f;
+    c->params.stage2_standin[1] = (double)0.05f;
+    c->params.stage2_standin[2] = (double)0.17f;
+    CK(cudaFuncSetAttribute(sim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes()));
+    *out = c;
+    return FMC_OK;
+}
+
+extern "C" void fmc_destroy(fmc_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_slots); cudaFree(c->d_roots); cudaFree(c->d_matchups); cudaFree(c->d_next);
+    cudaFree(c->p_slots); cudaFree(c->p_roots);
+    delete c;
+}
+
+extern "C" int fmc_device_info(fmc_ctx *c, int32_t *sm_count, int32_t *smem_per_block, char *name, int32_t name_len) {
+    if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
+    if (sm_count) *sm_count = c->prop.multiProcessorCount;
+    if (smem_per_block) *smem_per_block = (int32_t)c->prop.sharedMemPerBlockOptin;
+    if (name && name_len > 0) { std::strncpy(name, c->prop.name, name_len - 1); name[name_len - 1] = 0; }
+    return FMC_OK;
+}
+
+extern "C" int fmc_load_forest(fmc_ctx *c, int32_t id, const fmc_forest_desc *d) {
+    if (!c || !d || id < 0 || id >= FMC_N_MODELS) return fail(FMC_ERR_INVALID, "fmc_load_forest: bad argument");
+    if (d->n_outputs < 1 || d->n_outputs > 8 || d->n_nodes <= 0 || d->n_trees <= 0 || d->n_num > kNumMax)
+        return fail(FMC_ERR_INVALID, "fmc_load_forest: bad shape");
+    const int32_t keep0 = c->forest[id].active[0], keep1 = c->forest[id].active[1];
+    const bool had = c->forest[id].loaded;
+    c->forest[id].assign(*d);
+    if (!had) { c->forest[id].active[0] = -1; c->forest[id].active[1] = -1; }
+    else { c->forest[id].active[0] = keep0; c->forest[id].active[1] = keep1; }
+    c->tables_dirty = true;
+    return FMC_OK;
+}
+
+extern "C" int fmc_set_scaler(fmc_ctx *c, int32_t id, int32_t n, const int32_t *cols, const double *mean, const double *scale) {
+    if (!c || id < 0 || id >= FMC_N_MODELS || n < 0 || n > 16) return fail(FMC_ERR_INVALID, "fmc_set_scaler: bad argument");
+    HostForest &f = c->forest[id];
+    f.n_scaled = n;
+    for (int i = 0; i < n; ++i) { f.scaler_cols[i] = cols[i]; f.scaler_mean[i] = mean[i]; f.scaler_scale[i] = scale[i]; }
+    c->tables_dirty = true;
+    return FMC_OK;
+}
+
+extern "C" int fmc_set_active_columns(fmc_ctx *c, int32_t id, int32_t col0, int32_t col1) {
+    if (!c || id < 0 || id >= FMC_N_MODELS) return fail(FMC_ERR_INVALID, "fmc_set_active_columns: bad argument");
+    c->forest[id].active[0] = col0;
+    c->forest[id].active[1] = col1;
+    c->tables_dirty = true;
+    return FMC_OK;
+}
+
+extern "C" int fmc_set_params(fmc_ctx *c, const fmc_params *p) {
+    if (!c || !p) return fail(FMC_ERR_INVALID, "fmc_set_params: bad argument");
+    if (p->policy < 0 || p->policy > 1 || p->sampler < 0 || p->sampler > 1 || p->stage2_mode < 0 || p->stage2_mode > 1)
+        return fail(FMC_ERR_INVALID, "fmc_set_params: unknown mode");
+    c->params = *p;
+    c->tables_dirty = true;
+    return FMC_OK;
+}
+
+extern "C" int fmc_set_matchups(fmc_ctx *c, int32_t n, const fmc_matchup *m) {
+    if (!c || n <= 0 || !m) return fail(FMC_ERR_INVALID, "fmc_set_matchups: bad argument");
+    for (int i = 0; i < n; ++i)
+        if (m[i].game_end < m[i].game_begin) return fail(FMC_ERR_INVALID, "fmc_set_matchups: game_end < game_begin");
+    c->matchups.assign(m, m + n);
+    c->tables_dirty = true;
+    return FMC_OK;
+}
+
+static bool family_needed(const fmc_ctx *c, int fam) {
+    if (fam == FMC_PASS_STAGE2) return c->params.stage2_mode == 1;
+    if (fam == FMC_PLAY_MODEL) return c->params.policy == 1;
+    return fam <= FMC_SACK_YARDS;
+}
+
+// Specialise + pack every needed forest for both orientations of every matchup; upload.
+static int build_tables(fmc_ctx *c) {
+    if (c->matchups.empty()) return fail(FMC_ERR_INVALID, "fmc_set_matchups has not been called");
+    for (int fam = 0; fam < kNumFam; ++fam)
+        if (family_needed(c, fam) && !c->forest[fam].loaded)
+            return fail(FMC_ERR_INVALID, "model " + std::to_string(fam) + " is required by the current fmc_params but not loaded");
+    const int n = (int)c->matchups.size();
+    std::vector<uint64_t> slots;
+    std::vector<uint32_t> roots;
+    std::vector<MatchupDev> md(n);
+    c->packed_slots.assign((size_t)n * FMC_N_MODELS * 2, 0);
+    for (int i = 0; i < n; ++i) {
+        const fmc_matchup &mu = c->matchups[i];
+        MatchupDev &M = md[i];
+        std::memset(&M, 0, sizeof(M));
+        M.game_begin = mu.game_begin; M.game_end = mu.game_end; M.out_offset = mu.out_offset;
+        for (int off = 0; off < 2; ++off) {
+            const int de = off ^ 1;
+            const double O = mu.sp[off][1], D = mu.sp[de][2];
+            M.bias[off] = 0.12 * (O - D) / 40.0;                 // matchup_bias FMC:431-433
+            M.ymul[off] = 1.0 + 0.10 * std::tanh((O - D) / 30.0);  // yardage_multiplier FMC:435-437
+            M.mz[off] = (O - D) / 40.0;                          // mismatch_z FMC:440-442
+            M.tanh35[off] = std::tanh((O - D) / 35.0);           // FMC:448, 456
+            for (int fam = 0; fam < kNumFam; ++fam) {
+                if (!family_needed(c, fam)) continue;
+                const HostForest &f = c->forest[fam];
+                PackSpec s;
+                preset_sim(s);
+                s.active[0] = f.active[0]; s.active[1] = f.active[1];
+                if (fam == FMC_PLAY_MODEL) { s.active[0] = mu.coach_col[off]; s.active[1] = -1; }
+                s.fold_value[6] = 3.0; s.fold_value[7] = 3.0;    // timeouts are never spent (FMC:911-912)
+                s.fold_value[8] = mu.sp[off][0]; s.fold_value[9] = mu.sp[off][1];
+                s.fold_value[10] = mu.sp[de][2]; s.fold_value[11] = mu.sp[de][0];
+                s.n_scaled = f.n_scaled;
+                for (int j = 0; j < f.n_scaled; ++j) { s.scaler_cols[j] = f.scaler_cols[j]; s.scaler_mean[j] = f.scaler_mean[j]; s.scaler_scale[j] = f.scaler_scale[j]; }
+                PackedForest pf;
+                const std::string err = pack_forest(f, s, pf);
+                if (!err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(fam) + ": " + err);
+                TableRef &T = M.tbl[fam][off];
+                if (slots.size() + pf.slots.size() >= 0xFFFFFFFFull) return fail(FMC_ERR_CAPACITY, "slot buffer too large");
+                T.slots_off = (uint32_t)slots.size();
+                T.roots_off = (uint32_t)roots.size();
+                T.rounds_padded = (uint16_t)pf.rounds_padded;
+                T.n_outputs = (uint8_t)pf.n_outputs;
+                T.max_depth = (uint8_t)pf.max_depth;
+                for (int k = 0; k < 5 && k < f.n_outputs; ++k) T.base[k] = (float)f.base[k];
+                for (int k = 0; k < 3 && k < f.n_outputs; ++k) T.base64[k] = f.base[k];
+                slots.insert(slots.end(), pf.slots.begin(), pf.slots.end());
+                roots.insert(roots.end(), pf.roots.begin(), pf.roots.end());
+                c->packed_slots[((size_t)i * FMC_N_MODELS + fam) * 2 + off] = (int32_t)pf.slots.size();
+            }
+        }
+    }
+    CK(cudaSetDevice(c->device));
+    cudaFree(c->d_slots); cudaFree(c->d_roots); cudaFree(c->d_matchups); cudaFree(c->d_next);
+    c->d_slots = nullptr; c->d_roots = nullptr; c->d_matchups = nullptr; c->d_next = nullptr;
+    CK(cudaMalloc(&c->d_slots, slots.size() * 8));
+    CK(cudaMalloc(&c->d_roots, roots.size() * 4));
+    CK(cudaMalloc(&c->d_matchups, md.size() * sizeof(MatchupDev)));
+    CK(cudaMalloc(&c->d_next, (size_t)n * 8));
+    CK(cudaMemcpy(c->d_slots, slots.data(), slots.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_roots, roots.data(), roots.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_matchups, md.data(), md.size() * sizeof(MatchupDev), cudaMemcpyHostToDevice));
+    c->h_next.resize(n);
+    c->tables_dirty = false;
+    return FMC_OK;
+}
+
+// skl leaves are stored pre-multiplied by the learning rate: scale * value is the same IEEE product
+// whether it is formed at pack time or per row (sklearn: out += scale * value[leaf]).
+static void prescale(HostForest &f) {
+    if (f.kind == FMC_KIND_SKL && f.scale != 1.0) {
+        for (size_t i = 0; i < f.value.size(); ++i)
+            if (f.left[i] < 0) f.value[i] = f.scale * f.value[i];
+        f.scale = 1.0;
+    }
+}
+
+extern "C" int fmc_packed_slots(fmc_ctx *c, int32_t m, int32_t *out) {
+    if (!c || !out) return fail(FMC_ERR_INVALID, "fmc_packed_slots: bad argument");
+    if (c->tables_dirty) {
+        for (int i = 0; i < FMC_N_MODELS; ++i) prescale(c->forest[i]);
+        int rc = build_tables(c);
+        if (rc) return rc;
+    }
+    if (m < 0 || m >= (int)c->matchups.size()) return fail(FMC_ERR_INVALID, "fmc_packed_slots: bad matchup");
+    std::memcpy(out, c->packed_slots.data() + (size_t)m * FMC_N_MODELS * 2, sizeof(int32_t) * FMC_N_MODELS * 2);
+    return FMC_OK;
+}
+
+extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
+    if (!c || !g) return fail(FMC_ERR_INVALID, "fmc_simulate: bad argument");
+    CK(cudaSetDevice(c->device));
+    if (c->tables_dirty) {
+        for (int i = 0; i < FMC_N_MODELS; ++i) prescale(c->forest[i]);
+        int rc = build_tables(c);
+        if (rc) return rc;
+    }
+    if (g->n_matchups != (int)c->matchups.size()) return fail(FMC_ERR_INVALID, "fmc_simulate: n_matchups mismatch");
+    cudaStream_t st = (cudaStream_t)g->stream;
+    for (size_t i = 0; i < c->matchups.size(); ++i) c->h_next[i] = c->matchups[i].game_begin;
+    CK(cudaMemcpyAsync(c->d_next, c->h_next.data(), c->h_next.size() * 8, cudaMemcpyHostToDevice, st));
+    SimKernelArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.matchups = c->d_matchups; a.n_matchups = (int)c->matchups.size(); a.next_game = c->d_next;
+    a.slots = c->d_slots; a.roots = c->d_roots;
+    a.seed_lo = (uint32_t)g->seed; a.seed_hi = (uint32_t)(g->seed >> 32);
+    a.policy = c->params.policy; a.sampler = c->params.sampler; a.stage2_mode = c->params.stage2_mode;
+    a.play_temp = (float)c->params.play_temp; a.qy_noise = c->params.qy_noise;
+    for (int k = 0; k < 3; ++k) a.standin[k] = c->params.stage2_standin[k];
+    const HostForest &pm = c->forest[FMC_PLAY_MODEL];
+    for (int k = 0; k < 6; ++k) { a.pm_scaled[k] = 0; a.pm_mean[k] = 0.0; a.pm_scale[k] = 1.0; }
+    for (int j = 0; j < pm.n_scaled; ++j) {
+        const int k = pm.scaler_cols[j];
+        if (k >= 0 && k < 6) { a.pm_scaled[k] = 1; a.pm_mean[k] = pm.scaler_mean[j]; a.pm_scale[k] = pm.scaler_scale[j]; }
+    }
+    a.scores = g->scores_dev; a.hist = g->hist_dev; a.counters = (unsigned long long *)g->counters_dev;
+    a.stream = g->stream_dev; a.trace = g->trace_dev; a.iters = g->iters_dev;
+    const int grid = c->prop.multiProcessorCount;
+    sim_kernel<<<grid, kSimThreads, sim_smem_bytes(), st>>>(a);
+    CK(cudaGetLastError());
+    return FMC_OK;
+}
+
+extern "C" int fmc_simulate_host(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
+                                 uint64_t *counters_host, const double *stream_host, double *trace_host,
+                                 uint16_t *iters_host) {
+    if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
+    if (c->matchups.empty()) return fail(FMC_ERR_INVALID, "fmc_set_matchups has not been called");
+    CK(cudaSetDevice(c->device));
+    size_t games = 0;
+    for (auto &m : c->matchups) {
+        const size_t hi = (size_t)(m.out_offset + (m.game_end - m.game_begin));
+        if (hi > games) games = hi;
+    }
+    const size_t nm = c->matchups.size();
+    const size_t hist_n = nm * 2 * FMC_HIST_BINS * FMC_HIST_BINS;
+    uint32_t *d_scores = nullptr, *d_hist = nullptr;
+    uint64_t *d_cnt = nullptr;
+    double *d_stream = nullptr, *d_trace = nullptr;
+    uint16_t *d_iters = nullptr;
+    int rc = FMC_OK;
+    cudaError_t e = cudaSuccess;
+    auto bail = [&](cudaError_t err, const char *what) { rc = fail(FMC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err)); };
+    do {
+        if (scores_host && games) { if ((e = cudaMalloc(&d_scores, games * 4)) != cudaSuccess) { bail(e, "cudaMalloc scores"); break; } }
+        if (hist_host) {
+            if ((e = cudaMalloc(&d_hist, hist_n * 4)) != cudaSuccess) { bail(e, "cudaMalloc hist"); break; }
+            if ((e = cudaMemsetAsync(d_hist, 0, hist_n * 4)) != cudaSuccess) { bail(e, "memset hist"); break; }
+        }
+        if ((e = cudaMalloc(&d_cnt, FMC_N_COUNTERS * 8)) != cudaSuccess) { bail(e, "cudaMalloc counters"); break; }
+        if ((e = cudaMemsetAsync(d_cnt, 0, FMC_N_COUNTERS * 8)) != cudaSuccess) { bail(e, "memset counters"); break; }
+        if (stream_host && games) {
+            const size_t b = games * FMC_MAX_ITERS * FMC_N_SLOTS * 8;
+            if ((e = cudaMalloc(&d_stream, b)) != cudaSuccess) { bail(e, "cudaMalloc stream"); break; }
+            if ((e = cudaMemcpy(d_stream, stream_host, b, cudaMemcpyHostToDevice)) != cudaSuccess) { bail(e, "H2D stream"); break; }
+        }
+        if (trace_host && games) {
+            const size_t b = games * FMC_MAX_ITERS * FMC_TRACE_COLS * 8;
+            if ((e = cudaMalloc(&d_trace, b)) != cudaSuccess) { bail(e, "cudaMalloc trace"); break; }
+            if ((e = cudaMemsetAsync(d_trace, 0xFF, b)) != cudaSuccess) { bail(e, "memset trace"); break; }   // NaN fill
+        }
+        if (iters_host && games) { if ((e = cudaMalloc(&d_iters, games * 2)) != cudaSuccess) { bail(e, "cudaMalloc iters"); break; } }
+        fmc_sim_args g;
+        std::memset(&g, 0, sizeof(g));
+        g.seed = seed; g.n_matchups = (int)nm; g.scores_dev = d_scores; g.hist_dev = d_hist; g.counters_dev = d_cnt;
+        g.stream_dev = d_stream; g.trace_dev = d_trace; g.iters_dev = d_iters; g.stream = nullptr;
+        rc = fmc_simulate(c, &g);
+        if (rc) break;
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) { bail(e, "sim_kernel"); break; }
+        if (scores_host && games && (e = cudaMemcpy(scores_host, d_scores, games * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H scores"); break; }
+        if (hist_host && (e = cudaMemcpy(hist_host, d_hist, hist_n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H hist"); break; }
+        if (counters_host && (e = cudaMemcpy(counters_host, d_cnt, FMC_N_COUNTERS * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H counters"); break; }
+        if (trace_host && games && (e = cudaMemcpy(trace_host, d_trace, games * FMC_MAX_ITERS * FMC_TRACE_COLS * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H trace"); break; }
+        if (iters_host && games && (e = cudaMemcpy(iters_host, d_iters, games * 2, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H iters"); break; }
+    } while (0);
+    cudaFree(d_scores); cudaFree(d_hist); cudaFree(d_cnt); cudaFree(d_stream); cudaFree(d_trace); cudaFree(d_iters);
+    return rc;
+}
+
+extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, int64_t n, double *out_dev,
+                                int32_t tree_begin, int32_t tree_end, int32_t coach_col, void *stream) {
+    if (!c || id < 0 || id >= FMC_N_MODELS || !c->forest[id].loaded) return fail(FMC_ERR_INVALID, "fmc_tree_predict: model not loaded");
+    if (n < 0 || (n > 0 && (!rows_dev || !out_dev))) return fail(FMC_ERR_INVALID, "fmc_tree_predict: bad buffers");
+    if (n == 0) return FMC_OK;
+    CK(cudaSetDevice(c->device));
+    HostForest &f = c->forest[id];
+    prescale(f);
+    PackSpec s;
+    preset_predict(s);
+    s.active[0] = f.active[0]; s.active[1] = f.active[1];
+    if (id == FMC_PLAY_MODEL) { s.active[0] = coach_col; s.active[1] = -1; }
+    s.tree_begin = tree_begin; s.tree_end = tree_end;
+    PackedForest pf;
+    const std::string err = pack_forest(f, s, pf);
+    if (!err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(id) + ": " + err);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (pf.slots.size() > c->p_slots_cap) {
+        cudaFree(c->p_slots);
+        c->p_slots = nullptr; c->p_slots_cap = 0;
+        CK(cudaMalloc(&c->p_slots, pf.slots.size() * 8));
+        c->p_slots_cap = pf.slots.size();
+    }
+    if (pf.roots.size() > c->p_roots_cap) {
+        cudaFree(c->p_roots);
+        c->p_roots = nullptr; c->p_roots_cap = 0;
+        CK(cudaMalloc(&c->p_roots, pf.roots.size() * 4));
+        c->p_roots_cap = pf.roots.size();
+    }
+    CK(cudaStreamSynchronize(st));   // a previous launch may still read the scratch tables
+    CK(cudaMemcpy(c->p_slots, pf.slots.data(), pf.slots.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->p_roots, pf.roots.data(), pf.roots.size() * 4, cudaMemcpyHostToDevice));
+    PredictArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.rows = rows_dev; a.out = out_dev; a.n = n; a.slots = c->p_slots; a.roots = c->p_roots;
+    a.n_outputs = f.n_outputs; a.rounds_padded = pf.rounds_padded; a.max_depth = pf.max_depth; a.n_num = f.n_num;
+    a.zero_is_missing = (f.kind == FMC_KIND_XGB && f.zero_is_missing) ? 1 : 0;
+    for (int k = 0; k < 8; ++k) a.base[k] = f.base[k];
+    a.n_scaled = f.n_scaled;
+    for (int j = 0; j < f.n_scaled; ++j) { a.scaler_cols[j] = f.scaler_cols[j]; a.scaler_mean[j] = f.scaler_mean[j]; a.scaler_scale[j] = f.scaler_scale[j]; }
+    long long blocks = (n + kPredThreads - 1) / kPredThreads;
+    const long long cap = (long long)c->prop.multiProcessorCount * 8;
+    if (blocks > cap) blocks = cap;
+    if (f.kind == FMC_KIND_SKL) predict_kernel<true><<<(int)blocks, kPredThreads, 0, st>>>(a);
+    else predict_kernel<false><<<(int)blocks, kPredThreads, 0, st>>>(a);
+    CK(cudaGetLastError());
+    return FMC_OK;
+}
+
+extern "C" int fmc_tree_predict_host(fmc_ctx *c, int32_t id, const double *rows_host, int64_t n, double *out_host,
+                                     int32_t tree_begin, int32_t tree_end, int32_t coach_col) {
+    if (!c || id < 0 || id >= FMC_N_MODELS || !c->forest[id].loaded) return fail(FMC_ERR_INVALID, "fmc_tree_predict_host: model not loaded");
+    if (n <= 0) return FMC_OK;
+    CK(cudaSetDevice(c->device));
+    const int no = c->forest[id].n_outputs;
+    double *d_rows = nullptr, *d_out = nullptr;
+    CK(cudaMalloc(&d_rows, (size_t)n * kNumMax * 8));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)n * no * 8);
+    if (e != cudaSuccess) { cudaFree(d_rows); return fail(FMC_ERR_CUDA, std::string("cudaMalloc out: ") + cudaGetErrorString(e)); }
+    int rc = FMC_OK;
+    e = cudaMemcpy(d_rows, rows_host, (size_t)n * kNumMax * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        rc = fmc_tree_predict(c, id, d_rows, n, d_out, tree_begin, tree_end, coach_col, nullptr);
+        if (rc == FMC_OK) e = cudaDeviceSynchronize();
+        if (rc == FMC_OK && e == cudaSuccess) e = cudaMemcpy(out_host, d_out, (size_t)n * no * 8, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_rows); cudaFree(d_out);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(FMC_ERR_CUDA, std::string("fmc_tree_predict_host: ") + cudaGetErrorString(e));
+    return FMC_OK;
+}
+
+extern "C" int fmc_sync(fmc_ctx *c) {
+    if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    return FMC_OK;
+}
+
+// Host-only packing entry point: lets CPU tests inspect the specialised tables without a GPU.  It
+// performs no evaluation -- tests walk the returned slots themselves.
+//   mode 0 = simulation preset (timeouts + SP+ folded to `fold_value`), 1 = predict preset.
+// Returns the number of slots, or a negative status; fills up to the given capacities.
+extern "C" int64_t fmc_pack_forest_host(const fmc_forest_desc *d, int32_t mode, int32_t col0, int32_t col1,
+                                        const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
+                                        const double *scaler_mean, const double *scaler_scale, int32_t tree_begin,
+                                        int32_t tree_end, uint64_t *slots_out, int64_t slots_cap, uint32_t *roots_out,
+                                        int64_t roots_cap, int32_t *info_out /* rounds, rounds_padded, max_depth, n_outputs */) {
+    if (!d) return fail(FMC_ERR_INVALID, "fmc_pack_forest_host: desc is NULL");
+    HostForest f;
+    f.assign(*d);
+    prescale(f);
+    PackSpec s;
+    if (mode == 0) preset_sim(s); else preset_predict(s);
+    s.active[0] = col0; s.active[1] = col1;
+    if (fold_value17) for (int k = 0; k < kNumMax; ++k) s.fold_value[k] = fold_value17[k];
+    s.n_scaled = n_scaled;
+    for (int j = 0; j < n_scaled && j < 16; ++j) { s.scaler_cols[j] = scaler_cols[j]; s.scaler_mean[j] = scaler_mean[j]; s.scaler_scale[j] = scaler_scale[j]; }
+    s.tree_begin = tree_begin; s.tree_end = tree_end;
+    PackedForest pf;
+    const std::string err = pack_forest(f, s, pf);
+    if (!err.empty()) return fail(FMC_ERR_CAPACITY, err);
+    if (info_out) { info_out[0] = pf.rounds; info_out[1] = pf.rounds_padded; info_out[2] = pf.max_depth; info_out[3] = pf.n_outputs; }
+    if (slots_out && (int64_t)pf.slots.size() <= slots_cap) std::memcpy(slots_out, pf.slots.data(), pf.slots.size() * 8);
+    if (roots_out && (int64_t)pf.roots.size() <= roots_cap) std::memcpy(roots_out, pf.roots.data(), pf.roots.size() * 4);
+    return (int64_t)pf.slots.size();
+}

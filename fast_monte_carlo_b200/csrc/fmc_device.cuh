@@ -1,0 +1,182 @@
+// Device building blocks shared by the predict kernel and the persistent simulation kernel:
+// Philox4x32-10, the AS241 inverse normal, and the lock-step tree walker over packed 8-byte slots
+// (layout: fmc_pack.hpp).  Compiled with -fmad=false: float64 state arithmetic must round exactly
+// like CPython evaluates the reference's expressions (one IEEE operation at a time).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fmc {
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011).  Counter = (game lo, game hi, matchup,
+// iteration << 2 | block), key = seed.  One call yields the four 32-bit words of one block of the
+// 16-slot draw record.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ double u01(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
+
+// Wichura (1988), algorithm AS241 PPND16: inverse standard normal CDF, |error| < 1e-16 relative.
+__device__ __noinline__ double ppnd16(double p) {
+    const double q = p - 0.5;
+    double r, num, den;
+    if (fabs(q) <= 0.425) {
+        r = 0.180625 - q * q;
+        num = 2.5090809287301226727e+3;
+        num = num * r + 3.3430575583588128105e+4;
+        num = num * r + 6.7265770927008700853e+4;
+        num = num * r + 4.5921953931549871457e+4;
+        num = num * r + 1.3731693765509461125e+4;
+        num = num * r + 1.9715909503065514427e+3;
+        num = num * r + 1.3314166789178437745e+2;
+        num = num * r + 3.3871328727963666080e0;
+        den = 5.2264952788528545610e+3;
+        den = den * r + 2.8729085735721942674e+4;
+        den = den * r + 3.9307895800092710610e+4;
+        den = den * r + 2.1213794301586595867e+4;
+        den = den * r + 5.3941960214247511077e+3;
+        den = den * r + 6.8718700749205790830e+2;
+        den = den * r + 4.2313330701600911252e+1;
+        den = den * r + 1.0;
+        return q * num / den;
+    }
+    r = q < 0.0 ? p : 1.0 - p;
+    r = sqrt(-log(r));
+    if (r <= 5.0) {
+        r -= 1.6;
+        num = 7.74545014278341407640e-4;
+        num = num * r + 2.27238449892691845833e-2;
+        num = num * r + 2.41780725177450611770e-1;
+        num = num * r + 1.27045825245236838258e0;
+        num = num * r + 3.64784832476320460504e0;
+        num = num * r + 5.76949722146069140550e0;
+        num = num * r + 4.63033784615654529590e0;
+        num = num * r + 1.42343711074968357734e0;
+        den = 1.05075007164441684324e-9;
+        den = den * r + 5.47593808499534494600e-4;
+        den = den * r + 1.51986665636164571966e-2;
+        den = den * r + 1.48103976427480074590e-1;
+        den = den * r + 6.89767334985100004550e-1;
+        den = den * r + 1.67638483018380384940e0;
+        den = den * r + 2.05319162663775882187e0;
+        den = den * r + 1.0;
+    } else {
+        r -= 5.0;
+        num = 2.01033439929228813265e-7;
+        num = num * r + 2.71155556874348757815e-5;
+        num = num * r + 1.24266094738807843860e-3;
+        num = num * r + 2.65321895265761230930e-2;
+        num = num * r + 2.96560571828504891230e-1;
+        num = num * r + 1.78482653991729133580e0;
+        num = num * r + 5.46378491116411436990e0;
+        num = num * r + 6.65790464350110377720e0;
+        den = 2.04426310338993978564e-15;
+        den = den * r + 1.42151175831644588870e-7;
+        den = den * r + 1.84631831751005468180e-5;
+        den = den * r + 7.86869131145613259100e-4;
+        den = den * r + 1.48753612908506148525e-2;
+        den = den * r + 1.36929880922735805310e-1;
+        den = den * r + 5.99832206555887937690e-1;
+        den = den * r + 1.0;
+    }
+    const double v = num / den;
+    return q < 0.0 ? -v : v;
+}
+
+// float exp with a single rounding: double exp (<= 1 ulp of double) rounded once to float.
+__device__ __forceinline__ float expf_cr(float x) { return (float)exp((double)x); }
+
+// ---------------------------------------------------------------------------------------------
+// Tree walker.  One lane = one row; all 32 lanes of a warp walk the SAME tree at the same time
+// (different paths), so the slots a warp touches per level sit inside one small tree (at most
+// 2^level distinct 8-byte words) -- broadcast-friendly in shared memory and in L1.  Three trees
+// are in flight per lane for instruction-level parallelism.
+//
+// Table formats (fmc_pack.hpp):  SKL: hi32 = 0x7FF00000 | row << CB | child, leaf = float64 bits.
+//                                XGB: hi32 = 0x80000000 | row << 23 | child, leaf = float32 in lo32.
+// ---------------------------------------------------------------------------------------------
+template <bool SKL, int FEAT_BITS>
+struct Fmt {
+    static constexpr int CB = SKL ? 20 - FEAT_BITS : 23;
+    __device__ static __forceinline__ bool internal(uint32_t hi) {
+        return SKL ? ((int)hi >= 0x7FF00000) : ((int)hi < 0);
+    }
+    __device__ static __forceinline__ uint32_t row(uint32_t hi) {
+        return SKL ? ((hi >> CB) & ((1u << FEAT_BITS) - 1u)) : ((hi >> 23) & 0xFFu);
+    }
+    __device__ static __forceinline__ uint32_t child(uint32_t hi) { return hi & ((1u << CB) - 1u); }
+};
+
+template <bool GLOBAL>
+__device__ __forceinline__ uint2 load_slot(const uint2 *p) {
+    if (GLOBAL) return __ldg(p);
+    return *p;
+}
+
+template <bool SKL, int FEAT_BITS, bool GLOBAL>
+__device__ __forceinline__ void walk_step(uint2 &n, bool &act, const uint2 *__restrict__ slots,
+                                          const float *__restrict__ frow) {
+    using F = Fmt<SKL, FEAT_BITS>;
+    if (act) {
+        const uint32_t hi = n.y;
+        const float fv = frow[F::row(hi)];
+        const float thr = __uint_as_float(n.x);
+        const bool right = SKL ? !(fv <= thr) : !(fv < thr);
+        n = load_slot<GLOBAL>(slots + F::child(hi) + (right ? 1u : 0u));
+        act = F::internal(n.y);
+    }
+}
+
+// Sum one output of a packed forest over `rounds_padded` trees (multiple of 3), in tree order.
+// SKL: float64 accumulate of pre-scaled leaves; XGB: float32 accumulate (returned widened).
+template <bool SKL, int FEAT_BITS, bool GLOBAL, int MAX_DEPTH>
+__device__ __forceinline__ double walk_output(const uint2 *__restrict__ slots, const uint32_t *__restrict__ roots,
+                                              int rounds_padded, const float *__restrict__ frow, double base) {
+    using F = Fmt<SKL, FEAT_BITS>;
+    double acc64 = base;
+    float acc32 = (float)base;
+    for (int t = 0; t < rounds_padded; t += 3) {
+        uint2 n0 = load_slot<GLOBAL>(slots + (GLOBAL ? __ldg(roots + t) : roots[t]));
+        uint2 n1 = load_slot<GLOBAL>(slots + (GLOBAL ? __ldg(roots + t + 1) : roots[t + 1]));
+        uint2 n2 = load_slot<GLOBAL>(slots + (GLOBAL ? __ldg(roots + t + 2) : roots[t + 2]));
+        bool a0 = F::internal(n0.y), a1 = F::internal(n1.y), a2 = F::internal(n2.y);
+        if (MAX_DEPTH <= 4) {
+#pragma unroll
+            for (int d = 0; d < MAX_DEPTH; ++d) {
+                walk_step<SKL, FEAT_BITS, GLOBAL>(n0, a0, slots, frow);
+                walk_step<SKL, FEAT_BITS, GLOBAL>(n1, a1, slots, frow);
+                walk_step<SKL, FEAT_BITS, GLOBAL>(n2, a2, slots, frow);
+            }
+        } else {
+            while (__any_sync(0xFFFFFFFFu, a0 | a1 | a2)) {
+                walk_step<SKL, FEAT_BITS, GLOBAL>(n0, a0, slots, frow);
+                walk_step<SKL, FEAT_BITS, GLOBAL>(n1, a1, slots, frow);
+                walk_step<SKL, FEAT_BITS, GLOBAL>(n2, a2, slots, frow);
+            }
+        }
+        if (SKL) {
+            acc64 = __dadd_rn(acc64, __hiloint2double((int)n0.y, (int)n0.x));
+            acc64 = __dadd_rn(acc64, __hiloint2double((int)n1.y, (int)n1.x));
+            acc64 = __dadd_rn(acc64, __hiloint2double((int)n2.y, (int)n2.x));
+        } else {
+            acc32 = __fadd_rn(acc32, __uint_as_float(n0.x));
+            acc32 = __fadd_rn(acc32, __uint_as_float(n1.x));
+            acc32 = __fadd_rn(acc32, __uint_as_float(n2.x));
+        }
+    }
+    return SKL ? acc64 : (double)acc32;
+}
+
+}  // namespace fmc

@@ -1,0 +1,619 @@
+// Persistent play-by-play simulation kernel (one lane per simulated game).
+//
+// Restates, for the GPU, the reference's game engine:
+//   simulate_game FMC:1428-1464, handle_fourth FMC:1382-1421, simulate_play FMC:1026-1257,
+//   advance_down / change_possession / tick_clock FMC:932-968, pass_prob_v1 FMC:719-735,
+//   modifiers FMC:431-472, samplers FMC:817-852 (+ sim_helpers.py:32-38), special teams FMC:858-896.
+//
+// Structure (DESIGN.md "simulation kernel"): one CTA of 1024 lanes per SM, each lane owns one game
+// and keeps its whole state in registers.  A game is a little coroutine: it advances until it needs
+// a tree model (a "request": family x orientation), parks, and resumes when the value is there.
+// Per round the CTA
+//   A. advances every lane to its next request (state machine, Philox draws, special teams),
+//   B. compacts the requests per (family, orientation) with warp match + shared atomics and writes
+//      each request's feature row into shared memory at its compacted position,
+//   C. evaluates the requests: work items = (list, 32-request chunk, output) are handed to warps
+//      dynamically, heaviest families first; all 32 lanes of a warp walk the same trees,
+//   D. lanes read their results back and continue.
+// Finished games are replaced at once from a global per-matchup game counter, so lanes stay busy
+// until the matchup is exhausted (the warp-level compaction of finished games the north star asks
+// for is the same mechanism: a parked lane is either refilled or absent from every request list).
+#pragma once
+
+#include "fmc_device.cuh"
+#include "fmc_pack.hpp"
+
+namespace fmc {
+
+constexpr int kSimThreads = 1024;
+constexpr int kNumFam = 6;           // S1, S2, PQ, RQ, SQ, PM  (== model ids 0..5)
+constexpr int kNumKeys = kNumFam * 2;
+
+struct TableRef {
+    uint32_t slots_off;     // in 8-byte slots, into the global slot buffer
+    uint32_t roots_off;     // in uint32, into the global roots buffer
+    uint16_t rounds_padded;
+    uint8_t n_outputs;
+    uint8_t max_depth;
+    float base[5];          // xgb margin offsets (f32-exact) ...
+    double base64[3];       // ... or sklearn init constants
+};
+
+struct MatchupDev {
+    double bias[2], ymul[2], mz[2], tanh35[2];
+    unsigned long long game_begin, game_end, out_offset;
+    TableRef tbl[kNumFam][2];
+};
+
+struct SimKernelArgs {
+    const MatchupDev *matchups;
+    int n_matchups;
+    unsigned long long *next_game;     // [n_matchups] global work counters (start at game_begin)
+    const uint2 *slots;
+    const uint32_t *roots;
+    uint32_t seed_lo, seed_hi;
+    int policy, sampler, stage2_mode;
+    float play_temp;
+    double qy_noise;
+    double standin[3];
+    // play_model standardisation of the six varying numerics (rows 0..5): x = (x - mean) / scale
+    double pm_mean[6], pm_scale[6];
+    int pm_scaled[6];
+    uint32_t *scores;
+    uint32_t *hist;
+    unsigned long long *counters;
+    const double *stream;
+    double *trace;
+    uint16_t *iters;
+};
+
+enum Stage : int {
+    ST_NEED_GAME = 0, ST_ITER, ST_WAIT_PM, ST_WAIT_S1, ST_WAIT_S2, ST_WAIT_PQ, ST_WAIT_RQ, ST_WAIT_SQ, ST_IDLE
+};
+
+// slot ids of the 16-slot draw record
+enum { S_U_CALL = 0, S_U_COMP, S_Z_YARDS, S_U_EX, S_U_BOOST, S_U_FIN, S_U_S2, S_Z_INT,
+       S_U_GO, S_U_FG, S_Z_GROSS, S_Z_RET, S_U_TB, S_U_P1, S_U_WR, S_U_YQ };
+
+struct Lane {
+    unsigned long long game;   // game id inside the matchup
+    double dist, ytg;
+    int sec, down, offense, period, going, iter;
+    int score[2];
+    int stage;
+    int plays;                 // plays of the current game
+};
+
+// python semantics helpers (FMC:97 softclip = max(lo, min(hi, x)))
+__device__ __forceinline__ double pymax(double a, double b) { return (b > a) ? b : a; }
+__device__ __forceinline__ double pymin(double a, double b) { return (b < a) ? b : a; }
+__device__ __forceinline__ double softclip(double x, double lo, double hi) {
+    const double m = (x < hi) ? x : hi;
+    return (m > lo) ? m : lo;
+}
+
+struct Draws {
+    const SimKernelArgs &a;
+    const double *rec;        // injected record base for this game (or nullptr)
+    uint4 ctr;                // x,y = game; z = matchup; w = iter << 2 | block
+    uint32_t have;            // bit b: block b cached
+    uint4 w[4];
+    __device__ Draws(const SimKernelArgs &a_, const MatchupDev &M, int matchup, const Lane &L) : a(a_) {
+        rec = a.stream ? a.stream + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_N_SLOTS
+                       : nullptr;
+        ctr = make_uint4((uint32_t)L.game, (uint32_t)(L.game >> 32), (uint32_t)matchup, (uint32_t)L.iter << 2);
+        have = 0;
+    }
+    __device__ __forceinline__ uint32_t word(int slot) {
+        const int b = slot >> 2;
+        if (!((have >> b) & 1u)) {
+            uint4 c = ctr;
+            c.w |= (uint32_t)b;
+            w[b] = philox4x32_10(c, make_uint2(a.seed_lo, a.seed_hi));
+            have |= 1u << b;
+        }
+        const uint4 v = w[b];
+        const int j = slot & 3;
+        return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
+    }
+    __device__ __forceinline__ double u(int slot) { return rec ? rec[slot] : u01(word(slot)); }
+    __device__ __forceinline__ double z(int slot) { return rec ? rec[slot] : ppnd16(u01(word(slot))); }
+};
+
+// ---- state transitions -------------------------------------------------------------------------
+__device__ __forceinline__ void change_possession(Lane &L, bool has_spot, double spot) {   // FMC:943-953
+    L.offense ^= 1;
+    L.down = 1;
+    L.dist = 10.0;
+    L.going = 0;
+    L.ytg = has_spot ? spot : 100.0 - L.ytg;
+}
+__device__ __forceinline__ void advance_down(Lane &L, double gained) {                      // FMC:932-941
+    L.ytg = pymax(0.0, L.ytg - gained);
+    if (gained + 1e-6 >= L.dist) {
+        L.down = 1;
+        L.dist = 10.0;
+        L.ytg = pymax(0.0, L.ytg - 0.0);
+    } else {
+        L.down += 1;
+        L.dist -= gained;
+        if (L.down > 4) change_possession(L, false, 0.0);
+    }
+}
+__device__ __forceinline__ void tick_clock(Lane &L, int base) {                             // FMC:956-968
+    const int v = L.sec - base;
+    L.sec = v > 0 ? v : 0;
+    const int old = L.period;
+    L.period = L.sec > 0 ? 4 - ((L.sec - 1) / 900) : 4;
+    if (L.period != old && L.period == 3) change_possession(L, true, 75.0);
+}
+__device__ __forceinline__ double pass_prob_v1(int down, double distance, double ytg, int sec, int sd) {  // FMC:719-735
+    double base = 0.53;
+    if (down == 1) base += 0.02 + 0.010 * pymax(0.0, distance - 10.0) / 10.0;
+    if (down == 2) base += 0.12 + 0.020 * pymax(0.0, distance - 7.0) / 10.0;
+    if (down == 3) base += 0.28 + 0.030 * pymax(0.0, distance - 5.0) / 10.0;
+    if (down == 4) base += 0.45 + 0.035 * pymax(0.0, distance - 3.0) / 10.0;
+    if (ytg <= 10.0) base -= 0.05;
+    if (ytg <= 5.0) base -= 0.03;
+    const bool two_min = (sec % 1800) <= 120;
+    if (two_min && sd < 0) base += 0.22;
+    if (sec < 600 && sd < 0) base += 0.06;
+    return softclip(base, 0.10, 0.95);
+}
+__device__ __forceinline__ double explosive_prob(double mz, double ytg) {                   // FMC:467-472
+    double base = 0.03 + 0.05 * mz;
+    if (ytg > 60.0) base += 0.02;
+    if (ytg > 40.0) base += 0.01;
+    return softclip(base, 0.01, 0.12);
+}
+__device__ __forceinline__ double rz_finish_prob(double ytg, double tanh35, int down, bool pass) {  // FMC:444-457
+    double base = (pass ? 0.32 : 0.30) + 0.30 * (pymax(0.0, 7.0 - ytg) / 7.0);
+    int dl = 4 - down;
+    if (dl < 0) dl = 0;
+    base += (pass ? 0.03 : 0.04) * (double)dl;
+    const double tilt = (pass ? 0.08 : 0.07) * tanh35;
+    return pass ? softclip(base + tilt, 0.22, 0.68) : softclip(base + tilt, 0.20, 0.62);
+}
+__device__ __forceinline__ double field_goal_prob(double d) {                               // FMC:858-865
+    if (d < 30.0) return 0.96;
+    if (d < 40.0) return 0.92;
+    if (d < 50.0) return 0.78;
+    if (d <= 55.0) return 0.50;
+    return 0.25;
+}
+__device__ __forceinline__ double go_for_it_prob(double ytg, double dist, int sd, int sec) {  // FMC:1336-1378
+    if (sec < 300 && sd < 0) return (ytg > 38.0) ? 0.90 : 0.75;
+    double p = 0.0;
+    if (ytg > 80.0) { if (dist <= 1.0) p = 0.15; else if (dist <= 2.0) p = 0.05; }
+    else if (ytg > 65.0) { if (dist <= 1.0) p = 0.30; else if (dist <= 2.0) p = 0.15; }
+    else if (ytg > 50.0) { if (dist <= 1.0) p = 0.60; else if (dist <= 2.0) p = 0.40; else if (dist <= 3.0) p = 0.20; }
+    else if (ytg > 35.0) { if (dist <= 1.0) p = 0.85; else if (dist <= 2.0) p = 0.65; else if (dist <= 3.0) p = 0.40; else if (dist <= 4.0) p = 0.25; }
+    else if (ytg > 20.0) { if (dist <= 1.0) p = 0.75; else if (dist <= 2.0) p = 0.50; else if (dist <= 3.0) p = 0.30; }
+    else if (ytg > 10.0) { if (dist <= 1.0) p = 0.70; else if (dist <= 2.0) p = 0.45; }
+    else { if (dist <= 2.0) p = 0.85; else if (dist <= 4.0) p = 0.40; }
+    if (sec < 300 && sd > 0) p *= 0.85;
+    return softclip(p, 0.0, 1.0);
+}
+
+// yardage samplers FMC:817-852 / sim_helpers.py:32-38
+__device__ __forceinline__ double sample_yards(const SimKernelArgs &a, Draws &D, const double q[3], double sig_floor,
+                                               double lo, double hi) {
+    if (a.sampler == 0) {
+        const double sigma = pymax(sig_floor, (q[2] - q[0]) / 2.56);
+        const double y = q[1] + sigma * D.z(S_Z_YARDS);
+        return softclip(y, lo, hi);
+    }
+    const double u = D.u(S_U_YQ);
+    double y = (u < 0.5) ? q[0] + (q[1] - q[0]) * (u / 0.5) : q[1] + (q[2] - q[1]) * ((u - 0.5) / 0.5);
+    y = y + (0.0 + a.qy_noise * D.z(S_Z_YARDS));
+    const double m = (y < lo) ? lo : y;      // np.clip
+    return (m > hi) ? hi : m;
+}
+
+struct SimShared {
+    MatchupDev M;
+    int cur_matchup;
+    unsigned int cnt[2][kNumKeys];    // requests per key, double-buffered by round parity
+    unsigned int off[kNumKeys];       // first position of each key's list
+    unsigned int item_prefix[kNumKeys + 1];
+    unsigned int item_next;
+    unsigned long long stat[FMC_N_COUNTERS];
+};
+
+constexpr size_t kSimSharedBytes = ((sizeof(SimShared) + 15) / 16) * 16;
+constexpr size_t kSimFeatBytes = (size_t)kSimThreads * kSimStride * 4;   // 61,440: a multiple of 16
+
+// keys in processing order, heaviest family first (LPT-style dynamic scheduling):
+// PQ, RQ (1200 depth-3 trees x3 outputs), S2, PM, SQ, S1
+__device__ __constant__ int kKeyOrder[kNumKeys] = {4, 5, 6, 7, 2, 3, 10, 11, 8, 9, 0, 1};
+
+__device__ __forceinline__ int splits_of(int fam) { return fam == 0 ? 1 : (fam == 5 ? 5 : 3); }
+
+// Outcome of the not-complete branch (FMC:751-770 nudges + 3-way categorical FMC:1157).
+__device__ __forceinline__ int stage2_outcome(const double raw[3], double u2) {
+    double p_inc = pymax(0.0, raw[0]), p_int = pymax(0.0, raw[1]), p_sck = pymax(0.0, raw[2]);
+    p_sck *= 0.65;
+    p_int = p_int * 1.20 + 0.004;
+    double ssum = p_inc + p_int + p_sck;
+    if (ssum == 0.0) ssum = 1.0;
+    double b0 = p_inc / ssum, b1 = p_int / ssum, b2 = p_sck / ssum;
+    const double bs = (b0 + b1) + b2;
+    b0 = b0 / bs; b1 = b1 / bs; b2 = b2 / bs;
+    double d0 = b0, d1 = b0 + b1;
+    const double d2 = (b0 + b1) + b2;
+    d0 = d0 / d2; d1 = d1 / d2;
+    int o = (d0 <= u2 ? 1 : 0) + (d1 <= u2 ? 1 : 0);
+    return o > 2 ? 2 : o;
+}
+
+// Advance one lane until it posts a request (returns key = family * 2 + offense) or has nothing
+// left to do (returns -1).  `res` points at this lane's result record of the previous round.
+__device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, SimShared &sh, const double *res) {
+    const MatchupDev &M = sh.M;
+    const int matchup = sh.cur_matchup;
+    for (;;) {
+        if (L.stage == ST_IDLE) return -1;
+        if (L.stage == ST_NEED_GAME) {
+            const unsigned long long g = atomicAdd(&a.next_game[matchup], 1ULL);
+            if (g >= M.game_end) { L.stage = ST_IDLE; return -1; }
+            L.game = g;
+            L.offense = (int)(g & 1ULL);
+            L.sec = 3600; L.down = 1; L.dist = 10.0; L.ytg = 75.0; L.period = 1; L.going = 0;
+            L.score[0] = 0; L.score[1] = 0; L.iter = 0; L.plays = 0;
+            L.stage = ST_ITER;
+        }
+        if (L.stage == ST_ITER) {
+            if (L.sec <= 0) {
+                // game over: outputs (FMC:1456-1464, 1501-1503)
+                const size_t oi = (size_t)(M.out_offset + (L.game - M.game_begin));
+                if (a.scores) a.scores[oi] = (uint32_t)L.score[0] | ((uint32_t)L.score[1] << 16);
+                if (a.iters) a.iters[oi] = (uint16_t)L.iter;
+                if (a.hist) {
+                    const int ha = L.score[0] < FMC_HIST_BINS ? L.score[0] : FMC_HIST_BINS - 1;
+                    const int hb = L.score[1] < FMC_HIST_BINS ? L.score[1] : FMC_HIST_BINS - 1;
+                    if (L.score[0] >= FMC_HIST_BINS || L.score[1] >= FMC_HIST_BINS) atomicAdd(&sh.stat[FMC_C_HIST_OVERFLOW], 1ULL);
+                    atomicAdd(&a.hist[(((size_t)matchup * 2 + (size_t)(L.game & 1ULL)) * FMC_HIST_BINS + ha) * FMC_HIST_BINS + hb], 1u);
+                }
+                atomicAdd(&sh.stat[FMC_C_GAMES], 1ULL);
+                atomicAdd(&sh.stat[FMC_C_PLAYS], (unsigned long long)L.plays);
+                atomicAdd(&sh.stat[FMC_C_ITERS], (unsigned long long)L.iter);
+                L.stage = ST_NEED_GAME;
+                continue;
+            }
+            if (a.trace && L.iter < FMC_MAX_ITERS) {
+                const int first = (int)(L.game & 1ULL);
+                double *t = a.trace + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_TRACE_COLS;
+                t[0] = (L.offense == first) ? 1.0 : 0.0; t[1] = (double)L.down; t[2] = (double)L.sec;
+                t[3] = (double)L.score[first]; t[4] = (double)L.score[first ^ 1]; t[5] = L.dist; t[6] = L.ytg;
+                t[7] = (double)L.going;
+            }
+            Draws D(a, M, matchup, L);
+            L.iter += 1;
+            const int team = L.offense;
+            const int sd = L.score[team] - L.score[team ^ 1];
+            if (L.down == 4) {                                   // handle_fourth FMC:1382-1421
+                const double ytg = L.ytg, dist = L.dist;
+                const double p_go = pymin(1.0, go_for_it_prob(ytg, dist, sd, L.sec) * 1.15);
+                if (D.u(S_U_GO) < p_go) {
+                    L.going = 1;
+                    atomicAdd(&sh.stat[FMC_C_GO], 1ULL);
+                } else if (ytg <= 38.0) {
+                    atomicAdd(&sh.stat[FMC_C_FGA], 1ULL);
+                    const bool good = D.u(S_U_FG) < field_goal_prob(ytg + 17.0);
+                    tick_clock(L, 12);
+                    if (good) { atomicAdd(&sh.stat[FMC_C_FG], 1ULL); L.score[team] += 3; change_possession(L, true, 75.0); }
+                    else change_possession(L, true, 100.0 - ytg);
+                    continue;
+                } else {
+                    atomicAdd(&sh.stat[FMC_C_PUNT], 1ULL);
+                    const double gross = pymax(30.0, 43.0 + 6.0 * D.z(S_Z_GROSS));      // attempt_punt FMC:876-896
+                    const double ret = pymax(0.0, 6.0 + 3.0 * D.z(S_Z_RET));
+                    double net = gross - ret;
+                    if (ytg <= 60.0) {
+                        const double tb = softclip((60.0 - ytg) / 60.0, 0.10, 0.55);
+                        if (D.u(S_U_TB) < tb) net = ytg - 25.0;
+                    }
+                    net = softclip(net, 15.0, ytg - 1.0);
+                    const int inet = (int)net;
+                    tick_clock(L, 16);
+                    change_possession(L, true, softclip(100.0 - (ytg - (double)inet), 1.0, 99.0));
+                    continue;
+                }
+            }
+            // simulate_play FMC:1026-...: the play call
+            L.plays += 1;
+            if (a.policy == 1) { L.stage = ST_WAIT_PM; return 5 * 2 + team; }
+            const double p_pass = pass_prob_v1(L.down, L.dist, L.ytg, L.sec, sd);
+            double a0 = 1.0 - p_pass, a1 = p_pass;
+            const double s = a0 + a1;
+            a0 = a0 / s; a1 = a1 / s;
+            const double c0 = a0 / (a0 + a1);
+            if (D.u(S_U_CALL) < c0) { atomicAdd(&sh.stat[FMC_C_RUN], 1ULL); L.stage = ST_WAIT_RQ; return 3 * 2 + team; }
+            atomicAdd(&sh.stat[FMC_C_PASS], 1ULL);
+            L.stage = ST_WAIT_S1;
+            return 0 * 2 + team;
+        }
+        // ---- resuming a parked play: the iteration counter already points past this iteration
+        Lane Lv = L;
+        Lv.iter = L.iter - 1;
+        Draws D(a, M, matchup, Lv);
+        const int team = L.offense;
+        const int sd = L.score[team] - L.score[team ^ 1];
+        const double mz = M.mz[team];
+        const double ytg0 = L.ytg;
+        if (L.stage == ST_WAIT_PM) {
+            // FMC:420-425: float32 softmax of margins / T, P(pass) clipped to [.02, .98]
+            const float *m = reinterpret_cast<const float *>(res);
+            float zv[5], zmax = 0.f, sum = 0.f, e1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { zv[k] = m[k] / a.play_temp; if (k == 0 || zv[k] > zmax) zmax = zv[k]; }
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { const float e = expf_cr(zv[k] - zmax); sum += e; if (k == 1) e1 = e; }
+            const double p_pass = softclip((double)(e1 / sum), 0.02, 0.98);
+            double a0 = 1.0 - p_pass, a1 = p_pass;
+            const double s = a0 + a1;
+            a0 = a0 / s; a1 = a1 / s;
+            const double c0 = a0 / (a0 + a1);
+            if (D.u(S_U_CALL) < c0) { atomicAdd(&sh.stat[FMC_C_RUN], 1ULL); L.stage = ST_WAIT_RQ; return 3 * 2 + team; }
+            atomicAdd(&sh.stat[FMC_C_PASS], 1ULL);
+            L.stage = ST_WAIT_S1;
+            return 0 * 2 + team;
+        }
+        if (L.stage == ST_WAIT_S1) {
+            const float m1 = *reinterpret_cast<const float *>(res);
+            const double p1 = (double)(1.0f / (expf_cr(-m1) + 1.0f));                 // xgboost sigmoid, float32
+            const double p_complete = softclip(p1 + M.bias[team], 0.02, 0.98);        // FMC:1086-1087
+            if (D.u(S_U_COMP) < p_complete) { atomicAdd(&sh.stat[FMC_C_COMP], 1ULL); L.stage = ST_WAIT_PQ; return 2 * 2 + team; }
+            if (a.stage2_mode == 1) { L.stage = ST_WAIT_S2; return 1 * 2 + team; }
+        }
+        if (L.stage == ST_WAIT_S1 || L.stage == ST_WAIT_S2) {
+            double raw[3];
+            if (L.stage == ST_WAIT_S2) {
+                const float *m = reinterpret_cast<const float *>(res);           // xgboost Softmax: f32 exp, double sum
+                float wmax = m[0];
+                wmax = fmaxf(m[1], wmax); wmax = fmaxf(m[2], wmax);
+                float e[3];
+                double wsum = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { e[k] = expf_cr(m[k] - wmax); wsum += (double)e[k]; }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) raw[k] = (double)(e[k] / (float)wsum);
+            } else {
+                raw[0] = a.standin[0]; raw[1] = a.standin[1]; raw[2] = a.standin[2];
+            }
+            const int outcome = stage2_outcome(raw, D.u(S_U_S2));
+            if (outcome == 0) {                                   // incomplete FMC:1160-1168
+                atomicAdd(&sh.stat[FMC_C_INC], 1ULL);
+                L.down += 1; L.going = 0;
+                tick_clock(L, 10);
+                L.stage = ST_ITER;
+                continue;
+            }
+            if (outcome == 2) { atomicAdd(&sh.stat[FMC_C_SACK], 1ULL); L.stage = ST_WAIT_SQ; return 4 * 2 + team; }
+            atomicAdd(&sh.stat[FMC_C_INT], 1ULL);                 // intercepted FMC:1186-1199
+            const double ret = softclip(6.0 + 5.0 * D.z(S_Z_INT), 0.0, L.ytg);
+            const double spot = 100.0 - (L.ytg - ret);
+            L.going = 0;
+            change_possession(L, true, spot);
+            tick_clock(L, 12);
+            L.stage = ST_ITER;
+            continue;
+        }
+        const double q[3] = {res[0], res[1], res[2]};
+        if (L.stage == ST_WAIT_PQ) {                              // completed pass FMC:1089-1152
+            double yards = sample_yards(a, D, q, 0.4, 0.0, L.ytg) * M.ymul[team];
+            if (ytg0 > 25.0 && D.u(S_U_EX) < 0.60 * explosive_prob(mz, ytg0)) {
+                const double ub = 0.35 + (0.95 - 0.35) * D.u(S_U_BOOST);
+                yards *= 1.0 + ub * (1.0 + 0.7 * mz);
+                yards = pymin(yards, ytg0);
+            }
+            if (ytg0 <= 12.0 && L.down <= 3 && D.u(S_U_FIN) < rz_finish_prob(ytg0, M.tanh35[team], L.down, true)) yards = ytg0;
+            if (yards + 1e-9 >= L.ytg) {
+                atomicAdd(&sh.stat[FMC_C_TD], 1ULL);
+                L.score[team] += 7; L.going = 0;
+                tick_clock(L, 20);
+                change_possession(L, true, 75.0);
+            } else {
+                L.going = 0;
+                advance_down(L, yards);
+                tick_clock(L, 26);
+            }
+        } else if (L.stage == ST_WAIT_RQ) {                       // run FMC:1201-1257
+            double yards = sample_yards(a, D, q, 0.35, -4.0, L.ytg) * M.ymul[team];
+            if (ytg0 > 25.0 && D.u(S_U_EX) < 0.5 * explosive_prob(mz, ytg0)) {
+                const double ub = 0.2 + (0.5 - 0.2) * D.u(S_U_BOOST);
+                yards *= 1.0 + ub * (1.0 + 0.6 * mz);
+                yards = pymin(yards, ytg0);
+            }
+            if (ytg0 <= 9.0 && L.down <= 3) {
+                if (D.u(S_U_FIN) < rz_finish_prob(ytg0, M.tanh35[team], L.down, false)) yards = ytg0;
+            }
+            if (yards + 1e-9 >= ytg0) {
+                atomicAdd(&sh.stat[FMC_C_TD], 1ULL);
+                L.score[team] += 7;
+                tick_clock(L, 28);
+                change_possession(L, true, 75.0);
+                L.going = 0;
+            } else {
+                advance_down(L, yards);
+                tick_clock(L, 28);
+                L.going = 0;
+            }
+        } else {                                                  // sack FMC:1170-1184
+            double loss = -sample_yards(a, D, q, 0.25, -20.0, 0.0);
+            loss = pymax(0.0, loss);
+            loss = pymin(loss, 100.0 - (100.0 - L.ytg));
+            L.ytg += loss; L.dist += loss; L.down += 1; L.going = 0;
+            tick_clock(L, 24);
+        }
+        L.stage = ST_ITER;
+    }
+}
+
+// Feature row of a request (FMC:996-1021 `_fill_row`, reduced to the columns that vary inside one
+// orientation).  Rows: 0 down 1 distance 2 yardsToGoal 3 is_red_zone 4 score_diff 5 seconds
+// 6 goal_to_go 7 fourth_and_short 8 fg_range 9 half 10 two_minute 11..13 "B" views of 1, 2, 4.
+__device__ __forceinline__ void write_features(float *row, const Lane &L, int fam, const SimKernelArgs &a) {
+    const int team = L.offense;
+    const int sd = L.score[team] - L.score[team ^ 1];
+    float v[6];
+    v[0] = (float)L.down; v[1] = (float)L.dist; v[2] = (float)L.ytg; v[3] = (L.ytg <= 20.0) ? 1.f : 0.f;
+    v[4] = (float)sd; v[5] = (float)L.sec;
+    if (fam == 5) {   // play_model.xgb: StandardScaler on everything but is_red_zone (dense rows, no missing)
+        const double raw[6] = {(double)L.down, L.dist, L.ytg, 0.0, (double)sd, (double)L.sec};
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (a.pm_scaled[k]) v[k] = (float)((raw[k] - a.pm_mean[k]) / a.pm_scale[k]);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) row[k] = v[k];
+        return;
+    }
+    const bool zm = fam <= 1;   // CSR-fed boosters: exact zero == missing
+    const float inf = __int_as_float(0x7f800000);
+    row[0] = v[0];
+    row[3] = v[3];
+    row[5] = v[5];
+    row[6] = (L.dist >= (L.ytg - 0.5)) ? 1.f : 0.f;
+    row[7] = (L.down == 4 && L.dist <= 2.0) ? 1.f : 0.f;
+    row[8] = (L.ytg <= 33.0) ? 1.f : 0.f;
+    row[9] = (L.sec > 1800) ? 1.f : 2.f;
+    row[10] = ((L.sec % 1800) <= 120) ? 1.f : 0.f;
+    if (zm) {
+        row[1] = v[1] == 0.f ? -inf : v[1]; row[11] = v[1] == 0.f ? inf : v[1];
+        row[2] = v[2] == 0.f ? -inf : v[2]; row[12] = v[2] == 0.f ? inf : v[2];
+        row[4] = v[4] == 0.f ? -inf : v[4]; row[13] = v[4] == 0.f ? inf : v[4];
+    } else {
+        row[1] = v[1]; row[2] = v[2]; row[4] = v[4];
+    }
+}
+
+template <bool GLOBAL>
+__device__ __forceinline__ double eval_output(int fam, const TableRef &T, int out, const uint2 *slots_base,
+                                              const uint32_t *roots_base, const float *frow) {
+    const uint2 *slots = slots_base + T.slots_off;
+    const uint32_t *roots = roots_base + T.roots_off + (size_t)out * T.rounds_padded;
+    if (fam >= 2 && fam <= 4) {
+        if (T.max_depth <= 3) return walk_output<true, 4, GLOBAL, 3>(slots, roots, T.rounds_padded, frow, T.base64[out]);
+        return walk_output<true, 4, GLOBAL, 99>(slots, roots, T.rounds_padded, frow, T.base64[out]);
+    }
+    return walk_output<false, 4, GLOBAL, 99>(slots, roots, T.rounds_padded, frow, (double)T.base[out]);
+}
+
+__global__ void __launch_bounds__(kSimThreads, 1) sim_kernel(const SimKernelArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SimShared &sh = *reinterpret_cast<SimShared *>(smem_raw);
+    float *feats = reinterpret_cast<float *>(smem_raw + kSimSharedBytes);
+    double *results = reinterpret_cast<double *>(smem_raw + kSimSharedBytes + kSimFeatBytes);
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    if (tid < FMC_N_COUNTERS) sh.stat[tid] = 0ULL;
+    if (tid < kNumKeys) { sh.cnt[0][tid] = 0; sh.cnt[1][tid] = 0; }
+    if (tid == 0) sh.cur_matchup = -1;
+    __syncthreads();
+
+    Lane L;
+    L.stage = ST_IDLE;
+    unsigned long long rounds = 0, requests = 0;
+
+    for (int visit = 0;; ++visit) {
+        // ---- pick the next matchup that still has games; CTAs start at different matchups so that a
+        // slate is spread over the SMs and each CTA drains only when its matchup runs dry
+        if (tid == 0) {
+            int found = -1;
+            const int start = (sh.cur_matchup < 0) ? (int)(blockIdx.x % (unsigned)a.n_matchups) : sh.cur_matchup;
+            for (int j = 0; j < a.n_matchups; ++j) {
+                const int m = (start + j) % a.n_matchups;
+                if (*((volatile unsigned long long *)&a.next_game[m]) < a.matchups[m].game_end) { found = m; break; }
+            }
+            sh.cur_matchup = found;
+        }
+        __syncthreads();
+        const int m = sh.cur_matchup;
+        if (m < 0) break;
+        {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(a.matchups + m);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.M);
+            for (int i = tid; i < (int)(sizeof(MatchupDev) / 4); i += kSimThreads) dst[i] = src[i];
+        }
+        __syncthreads();
+        L.stage = ST_NEED_GAME;
+        int pos = 0;
+        int parity = 0;
+        for (;;) {
+            // ---- A: advance to the next request
+            const int key = advance_lane(L, a, sh, results + (size_t)pos * 3);
+            __syncwarp();
+            // ---- B: compaction
+            unsigned int rank = 0;
+            {
+                const unsigned int peers = __match_any_sync(0xFFFFFFFFu, key);
+                const int leader = __ffs(peers) - 1;
+                unsigned int base = 0;
+                if (key >= 0 && lane == leader) base = atomicAdd(&sh.cnt[parity][key], (unsigned int)__popc(peers));
+                base = __shfl_sync(0xFFFFFFFFu, base, leader);
+                rank = base + (unsigned int)__popc(peers & ((1u << lane) - 1u));
+            }
+            const int total = __syncthreads_count(key >= 0);
+            if (total == 0) break;
+            if (tid == 0) {
+                unsigned int o = 0, it = 0;
+                for (int j = 0; j < kNumKeys; ++j) {
+                    const int k = kKeyOrder[j];
+                    const unsigned int c = sh.cnt[parity][k];
+                    sh.off[k] = o;
+                    o += c;
+                    sh.item_prefix[j] = it;
+                    it += ((c + 31u) >> 5) * (unsigned int)splits_of(k >> 1);
+                }
+                sh.item_prefix[kNumKeys] = it;
+                sh.item_next = 0;
+            }
+            if (tid < kNumKeys) sh.cnt[parity ^ 1][tid] = 0;
+            __syncthreads();
+            if (key >= 0) {
+                pos = (int)(sh.off[key] + rank);
+                write_features(feats + (size_t)pos * kSimStride, L, key >> 1, a);
+            }
+            __syncthreads();
+            // ---- C: evaluate.  Work item = (key, chunk of 32 requests, output)
+            const unsigned int n_items = sh.item_prefix[kNumKeys];
+            for (;;) {
+                unsigned int it = 0;
+                if (lane == 0) it = atomicAdd(&sh.item_next, 1u);
+                it = __shfl_sync(0xFFFFFFFFu, it, 0);
+                if (it >= n_items) break;
+                int j = 0;
+                while (it >= sh.item_prefix[j + 1]) ++j;
+                const int k = kKeyOrder[j];
+                const int fam = k >> 1;
+                const unsigned int local = it - sh.item_prefix[j];
+                const int ns = splits_of(fam);
+                const unsigned int chunk = local / (unsigned int)ns;
+                const int out = (int)(local - chunk * (unsigned int)ns);
+                const unsigned int c = sh.cnt[parity][k];
+                const unsigned int idx = chunk * 32u + (unsigned int)lane;
+                const bool live = idx < c;
+                const unsigned int p = sh.off[k] + (live ? idx : chunk * 32u);
+                const double v = eval_output<true>(fam, sh.M.tbl[fam][k & 1], out, a.slots, a.roots, feats + (size_t)p * kSimStride);
+                if (live) {
+                    if (fam >= 2 && fam <= 4) results[(size_t)p * 3 + out] = v;
+                    else reinterpret_cast<float *>(results + (size_t)p * 3)[out] = (float)v;
+                }
+            }
+            __syncthreads();
+            parity ^= 1;
+            rounds += 1;
+            requests += (key >= 0) ? 1ULL : 0ULL;
+        }
+    }
+    // ---- flush counters
+    atomicAdd(&sh.stat[FMC_C_REQUESTS], requests);
+    if (tid == 0) sh.stat[FMC_C_ROUNDS] = rounds;
+    __syncthreads();
+    if (a.counters && tid < FMC_N_COUNTERS && sh.stat[tid]) atomicAdd(&a.counters[tid], sh.stat[tid]);
+}
+
+inline size_t sim_smem_bytes() { return kSimSharedBytes + kSimFeatBytes + (size_t)kSimThreads * 3 * 8; }
+
+}  // namespace fmc

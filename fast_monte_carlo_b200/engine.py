@@ -1,0 +1,99 @@
+"""Host-side engine: owns one GPU context, the compiled forests and the matchup table.
+
+Mirrors the reference's module-level state: the models loaded at import (FMC:641-668), the play
+policy switch (FMC:46, 326-328) and the per-process worker contexts (`_init_pool`, FMC:1306-1319),
+but as an object so that several engines (one per GPU / rank) can coexist.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import artifacts as art
+from . import native
+
+# FMC:55-61
+HEAD_COACH_MAP = {
+    "Kansas State": "Chris Klieman",
+    "Iowa State": "Matt Campbell",
+    "Kansas": "Lance Leipold",
+    "Fresno State": "Matt Entz",
+}
+
+SIM_MODELS = ("pass_stage1", "pass_stage2", "pass_yards", "run_yards", "sack_yards", "play_model")
+
+
+@dataclass
+class MatchupSpec:
+    """One team pair as the kernels see it."""
+    team_a: str
+    team_b: str
+    sp_a: Tuple[float, float, float]     # RATING, OFFENSE, DEFENSE  (lookup_sp_flex FMC:1625-1644)
+    sp_b: Tuple[float, float, float]
+    games: int                           # total games of this matchup in the run (all ranks)
+    game_begin: int = 0                  # this rank's slice [game_begin, game_end)
+    game_end: int = 0
+    out_offset: int = 0
+
+
+class Engine:
+    def __init__(self, models: Optional[art.ModelSet] = None, *, device: int = 0,
+                 policy: str = "heuristic", sampler: str = "normal", stage2: str = "auto",
+                 play_temp: float = 1.0, qy_noise: float = 0.5,
+                 stage2_standin: Sequence[float] = (0.78, 0.05, 0.17), player: str = "Unknown"):
+        self.models = models if models is not None else art.load_default_models()
+        self.ctx = native.Context(device)
+        self.player = player
+        for name in SIM_MODELS + ("run_fumble",):
+            if name in self.models:
+                f = self.models[name]
+                mid = art.MODEL_IDS[name]
+                self.ctx.load_forest(mid, f)
+                cols = [-1, -1]
+                if name != "play_model":
+                    for gi, g in enumerate(f.groups[:2]):
+                        cols[gi] = g.column_of(player)
+                self.ctx.set_active_columns(mid, cols[0], cols[1])
+        if stage2 == "auto":
+            stage2 = "booster" if "pass_stage2" in self.models else "standin"
+        if stage2 == "booster" and "pass_stage2" not in self.models:
+            raise ValueError("stage2='booster' but the model set has no pass_stage2 forest")
+        if policy == "play_model" and "play_model" not in self.models:
+            raise ValueError("policy='play_model' but the model set has no play_model forest")
+        self.policy, self.sampler, self.stage2 = policy, sampler, stage2
+        self.ctx.set_params(policy={"heuristic": 0, "play_model": 1}[policy],
+                            sampler={"normal": 0, "quantile_interp": 1}[sampler],
+                            stage2_mode={"standin": 0, "booster": 1}[stage2],
+                            play_temp=play_temp, qy_noise=qy_noise, stage2_standin=stage2_standin)
+        self.matchups: List[MatchupSpec] = []
+
+    # ------------------------------------------------------------------------------------------
+    def coach_col(self, team: str) -> int:
+        if "play_model" not in self.models:
+            return -1
+        g = self.models["play_model"].group("coach")
+        return g.column_of(HEAD_COACH_MAP.get(team)) if g is not None else -1
+
+    def set_matchups(self, specs: Iterable[MatchupSpec]) -> None:
+        self.matchups = list(specs)
+        self.ctx.set_matchups([
+            dict(sp=[list(m.sp_a), list(m.sp_b)], coach_col=(self.coach_col(m.team_a), self.coach_col(m.team_b)),
+                 game_begin=m.game_begin, game_end=m.game_end, out_offset=m.out_offset)
+            for m in self.matchups])
+
+    def simulate_host(self, seed: int, **kw) -> dict:
+        return self.ctx.simulate_host(seed=seed, **kw)
+
+    def predict(self, name: str, rows: np.ndarray, tree_begin: int = 0, tree_end: int = -1,
+                coach: Optional[str] = None) -> np.ndarray:
+        """Raw margins of one model on [n,17] numerics (hot columns = this engine's `player`)."""
+        f = self.models[name]
+        cc = -1
+        if name == "play_model" and coach is not None:
+            cc = f.group("coach").column_of(coach)
+        return self.ctx.tree_predict_host(art.MODEL_IDS[name], rows, f.n_outputs, tree_begin, tree_end, cc)
+
+    def close(self) -> None:
+        self.ctx.close()

@@ -1,0 +1,177 @@
+/*
+ * fmc.h -- C ABI of libfmc_b200.so: the B200-native engine behind the reference's
+ * fast_monte_carlo_cfb.py ("FMC") / sim_helpers.py hot path.
+ *
+ * The reference has no FFI of its own: its boundary is the Python API
+ *     simulate_upcoming_matchup(...)   FMC:1661-1715
+ *     simulate_matchup(...)            FMC:1467-1521
+ * plus the model objects it loads at import (FMC:641-668).  Every entry point below names the
+ * reference interface it stands in for; fast_monte_carlo_b200/native.py binds them with ctypes and
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions: plain C types only; every call returns 0 on success or a negative fmc_status and
+ * leaves a message retrievable with fmc_last_error() (thread-local).  One context per GPU, used
+ * from one host thread at a time.  Pointers named *_dev are device pointers owned by the caller
+ * (e.g. torch tensors); pointers named *_host are host memory.  Calls taking `stream` are
+ * asynchronous on that CUDA stream (a cudaStream_t passed as void*, NULL = default stream).
+ * There is no CPU fallback: without a usable sm_100 device fmc_create fails.
+ */
+#ifndef FMC_H
+#define FMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMC_ABI_VERSION 1
+
+typedef enum {
+    FMC_OK = 0,
+    FMC_ERR_INVALID = -1,   /* bad argument / model not loaded */
+    FMC_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+    FMC_ERR_NO_DEVICE = -3, /* no CUDA device / not an sm_100 part */
+    FMC_ERR_CAPACITY = -4,  /* a packed forest exceeds the table format limits */
+} fmc_status;
+
+/* model ids (the artifacts FMC loads at import, FMC:641-668, plus the two shipped-but-unused boosters) */
+enum {
+    FMC_PASS_STAGE1 = 0, /* pass_stage1_complete_vs_not.json   FMC:641, 739-747 */
+    FMC_PASS_STAGE2 = 1, /* pass_stage2_notcomplete.json        FMC:642, 751-770 (optional) */
+    FMC_PASS_YARDS = 2,  /* pass_yards_q{10,50,90}.joblib       FMC:658-660, 780-789 */
+    FMC_RUN_YARDS = 3,   /* run_yards_q{10,50,90}.joblib        FMC:662-664, 791-800 */
+    FMC_SACK_YARDS = 4,  /* sack_yards_q{10,50,90}.joblib       FMC:666-668, 802-812 */
+    FMC_PLAY_MODEL = 5,  /* play_model.xgb (+ scaler.pkl, coach_label_encoder.pkl) */
+    FMC_RUN_FUMBLE = 6,  /* run_fumble.json (evaluated only through fmc_tree_predict) */
+    FMC_N_MODELS = 7
+};
+
+enum { FMC_KIND_XGB = 0, FMC_KIND_SKL = 1 };
+
+/* One tree ensemble in structure-of-arrays form, as produced by the artifact compiler
+ * (fast_monte_carlo_b200/artifacts.py).  Arrays are host memory and are copied.
+ * Replaces: xgb.Booster().load_model(...) FMC:641-642 and joblib.load(...) FMC:651-668. */
+typedef struct {
+    int32_t kind;            /* FMC_KIND_XGB: f32 sums, left iff x < thr;  FMC_KIND_SKL: f64 sums, left iff f32(x) <= thr */
+    int32_t n_outputs;       /* classes (xgb) or quantiles (skl family), <= 8 */
+    int32_t n_features;      /* width of the model's input row */
+    int32_t num_base;        /* column of the first of the 17 (12 for play_model) numerics */
+    int32_t n_num;
+    int32_t zero_is_missing; /* CSR-fed booster: an exact 0 takes the node's default branch */
+    double base[8];          /* margin offset per output (xgb) / init constant (skl) */
+    double scale;            /* skl learning rate; 1 for xgb */
+    int32_t n_nodes;
+    int32_t n_trees;
+    const int32_t *feat;     /* [n_nodes] split column, -1 for leaves */
+    const float *thr;        /* [n_nodes] */
+    const int32_t *left;     /* [n_nodes] absolute child index, -1 for leaves */
+    const int32_t *right;    /* [n_nodes] */
+    const uint8_t *default_left; /* [n_nodes] */
+    const double *value;     /* [n_nodes] leaf value */
+    const int32_t *tree_root;/* [n_trees] */
+    const int32_t *tree_out; /* [n_trees] output each tree adds into */
+} fmc_forest_desc;
+
+/* Engine switches.  Defaults (all zero except the doubles noted) reproduce FMC as shipped. */
+typedef struct {
+    int32_t policy;       /* 0: pass_prob_v1 heuristic (FMC:719-735, the path taken when play_model.json is
+                                absent, FMC:326-328);  1: softmax(play_model.xgb margins / T)[pass] (FMC:420-425) */
+    int32_t sampler;      /* 0: Normal(q50, (q90-q10)/2.56) sampler FMC:817-852;
+                                1: sim_helpers.QuantileYards.sample (sim_helpers.py:32-38) */
+    int32_t stage2_mode;  /* 0: fixed raw probabilities `stage2_standin` (the booster is missing from the
+                                reference snapshot);  1: evaluate FMC_PASS_STAGE2 */
+    int32_t reserved;
+    double play_temp;     /* _PLAY_TEMP, FMC:50 (default 1.0) */
+    double qy_noise;      /* sim_helpers noise (default 0.5) */
+    double stage2_standin[3]; /* raw [incomplete, intercepted, sack] before the nudges of FMC:764-770 */
+} fmc_params;
+
+/* One matchup = two TeamContext objects (FMC:255-271) reduced to what the hot path reads. */
+typedef struct {
+    double sp[2][3];      /* [team A/B][RATING, OFFENSE, DEFENSE]   lookup_sp_flex FMC:1625-1644 */
+    int32_t coach_col[2]; /* play_model.xgb one-hot column of each team's head coach (HEAD_COACH_MAP FMC:55-61), -1 = none */
+    uint64_t game_begin;  /* this process simulates games [game_begin, game_end) of the matchup; */
+    uint64_t game_end;    /* game g: team (g & 1) receives the opening kickoff (pairs, FMC:1321-1328) */
+    uint64_t out_offset;  /* index of game_begin in the per-game output arrays */
+} fmc_matchup;
+
+#define FMC_HIST_BINS 128        /* joint (points A, points B) histogram is FMC_HIST_BINS^2 per orientation */
+#define FMC_N_COUNTERS 32
+/* counters[] layout (totals over the call) */
+enum {
+    FMC_C_GAMES = 0, FMC_C_PLAYS, FMC_C_ITERS, FMC_C_PASS, FMC_C_COMP, FMC_C_INC, FMC_C_INT, FMC_C_SACK,
+    FMC_C_RUN, FMC_C_TD, FMC_C_FGA, FMC_C_FG, FMC_C_PUNT, FMC_C_GO, FMC_C_HIST_OVERFLOW,
+    FMC_C_ROUNDS, FMC_C_REQUESTS
+};
+
+#define FMC_N_SLOTS 16           /* injected-draw record per (game, loop iteration); see DESIGN.md */
+#define FMC_MAX_ITERS 360
+#define FMC_TRACE_COLS 8
+
+typedef struct {
+    uint64_t seed;            /* Philox key; ignored when stream_dev != NULL */
+    int32_t n_matchups;       /* must equal the last fmc_set_matchups */
+    int32_t reserved;
+    uint32_t *scores_dev;     /* optional [sum of games]: (points A) | (points B) << 16 at out_offset + (g - game_begin) */
+    uint32_t *hist_dev;       /* optional [n_matchups][2][BINS][BINS], += 1 at [m][g&1][min(A,BINS-1)][min(B,BINS-1)] */
+    uint64_t *counters_dev;   /* optional [FMC_N_COUNTERS], accumulated with atomics */
+    const double *stream_dev; /* optional injected draws [games][FMC_MAX_ITERS][FMC_N_SLOTS] (test mode) */
+    double *trace_dev;        /* optional per-iteration states [games][FMC_MAX_ITERS][FMC_TRACE_COLS] (test mode) */
+    uint16_t *iters_dev;      /* optional [games] loop iterations of each game */
+    void *stream;             /* cudaStream_t */
+} fmc_sim_args;
+
+typedef struct fmc_ctx fmc_ctx;
+
+const char *fmc_last_error(void);
+int fmc_abi_version(void);
+
+/* Context on CUDA device `device`.  Fails with FMC_ERR_NO_DEVICE when there is no sm_100 GPU. */
+int fmc_create(int device, fmc_ctx **out);
+void fmc_destroy(fmc_ctx *ctx);
+/* SM count, shared memory per block, and the resident-forest capacity the kernels were sized for. */
+int fmc_device_info(fmc_ctx *ctx, int32_t *sm_count, int32_t *smem_per_block, char *name, int32_t name_len);
+
+/* Replaces Booster.load_model / joblib.load at FMC:641-668. */
+int fmc_load_forest(fmc_ctx *ctx, int32_t model_id, const fmc_forest_desc *desc);
+/* StandardScaler of play_model.xgb: x[cols[i]] = (x - mean[i]) / scale[i]  (scaler.pkl). */
+int fmc_set_scaler(fmc_ctx *ctx, int32_t model_id, int32_t n, const int32_t *cols, const double *mean, const double *scale);
+/* Hot one-hot columns (-1 = name is not a category) every row of `model_id` uses: the
+ * OneHotEncoder(handle_unknown='ignore') half of ColumnTransformer.transform, FMC:744, 756, 784-809.
+ * With the shipped usage tables every player is "Unknown" (FMC:246-249). */
+int fmc_set_active_columns(fmc_ctx *ctx, int32_t model_id, int32_t col0, int32_t col1);
+int fmc_set_params(fmc_ctx *ctx, const fmc_params *p);
+/* Replaces build_team_context_from_sp_flex x2 + _init_pool (FMC:1646-1659, 1306-1319): specialises
+ * every loaded forest on the per-orientation constants and uploads the packed node tables. */
+int fmc_set_matchups(fmc_ctx *ctx, int32_t n, const fmc_matchup *m);
+
+/* Replaces simulate_matchup's pool of _run_pair workers (FMC:1467-1521): plays every game of every
+ * matchup range to completion on the GPU.  Asynchronous on args->stream. */
+int fmc_simulate(fmc_ctx *ctx, const fmc_sim_args *args);
+
+/* Same, with HOST result buffers (any may be NULL): allocates device scratch, runs, copies back and
+ * synchronises.  This is the call the reference-facing Python API makes (end-to-end path). */
+int fmc_simulate_host(fmc_ctx *ctx, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
+                      uint64_t *counters_host, const double *stream_host, double *trace_host,
+                      uint16_t *iters_host);
+
+/* Raw margins of one model on n rows of the 17 numerics (play_model: first 12), NUM order of
+ * FMC:676-682, float64 row-major [n][17]; out float64 [n][n_outputs].  Trees [tree_begin, tree_end)
+ * (tree_end < 0: all) -- iteration_range of sim_helpers.py:22-23 / pass_outcome_infer.py:57,62.
+ * Replaces Booster.inplace_predict / Booster.predict(output_margin=True) / Pipeline.predict. */
+int fmc_tree_predict(fmc_ctx *ctx, int32_t model_id, const double *rows_dev, int64_t n, double *out_dev,
+                     int32_t tree_begin, int32_t tree_end, int32_t coach_col, void *stream);
+int fmc_tree_predict_host(fmc_ctx *ctx, int32_t model_id, const double *rows_host, int64_t n, double *out_host,
+                          int32_t tree_begin, int32_t tree_end, int32_t coach_col);
+
+/* Packed-table statistics of the last fmc_set_matchups (slots per family/orientation), for
+ * DESIGN.md / roofline accounting.  out[FMC_N_MODELS][2] = 8-byte slots of matchup `m`. */
+int fmc_packed_slots(fmc_ctx *ctx, int32_t m, int32_t *out);
+
+int fmc_sync(fmc_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMC_H */
