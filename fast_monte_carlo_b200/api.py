@@ -1,0 +1,159 @@
+"""Drop-in Python entry points of the reference (fast_monte_carlo_cfb.py:1467-1521, 1661-1722),
+executed by the B200 engine.
+
+    simulate_upcoming_matchup(teamA, teamB, *, year, week, sp_path, n, show_progress,
+                              collect_players, save_csv, processes)
+        -> (sims_df, players_df, summary, A, B, meta)
+    simulate_matchup(teamA_ctx, teamB_ctx, n, seed, show_progress, collect_players, players_csv,
+                     processes) -> (sims_df, players_df | None)
+
+Same argument meaning, return shapes, file names (`scores_<save_csv>`, `players_<save_csv>`) and
+error behaviour (ValueError for an unknown team / schema).  `n` counts PAIRS of games (A receives,
+then B receives); `processes` and `show_progress` are accepted and ignored (the GPU replaces the
+process pool).  Differences, all documented in DESIGN.md: a given `seed` makes the run
+reproducible game by game (counter-based Philox keyed by (seed, game id)) instead of re-seeding
+NumPy before every game; per-player box scores are not simulated
+(SURVEY 8f row 1), so `players_df` is an empty table with the reference's PLAYER_COLS.
+"""
+from __future__ import annotations
+
+import os
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import pandas as pd
+
+from . import outputs
+from .engine import Engine, MatchupSpec
+from .priors import (TeamContext, build_team_context_from_sp_flex, csv_base_from, load_sp_flex,
+                     lookup_sp_flex, packaged_priors_path)
+
+# FMC:1259-1264
+PLAYER_COLS = [
+    "sim", "start", "team", "opp", "player", "role",
+    "pass_att", "pass_comp", "pass_yds", "pass_td", "INT", "sacks",
+    "rush_att", "rush_yds", "rush_td",
+    "rec", "tgt", "rec_yds", "rec_td",
+]
+
+_ENGINES: Dict[tuple, Engine] = {}
+# joint score histogram [2, 128, 128] + event counters of the most recent simulate_matchup call
+LAST_RUN: Dict[str, object] = {}
+
+
+def get_engine(device: Optional[int] = None, **kw) -> Engine:
+    """Process-wide engine per (device, options) -- the analogue of the reference's module-level
+    model objects.  Raises when the CUDA library or a GPU is missing: there is no CPU path."""
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    key = (device,) + tuple(sorted(kw.items()))
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(device=device, **kw)
+    return _ENGINES[key]
+
+
+def _fresh_seed() -> int:
+    return int.from_bytes(os.urandom(8), "little")
+
+
+def simulate_matchup(teamA: TeamContext, teamB: TeamContext, n: int = 100, seed: Optional[int] = None,
+                     show_progress: bool = True, collect_players: bool = False,
+                     players_csv: Optional[str] = None, processes: Optional[int] = None,
+                     *, engine: Optional[Engine] = None) -> Tuple[pd.DataFrame, Optional[pd.DataFrame]]:
+    eng = engine if engine is not None else get_engine()
+    games = 2 * int(n)
+    if games <= 0:
+        sims_df = pd.DataFrame(columns=["team", "opp", "pts", "opp_pts"])
+    else:
+        eng.set_matchups([MatchupSpec(teamA.name, teamB.name, teamA.sp, teamB.sp, games, 0, games, 0)])
+        res = eng.simulate_host(_fresh_seed() if seed is None else int(seed), want_scores=True, want_hist=True)
+        sims_df = outputs.sims_frame(teamA.name, teamB.name, res["scores"])
+        sims_df.attrs["counters"] = dict(res["counters"])
+        LAST_RUN.clear()
+        LAST_RUN.update(hist=res["hist"][0], counters=dict(res["counters"]), teams=(teamA.name, teamB.name))
+    players_df = None
+    if collect_players:
+        players_df = pd.DataFrame(columns=PLAYER_COLS)
+        if players_csv:
+            if players_csv.lower().endswith(".parquet"):
+                players_df.to_parquet(players_csv, index=False)
+            else:
+                players_df.to_csv(players_csv, index=False)
+    return sims_df, players_df
+
+
+def simulate_upcoming_matchup(teamA: str, teamB: str, *, year: int = 2025, week: int = 1,
+                              sp_path: str = "Pregame_SPPlus2025_1.csv", n: int = 1000,
+                              show_progress: bool = True, collect_players: bool = True,
+                              save_csv: Optional[str] = None, processes: Optional[int] = None,
+                              seed: Optional[int] = None, engine: Optional[Engine] = None):
+    sp_df = load_sp_flex(sp_path)
+    A = build_team_context_from_sp_flex(teamA, year, week, sp_df)
+    B = build_team_context_from_sp_flex(teamB, year, week, sp_df)
+
+    t0 = time.perf_counter()
+    sims_df, players_df = simulate_matchup(A, B, n=n, seed=seed, show_progress=show_progress,
+                                           collect_players=collect_players, processes=processes, engine=engine)
+    t1 = time.perf_counter()
+    summary = outputs.summary_frame(sims_df)
+
+    write_time = 0.0
+    if save_csv:
+        tw = time.perf_counter()
+        try:
+            if save_csv.lower().endswith(".parquet"):
+                sims_df.to_parquet(f"scores_{save_csv}", index=False)
+                if players_df is not None:
+                    players_df.to_parquet(f"players_{save_csv}", index=False)
+            else:
+                sims_df.to_csv(f"scores_{save_csv}", index=False)
+                if players_df is not None:
+                    players_df.to_csv(f"players_{save_csv}", index=False)
+        except Exception:
+            sims_df.to_csv(f"scores_{save_csv}.csv", index=False)
+            if players_df is not None:
+                players_df.to_csv(f"players_{save_csv}.csv", index=False)
+        write_time = time.perf_counter() - tw
+
+    sim_time = t1 - t0
+    meta = {"sim_time_sec": sim_time, "io_time_sec": write_time, "total_time_sec": sim_time + write_time, "sims": n}
+    c = sims_df.attrs.get("counters")
+    if c:
+        meta["plays"] = c["plays"]
+        meta["games"] = c["games"]
+    return sims_df, players_df, summary, A, B, meta
+
+
+# ---------------------------------------------------------------------------------------------
+# slates (BASELINE configs 4 and 5): many matchups, games sharded over ranks, one histogram merge
+# ---------------------------------------------------------------------------------------------
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice of [0, total) owned by `rank`; slices tile the range exactly."""
+    return (total * rank) // world, (total * (rank + 1)) // world
+
+
+def slate_specs(pairs: Sequence[Tuple[str, str]], games_per_matchup: int, sp_df: pd.DataFrame,
+                rank: int = 0, world: int = 1) -> List[MatchupSpec]:
+    """Every rank simulates its contiguous game-id slice of every matchup.  Results do not depend
+    on `world`: the Philox key is (seed, matchup, game id)."""
+    specs = []
+    off = 0
+    for a, b in pairs:
+        spa, spb = lookup_sp_flex(a, sp_df), lookup_sp_flex(b, sp_df)
+        g0, g1 = shard_range(int(games_per_matchup), rank, world)
+        specs.append(MatchupSpec(a, b, spa, spb, int(games_per_matchup), g0, g1, off))
+        off += g1 - g0
+    return specs
+
+
+def merge_histograms(hist, counters=None):
+    """The single exchange step of the multi-GPU path: all-reduce(sum) of the integer histograms
+    (+ counters) over the default torch.distributed group (NCCL over NVLink on GPUs, gloo on CPU).
+    `hist` / `counters` are int64 torch tensors and are reduced in place.  No-op without a group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM)
+        if counters is not None:
+            dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    return hist, counters

@@ -1,0 +1,49 @@
+"""In-tree build of libfmc_b200.so (sm_100a only).   python -m fast_monte_carlo_b200.build"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "fmc_abi.cu")
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("fmc_abi.cu", "fmc_sim.cuh", "fmc_device.cuh", "fmc_pack.hpp")] + \
+       [os.path.join(os.path.dirname(HERE), "include", "fmc.h")]
+OUT = os.path.join(HERE, "libfmc_b200.so")
+
+NVCC_FLAGS = [
+    "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-O3", "-lineinfo",
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    # float64 game state must round like CPython evaluates the reference's expressions: no FMA contraction
+    "-fmad=false",
+]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found")
+    return p
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if force or needs_build():
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(r.stdout)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed building libfmc_b200.so")
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,151 @@
+"""Outputs the consumer (`edge_finder.py`) reads, computed either from the per-game score table or
+directly from the joint (points A, points B) histogram the kernels accumulate.
+
+`edge_finder.game_market_odds` / `moneyline_from_sims` (edge_finder.py:235-336) only use the joint
+distribution of (pts, opp_pts) per orientation, so every statistic they print is a function of the
+histogram; `scores_*.csv` can still be materialised for a literal drop-in.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import pandas as pd
+
+HIST_BINS = 128
+
+
+def sims_frame(team_a: str, team_b: str, scores: np.ndarray, first_game: int = 0) -> pd.DataFrame:
+    """Per-game table with the reference's columns and row order (FMC:1501-1509): game g has the
+    opening-kickoff receiver as `team`; even games are A-first, odd games B-first."""
+    n = scores.shape[0]
+    g = np.arange(first_game, first_game + n)
+    a_first = (g & 1) == 0
+    names = np.array([team_a, team_b], dtype=object)
+    return pd.DataFrame({
+        "team": names[np.where(a_first, 0, 1)],
+        "opp": names[np.where(a_first, 1, 0)],
+        "pts": np.where(a_first, scores[:, 0], scores[:, 1]).astype(np.int64),
+        "opp_pts": np.where(a_first, scores[:, 1], scores[:, 0]).astype(np.int64),
+    })
+
+
+def summary_frame(sims_df: pd.DataFrame) -> pd.DataFrame:
+    """groupby(team) mean/sd/win_rate exactly as FMC:1681-1687 (sample std, ties are not wins)."""
+    win = (sims_df["pts"].to_numpy() > sims_df["opp_pts"].to_numpy())
+    tmp = sims_df.assign(_win=win)
+    out = tmp.groupby("team").agg(
+        mean_pts=("pts", "mean"), sd_pts=("pts", "std"),
+        mean_opp=("opp_pts", "mean"), sd_opp=("opp_pts", "std"),
+        win_rate=("_win", "mean"))
+    return out
+
+
+def histogram_from_scores(scores: np.ndarray, first_game: int = 0) -> np.ndarray:
+    """[2, BINS, BINS] joint histogram (orientation = game parity) from a per-game (A, B) table."""
+    h = np.zeros((2, HIST_BINS, HIST_BINS), dtype=np.int64)
+    g = np.arange(first_game, first_game + scores.shape[0]) & 1
+    a = np.minimum(scores[:, 0], HIST_BINS - 1)
+    b = np.minimum(scores[:, 1], HIST_BINS - 1)
+    np.add.at(h, (g, a, b), 1)
+    return h
+
+
+def _oriented(hist2: np.ndarray, team_is_a: bool):
+    """(pts, opp_pts, weight) grids of the orientation in which `team` received the kickoff --
+    the only rows edge_finder.game_market_odds keeps (edge_finder.py:301-302)."""
+    o = 0 if team_is_a else 1
+    w = hist2[o].astype(np.float64)
+    a = np.arange(HIST_BINS)[:, None] + np.zeros((1, HIST_BINS), dtype=np.int64)
+    b = np.arange(HIST_BINS)[None, :] + np.zeros((HIST_BINS, 1), dtype=np.int64)
+    return (a, b, w) if team_is_a else (b, a, w)
+
+
+def _weighted_median(values: np.ndarray, weights: np.ndarray) -> float:
+    """np.median of the multiset (even counts average the two middle values)."""
+    order = np.argsort(values, kind="stable")
+    v = values[order]
+    w = weights[order]
+    keep = w > 0
+    v, w = v[keep], w[keep]
+    c = np.cumsum(w)
+    n = c[-1]
+    lo = v[np.searchsorted(c, (n + 1) // 2, side="left")]
+    hi = v[np.searchsorted(c, n // 2 + 1, side="left")]
+    return float(lo + hi) / 2.0 if n % 2 == 0 else float(lo)
+
+
+def prob_to_american(p: float) -> int:
+    """edge_finder._prob_to_american (edge_finder.py:70-75)."""
+    p = float(np.clip(p, 1e-6, 1 - 1e-6))
+    return int(round(-100 * p / (1 - p))) if p >= 0.5 else int(round(100 * (1 - p) / p))
+
+
+def moneyline_from_hist(hist2: np.ndarray, team: str, opp: str) -> Dict[str, Dict]:
+    """edge_finder.moneyline_from_sims (edge_finder.py:249-281) with `team` = A: p_team from the
+    A-first orientation, p_opp from the B-first one (they need not sum to 1)."""
+    a, b, w = _oriented(hist2, True)
+    p_team = float((w * (a > b)).sum() / w.sum())
+    b2, a2, w2 = _oriented(hist2, False)
+    p_opp = float((w2 * (b2 > a2)).sum() / w2.sum())
+    return {"team": {"name": team, "p_win": round(p_team, 6), "ml_fair": prob_to_american(p_team)},
+            "opp": {"name": opp, "p_win": round(p_opp, 6), "ml_fair": prob_to_american(p_opp)}}
+
+
+def game_market_odds_from_hist(hist2: np.ndarray, team: str, opp: str, *, team_is_a: bool = True,
+                               spread: Optional[float] = None, total: Optional[float] = None) -> Dict[str, Dict]:
+    """edge_finder.game_market_odds (edge_finder.py:283-336) from the histogram."""
+    pts, opp_pts, w = _oriented(hist2, team_is_a)
+    n = w.sum()
+    if n <= 0:
+        raise ValueError("No rows from the TEAM perspective found in scores file.")
+    out: Dict[str, Dict] = {}
+    if spread is not None:
+        margin = (pts - opp_pts).astype(np.float64)
+        tgt = -float(spread)
+        p_cover = float((w * (margin > tgt)).sum() / n)
+        p_not = float((w * (margin < tgt)).sum() / n)
+        p_push = float((w * np.isclose(margin, tgt, atol=1e-9)).sum() / n)
+        out["spread"] = {
+            "team": team, "opp": opp, "spread": float(spread), "samples": int(n),
+            "p_cover": round(p_cover, 6), "p_notcover": round(p_not, 6), "push_rate": round(p_push, 6),
+            "american_cover": prob_to_american(p_cover), "american_notcover": prob_to_american(p_not),
+            "mean_margin": float((w * margin).sum() / n),
+            "median_margin": _weighted_median(margin.ravel(), w.ravel()),
+        }
+    if total is not None:
+        totals = (pts + opp_pts).astype(np.float64)
+        T = float(total)
+        p_over = float((w * (totals > T)).sum() / n)
+        p_under = float((w * (totals < T)).sum() / n)
+        p_push = float((w * np.isclose(totals, T, atol=1e-9)).sum() / n)
+        out["total"] = {
+            "team": team, "opp": opp, "total": float(total), "samples": int(n),
+            "p_over": round(p_over, 6), "p_under": round(p_under, 6), "push_rate": round(p_push, 6),
+            "american_over": prob_to_american(p_over), "american_under": prob_to_american(p_under),
+            "mean_total": float((w * totals).sum() / n),
+            "median_total": _weighted_median(totals.ravel(), w.ravel()),
+        }
+    if not out:
+        raise ValueError("Provide at least one of spread= or total=.")
+    return out
+
+
+def summary_from_hist(hist2: np.ndarray, team_a: str, team_b: str) -> pd.DataFrame:
+    """The `summary` frame of simulate_upcoming_matchup (FMC:1681-1687) from the histogram: each
+    team's row covers the orientation in which it received the opening kickoff."""
+    rows = {}
+    for name, is_a in ((team_a, True), (team_b, False)):
+        pts, opp_pts, w = _oriented(hist2, is_a)
+        n = w.sum()
+        def mean_sd(x):
+            m = (w * x).sum() / n
+            var = (w * (x - m) ** 2).sum() / (n - 1) if n > 1 else np.nan
+            return float(m), float(np.sqrt(var))
+        mp, sp_ = mean_sd(pts.astype(np.float64))
+        mo, so = mean_sd(opp_pts.astype(np.float64))
+        rows[name] = dict(mean_pts=mp, sd_pts=sp_, mean_opp=mo, sd_opp=so,
+                          win_rate=float((w * (pts > opp_pts)).sum() / n))
+    df = pd.DataFrame.from_dict(rows, orient="index")
+    df.index.name = "team"
+    return df.sort_index()

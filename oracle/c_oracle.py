@@ -57,6 +57,14 @@ def lib():
         _lib = C.CDLL(LIB)
         _lib.fo_ppnd16.restype = C.c_double
         _lib.fo_ppnd16.argtypes = [C.c_double]
+        _lib.fo_pass_prob_v1.restype = C.c_double
+        _lib.fo_pass_prob_v1.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+        _lib.fo_go_for_it_prob.restype = C.c_double
+        _lib.fo_go_for_it_prob.argtypes = [C.c_double, C.c_double, C.c_int, C.c_int]
+        _lib.fo_field_goal_prob.restype = C.c_double
+        _lib.fo_field_goal_prob.argtypes = [C.c_double]
+        _lib.fo_modifiers.restype = None
+        _lib.fo_modifiers.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double)]
     return _lib
 
 
@@ -161,3 +169,10 @@ def make_stream(n_games: int, seed: int) -> np.ndarray:
     for j, sl in enumerate(NORMAL_SLOTS):
         s[:, :, sl] = z[:, :, j]
     return s
+
+
+def modifiers(off_offense: float, def_defense: float, ytg: float, down: int) -> dict:
+    out = (C.c_double * 6)()
+    lib().fo_modifiers(float(off_offense), float(def_defense), float(ytg), int(down), out)
+    return dict(matchup_bias=out[0], yardage_multiplier=out[1], mismatch_z=out[2], explosive_prob=out[3],
+                rz_finish_prob_pass=out[4], rz_finish_prob_run=out[5])

@@ -740,3 +740,20 @@ int fo_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ---- scalar hooks so tests can pin the closed-form helpers against tests/golden/ref_scalars.json ---- */
+double fo_pass_prob_v1(int down, double distance, double ytg, int sec, int sd) { return pass_prob_v1(down, distance, ytg, sec, sd); }
+double fo_go_for_it_prob(double ytg, double dist, int sd, int sec) { return go_for_it_prob(ytg, dist, sd, sec); }
+double fo_field_goal_prob(double d) { return field_goal_prob(d); }
+/* out = {matchup_bias, yardage_multiplier, mismatch_z, explosive_prob(ytg), rz_finish_prob_pass, rz_finish_prob_run} */
+void fo_modifiers(double off_offense, double def_defense, double ytg, int down, double *out) {
+    FoConfig c;
+    FoGame G;
+    memset(&c, 0, sizeof(c));
+    c.sp[0][1] = off_offense; c.sp[1][2] = def_defense;
+    game_constants(&G, &c);
+    out[0] = G.bias[0]; out[1] = G.ymul[0]; out[2] = G.mz[0];
+    out[3] = explosive_prob(G.mz[0], ytg);
+    out[4] = rz_finish_prob_pass(ytg, G.tanh35[0], down);
+    out[5] = rz_finish_prob_run(ytg, G.tanh35[0], down);
+}

@@ -1,0 +1,78 @@
+"""The multi-rank path on CPU: world_size-2 gloo.  Each rank plays its contiguous game slice of every
+matchup (here with the C oracle standing in for the GPU), histograms are merged with ONE all-reduce,
+and the result must equal the single-process histogram -- independent of the number of ranks."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from fast_monte_carlo_b200 import api, outputs
+
+
+def test_shard_ranges_tile():
+    for total in (0, 1, 7, 1000, 10_000_001):
+        for world in (1, 2, 3, 8):
+            edges = [api.shard_range(total, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == total
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, games, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fast_monte_carlo_b200 import artifacts as art, priors
+    from oracle import c_oracle as co
+    ms = art.load_default_models()
+    co.load_models(ms)
+    sp = priors.load_sp_flex(priors.packaged_priors_path())
+    pairs = [("Kansas State", "Iowa State"), ("UTSA", "Ohio State")]
+    specs = api.slate_specs(pairs, games, sp, rank, world)
+    hist = torch.zeros((len(pairs), 2, outputs.HIST_BINS, outputs.HIST_BINS), dtype=torch.int64)
+    counters = torch.zeros(4, dtype=torch.int64)
+    for m, s in enumerate(specs):
+        cfg = co.make_config(ms, s.sp_a, s.sp_b)
+        r = co.simulate(cfg, s.game_end - s.game_begin, game0=s.game_begin, matchup=m, seed=99, threads=1)
+        hist[m] += torch.from_numpy(outputs.histogram_from_scores(r["scores"], s.game_begin))
+        counters[0] += s.game_end - s.game_begin
+        counters[1] += r["counters"]["plays"]
+    api.merge_histograms(hist, counters)
+    if rank == 0:
+        q.put((hist.numpy(), counters.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_histogram_merge_equals_single_process():
+    games = 300
+    ctx = mp.get_context("spawn")
+    results = {}
+    for world in (1, 2):
+        q = ctx.SimpleQueue()
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, world, port, games, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        results[world] = q.get()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+    h1, c1 = results[1]
+    h2, c2 = results[2]
+    assert np.array_equal(h1, h2) and np.array_equal(c1, c2)
+    assert h1.sum() == 2 * games and c1[0] == 2 * games

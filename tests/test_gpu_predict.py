@@ -1,0 +1,100 @@
+"""GPU tree-ensemble evaluator vs the oracle, through the C-ABI (fmc_tree_predict_host).
+Tolerance: the north star asks for 1e-5 relative on raw margins; the kernels accumulate in the same
+precision and order as the oracle, so the tests demand bit equality."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from fast_monte_carlo_b200 import artifacts as art
+from oracle import tree_oracle as to
+from test_pack import _rows
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["pass_stage1", "pass_stage2", "pass_yards", "run_yards", "sack_yards", "run_fumble", "play_model"]
+
+
+def _oracle_margins(oracle, f, name, rows, cols, tb=0, te=-1):
+    x = to.play_model_features(f, rows[:, :12]) if f.scaler_cols is not None else rows
+    return oracle.predict(name, x, np.tile(np.array(cols, dtype=np.int32), (rows.shape[0], 1)), f.n_outputs, tb, te)
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_margins_bit_exact(engine, oracle, models_s2, name):
+    f = models_s2[name]
+    rows = _rows(20000, 11)          # includes exact-zero distance / ytg / score_diff / SP rating and down >= 5
+    cols = [g.column_of("Unknown") for g in f.groups if g.name != "coach"] + [-1, -1]
+    ref = _oracle_margins(oracle, f, name, rows, cols[:2])
+    got = engine.predict(name, rows[:, :f.n_num])
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)
+    rel = np.abs(got - ref) / np.maximum(np.abs(ref), 1e-12)
+    assert rel.max() <= 1e-5
+
+
+def test_sklearn_golden_through_gpu(engine, models_s2):
+    """The live sklearn pipelines' own predictions (all-"Unknown" rows of the golden file)."""
+    g = np.load(os.path.join(GOLDEN, "sklearn_quantiles.npz"))
+    for fam in ("pass_yards", "run_yards", "sack_yards"):
+        f = models_s2[fam]
+        cols = [gr.column_of("Unknown") for gr in f.groups] + [-1]
+        act = g[f"{fam}/active"]
+        sel = np.all(act == np.array(cols[:2]), axis=1)
+        assert sel.sum() > 100
+        got = engine.predict(fam, g["num"][sel])
+        assert np.array_equal(got, g[f"{fam}/pred"][sel])
+
+
+def test_named_players_and_tree_ranges(engine, oracle, models_s2):
+    """Real one-hot columns (fmc_set_active_columns) and iteration_range (sim_helpers.py:22-23)."""
+    p = json.load(open(os.path.join(GOLDEN, "xgb_provisional.json")))
+    f = models_s2["pass_stage1"]
+    mid = art.MODEL_IDS["pass_stage1"]
+    col = f.groups[0].column_of("Caleb Williams")
+    engine.ctx.set_active_columns(mid, col, -1)
+    try:
+        r0 = np.array([p["r0"]], dtype=float)
+        for v in p["stage1"][:2]:
+            got = engine.ctx.tree_predict_host(mid, r0, 1, 0, v["trees"])
+            assert abs(got[0, 0] - v["margin"]) < 2e-7
+        rows = _rows(3000, 12)
+        got = engine.ctx.tree_predict_host(mid, rows, 1, 0, 68)
+        assert np.array_equal(got, _oracle_margins(oracle, f, "pass_stage1", rows, (col, -1), 0, 68))
+    finally:
+        engine.ctx.set_active_columns(mid, -1, -1)
+    g = np.load(os.path.join(GOLDEN, "sklearn_quantiles.npz"))
+    fq = models_s2["pass_yards"]
+    act = g["pass_yards/active"]
+    combos, counts = np.unique(act, axis=0, return_counts=True)
+    pick = combos[np.argsort(-counts)[1]]          # most common non-"Unknown,Unknown" combination
+    sel = np.all(act == pick, axis=1)
+    engine.ctx.set_active_columns(art.MODEL_IDS["pass_yards"], int(pick[0]), int(pick[1]))
+    try:
+        got = engine.predict("pass_yards", g["num"][sel])
+        assert np.array_equal(got, g["pass_yards/pred"][sel])
+    finally:
+        engine.ctx.set_active_columns(art.MODEL_IDS["pass_yards"], fq.groups[0].column_of("Unknown"),
+                                      fq.groups[1].column_of("Unknown"))
+
+
+def test_play_model_coach_column(engine, oracle, models_s2):
+    f = models_s2["play_model"]
+    col = f.group("coach").column_of("Chris Klieman")
+    assert col >= 12
+    rows = _rows(2000, 13)
+    ref = _oracle_margins(oracle, f, "play_model", rows, (col, -1))
+    got = engine.predict("play_model", rows[:, :12], coach="Chris Klieman")
+    assert np.array_equal(got, ref)
+    assert not np.array_equal(got, engine.predict("play_model", rows[:, :12]))
+
+
+def test_empty_and_ragged_sizes(engine, oracle, models_s2):
+    f = models_s2["run_yards"]
+    cols = [f.groups[0].column_of("Unknown"), -1]
+    assert engine.predict("run_yards", np.zeros((0, 17))).shape == (0, 3)
+    for n in (1, 31, 33, 255, 257, 1000):
+        rows = _rows(n, n)
+        assert np.array_equal(engine.predict("run_yards", rows), _oracle_margins(oracle, f, "run_yards", rows, cols))

@@ -1,0 +1,89 @@
+"""The C++ specialiser/packer (fmc_pack.hpp) on CPU: the packed tables, walked in NumPy by the test,
+must reproduce the oracle's margins on the ORIGINAL trees bit for bit."""
+import numpy as np
+import pytest
+
+import packed_walk as pw
+from fast_monte_carlo_b200 import native
+from oracle import tree_oracle as to
+
+KSU, ISU, UTSA = (15.6, 35.7, 20.0), (11.0, 31.5, 20.6), (0.0, 28.0, 27.5)
+
+
+def _rows(n, seed):
+    rng = np.random.default_rng(seed)
+    down = rng.choice([1, 2, 3, 4, 5, 6], size=n)
+    dist = np.round(rng.uniform(0.3, 25, n), 2)
+    ytg = np.round(rng.uniform(0.5, 102, n), 2)
+    sd = rng.integers(-28, 29, n)
+    sd[::4] = 0
+    sec = rng.integers(1, 3601, n)
+    num = np.zeros((n, 17))
+    num[:, 0] = down; num[:, 1] = dist; num[:, 2] = ytg; num[:, 3] = ytg <= 20; num[:, 4] = sd; num[:, 5] = sec
+    num[:, 6] = rng.integers(0, 4, n); num[:, 7] = rng.integers(0, 4, n)
+    num[:, 8:12] = np.round(rng.normal(5, 15, (n, 4)), 1)
+    num[::7, 8] = 0.0
+    num[:, 12] = dist >= ytg - 0.5; num[:, 13] = (down == 4) & (dist <= 2); num[:, 14] = ytg <= 33
+    num[:, 15] = np.where(sec > 1800, 1, 2); num[:, 16] = (sec % 1800) <= 120
+    num[:3, 1] = 0.0
+    num[3:6, 2] = 0.0
+    return num
+
+
+def _setup(models_s2, name, player="Unknown"):
+    f = models_s2[name]
+    cols = [g.column_of(player) for g in f.groups if g.name != "coach"] + [-1, -1]
+    skl = f.kind == 1
+    zm = bool(f.zero_is_missing) and not skl
+    scaler = (f.scaler_cols, f.scaler_mean, f.scaler_scale) if f.scaler_cols is not None else None
+    return f, cols[:2], skl, zm, scaler
+
+
+@pytest.mark.parametrize("name", ["pass_stage1", "pass_stage2", "pass_yards", "run_yards", "sack_yards", "run_fumble", "play_model"])
+def test_predict_preset(models_s2, native_lib, name):
+    f, cols, skl, zm, scaler = _setup(models_s2, name)
+    num = _rows(96, 1)[:, :f.n_num]
+    slots, roots, meta = native.pack_forest_host(f, mode=1, cols=cols)
+    got = pw.walk(slots, roots, meta, pw.predict_rows(num, zm, scaler), skl, 5, f.base_margin)
+    x = to.play_model_features(f, num) if scaler else num
+    ref = to.raw_margin(f, x, np.tile(np.array(cols), (num.shape[0], 1)))
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("name", ["pass_stage1", "pass_stage2", "pass_yards", "run_yards", "sack_yards", "play_model"])
+@pytest.mark.parametrize("off,de", [(KSU, ISU), (UTSA, KSU), (ISU, UTSA)])
+def test_sim_preset_folds_orientation_constants(models_s2, native_lib, name, off, de):
+    f, cols, skl, zm, scaler = _setup(models_s2, name)
+    num = _rows(64, 2)[:, :f.n_num]
+    fv = np.zeros(17)
+    fv[6] = fv[7] = 3.0
+    fv[8], fv[9], fv[10], fv[11] = off[0], off[1], de[2], de[0]
+    num[:, 6:12] = fv[6:12]
+    slots, roots, meta = native.pack_forest_host(f, mode=0, cols=cols, fold_values=fv)
+    got = pw.walk(slots, roots, meta, pw.sim_rows(num, zm, scaler), skl, 4, f.base_margin)
+    x = to.play_model_features(f, num) if scaler else num
+    ref = to.raw_margin(f, x, np.tile(np.array(cols), (num.shape[0], 1)))
+    assert np.array_equal(got, ref)
+    # specialisation must shrink the table, never grow it
+    assert len(slots) <= f.n_nodes + 1
+
+
+def test_tree_range_and_named_player(models_s2, native_lib):
+    """iteration_range (best_iteration + 1 rounds, pass_outcome_infer.py:57) and a real passer column."""
+    f, _, skl, zm, scaler = _setup(models_s2, "pass_stage1")
+    col = f.groups[0].column_of("Caleb Williams")
+    assert col == 82
+    num = _rows(40, 3)
+    slots, roots, meta = native.pack_forest_host(f, mode=1, cols=(col, -1), tree_begin=0, tree_end=68)
+    assert meta["rounds"] == 68
+    got = pw.walk(slots, roots, meta, pw.predict_rows(num, zm, None), skl, 5, f.base_margin)
+    ref = to.raw_margin(f, num, np.tile(np.array([col, -1]), (40, 1)), 0, 68)
+    assert np.array_equal(got, ref)
+
+
+def test_padding_trees_are_exact_zero(models_s2, native_lib):
+    f = models_s2["pass_yards"]
+    slots, roots, meta = native.pack_forest_host(f, mode=1, cols=(491, 2877))
+    assert meta["rounds"] == 400 and meta["rounds_padded"] == 402
+    r = roots.reshape(3, 402)
+    assert np.all(r[:, 400:] == 0) and slots[0] == 0      # +0.0 leaf
