@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""Headline benchmark: simulated plays/s (and games/s) of the play-by-play Monte Carlo engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--games G]
+
+Workload (BASELINE.json configs[1]): Kansas State vs Iowa State from the 2025 week-1 SP+ priors,
+10,000,000 simulated games per GPU per step (weak scaling: rank r plays game ids
+[r*G, (r+1)*G) of the same matchup; the integer histograms are merged with ONE all-reduce per
+step).  Shipped model artifacts; the stage-2 booster the reference snapshot lacks is replaced by a
+synthetic booster of the trained shape (fast_monte_carlo_b200/synth.py) so that the stage-2 tree
+work is NOT skipped.  One step = one launch of the persistent simulation kernel over the batch.
+
+Prints ONE JSON line (rank 0).  `value` = plays/s with everything resident in HBM (CUDA events on
+the launch stream); `e2e` = the same metric through the C-ABI host-buffer call
+(fmc_simulate_host: forest specialisation + upload, kernel, per-game score table + histogram copied
+back) timed with the host clock; `cpu_baseline` = the C oracle (a port of the reference's
+algorithm) on this box's host cores; `--impl reference` times that CPU port as its own arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+KSU = ("Kansas State", (15.6, 35.7, 20.0))
+ISU = ("Iowa State", (11.0, 31.5, 20.6))
+SEED = 20251018
+METRIC = "simulated_plays_per_sec"
+UNIT = "plays/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=10_000_000, help="games per GPU per step")
+    ap.add_argument("--stage2", default="synthetic", choices=["synthetic", "standin"])
+    ap.add_argument("--cpu-games", type=int, default=0, help="games of the bounded CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def workload(args, n_gpus):
+    return {
+        "workload": "configs[1]: Kansas State vs Iowa State (PregameSPPlus2025_1 priors), "
+                    f"{args.games:,} simulated games per GPU per step, Philox seed {SEED}",
+        "games_per_gpu_per_step": args.games,
+        "total_games_per_step": args.games * n_gpus,
+        "play_call": "pass_prob_v1 heuristic (reference behaviour when play_model.json is absent)",
+        "stage2": ("synthetic booster of the trained shape (1086 trees, depth<=7)" if args.stage2 == "synthetic"
+                   else "fixed stand-in probabilities"),
+        "players": "Unknown (no usage tables shipped)",
+        "parallelism": f"games sharded over {n_gpus} GPU(s); one NCCL all-reduce of the histograms per step",
+        "l2": "flushed between timed steps (256 MiB write); node tables are meant to be cache-resident",
+    }
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        pw = [float(r[3]) for r in self.rows if len(r) >= 9 and r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+
+# ----------------------------------------------------------------------------------------------
+# algorithmic bytes: 8 B per internal-node visit + one leaf fetch (4 B xgb / 8 B sklearn)
+# per tree, visits = cover-weighted expected path length on the ORIGINAL (unpruned) forests
+# ----------------------------------------------------------------------------------------------
+def algorithmic_bytes_per_row(forest) -> float:
+    import numpy as np
+    leaf = forest.left < 0
+    cover = forest.cover if forest.cover is not None else np.ones(forest.n_nodes)
+    visits = 0.0
+    bounds = np.append(forest.tree_root, forest.n_nodes)
+    root_cover = cover[forest.tree_root]
+    # expected internal-node visits of a tree = sum over internal nodes of cover(node)/cover(root)
+    tree_of = np.repeat(np.arange(forest.n_trees), np.diff(bounds))
+    w = cover / np.maximum(root_cover[tree_of], 1e-30)
+    visits = float(w[~leaf].sum())
+    leaf_bytes = 8 if forest.kind == 1 else 4
+    return 8.0 * visits + leaf_bytes * forest.n_trees
+
+
+def step_algorithmic_bytes(models, counters, stage2_booster: bool) -> float:
+    b = {k: algorithmic_bytes_per_row(models[k]) for k in ("pass_stage1", "pass_yards", "run_yards", "sack_yards")}
+    total = counters["pass"] * b["pass_stage1"] + counters["comp"] * b["pass_yards"] + \
+        counters["run"] * b["run_yards"] + counters["sack"] * b["sack_yards"]
+    if stage2_booster:
+        total += (counters["pass"] - counters["comp"]) * algorithmic_bytes_per_row(models["pass_stage2"])
+    return float(total)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of sim_kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "sim_kernel_ncu_summary.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the C oracle (port of the reference algorithm) on the host cores
+# ----------------------------------------------------------------------------------------------
+def load_models(stage2: str):
+    from fast_monte_carlo_b200 import artifacts as art, synth
+    ms = art.load_default_models()
+    if stage2 == "synthetic":
+        ms = synth.with_synthetic_stage2(ms)
+    return ms
+
+
+def cpu_run(ms, games: int, stage2: str, game0: int = 0):
+    from oracle import c_oracle as co
+    co.load_models(ms)
+    cfg = co.make_config(ms, KSU[1], ISU[1], stage2="booster" if stage2 == "synthetic" else "standin")
+    threads = co.lib().fo_max_threads()
+    t = time.perf_counter()
+    r = co.simulate(cfg, games, game0=game0, seed=SEED, threads=threads)
+    dt = time.perf_counter() - t
+    return r, dt, threads
+
+
+def cpu_baseline(ms, args):
+    games = args.cpu_games
+    if games <= 0:
+        _, dt, _ = cpu_run(ms, 2000, args.stage2)
+        games = int(max(4000, min(400_000, 15.0 / (dt / 2000))))     # ~15 s of CPU work
+    r, dt, threads = cpu_run(ms, games, args.stage2)
+    return {"value": r["counters"]["plays"] / dt, "unit": UNIT, "games_per_sec": games / dt, "cores": threads,
+            "host_cpus": os.cpu_count(), "kind": "port",
+            "sample": f"{games} games of the same matchup/seed through oracle/fmc_oracle.c (OpenMP, {threads} threads), {dt:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ms = load_models(args.stage2)
+    _, dt0, threads = cpu_run(ms, 2000, args.stage2)
+    per_step = int(max(4000, min(400_000, 20.0 / (dt0 / 2000))))       # ~20 s per step
+    for w in range(args.warmup):
+        cpu_run(ms, max(2000, per_step // 10), args.stage2)
+    plays = 0
+    t_tot = 0.0
+    for s in range(args.steps):
+        r, dt, threads = cpu_run(ms, per_step, args.stage2, game0=s * per_step)
+        plays += r["counters"]["plays"]
+        t_tot += dt
+    value = plays / t_tot
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload(args, args.gpus),
+        "games_per_sec": args.steps * per_step / t_tot,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "host_cpus": os.cpu_count(), "kind": "port",
+                         "sample": f"{per_step} games per step (bounded sample of the {args.games:,}-game workload) "
+                                   f"through oracle/fmc_oracle.c, the CPU port of the reference algorithm; the "
+                                   f"reference itself cannot run (xgboost absent, stage-2 blob missing)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+
+    from fast_monte_carlo_b200 import native
+    from fast_monte_carlo_b200.engine import Engine, MatchupSpec
+    ms = load_models(args.stage2)
+    eng = Engine(ms, device=local, stage2="booster" if args.stage2 == "synthetic" else "standin")
+    G = args.games
+    g0, g1 = rank * G, (rank + 1) * G
+    spec = [MatchupSpec(KSU[0], ISU[0], KSU[1], ISU[1], G * world, g0, g1, 0)]
+    eng.set_matchups(spec)
+    eng.ctx.packed_slots(0)          # forces the specialise + upload now, outside the timed region
+
+    dev = torch.device("cuda", local)
+    scores = torch.empty(G, dtype=torch.int32, device=dev)
+    hist = torch.zeros((1, 2, native.HIST_BINS, native.HIST_BINS), dtype=torch.int32, device=dev)
+    hist64 = torch.zeros((1, 2, native.HIST_BINS, native.HIST_BINS), dtype=torch.int64, device=dev)
+    counters = torch.zeros(native.N_COUNTERS, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        hist.zero_()
+        counters.zero_()
+        eng.ctx.simulate_device(seed=SEED, scores=scores.data_ptr(), hist=hist.data_ptr(), counters=counters.data_ptr(),
+                                cuda_stream=stream.cuda_stream)
+        if world > 1:
+            hist64.copy_(hist)
+            dist.all_reduce(hist64)
+            dist.all_reduce(counters)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+        flush.zero_()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    plays_local = 0
+    step_counters = None
+    for i in range(args.steps):
+        ev[i][0].record()
+        step()
+        ev[i][1].record()
+        flush.zero_()
+    k1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    total_ms = k0.elapsed_time(k1)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    c = counters.cpu().numpy()
+    step_counters = {k: int(c[i]) for i, k in enumerate(native.COUNTER_NAMES)}   # all ranks (after all-reduce)
+    t = torch.tensor([total_ms, sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(t[0]), float(t[1])
+    plays_step = step_counters["plays"]
+    games_step = step_counters["games"]
+    assert games_step == G * world, (games_step, G, world)
+    value = plays_step * args.steps / (total_ms / 1e3)
+
+    # ---- end-to-end through the C-ABI host-buffer call --------------------------------------------------
+    e2e_plays, e2e_t = 0, 0.0
+    h2d = d2h = 0
+    slots = eng.ctx.packed_slots(0)
+    table_bytes = int(slots.sum()) * 8
+    for i in range(args.e2e_steps + 1):
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        eng.set_matchups(spec)                                   # forces re-specialisation + H2D of the tables
+        r = eng.simulate_host(SEED, want_scores=True, want_hist=True)
+        h = torch.from_numpy(r["hist"].astype(np.int64))
+        if world > 1:
+            hd = h.to(dev)
+            dist.all_reduce(hd)
+            h = hd.cpu()
+        dt = time.perf_counter() - t0
+        if i == 0:
+            continue                                             # warm-up
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        pp = torch.tensor([r["counters"]["plays"]], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(pp)
+        e2e_t += float(tt[0])
+        e2e_plays += int(pp[0])
+        h2d = table_bytes + 200 + 8
+        d2h = G * 4 + int(np.prod(r["hist"].shape)) * 4 + native.N_COUNTERS * 8
+    e2e_value = e2e_plays / e2e_t if e2e_t > 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        algo = step_algorithmic_bytes(ms, step_counters, args.stage2 == "synthetic") / world   # per launch (one GPU)
+        kern_s = (kernel_ms / args.steps) / 1e3
+        achieved = algo / kern_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload(args, n_gpus),
+            "games_per_sec": games_step * args.steps / (total_ms / 1e3),
+            "plays_per_game": plays_step / games_step,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "how": "fmc_simulate_host through ctypes: forest specialisation + table upload, kernel, "
+                           "per-game scores + histogram + counters copied to host; host wall clock, max over ranks"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "fmc::sim_kernel",
+                "kernel_ms_per_launch": kernel_ms / args.steps,
+                "algorithmic_bytes_per_launch": algo,
+                "note": "algorithmic bytes = SURVEY 8(d) per-row figures on the unpruned forests x requests per "
+                        "family; the node tables are L1/L2-resident by design, so this gather traffic never reaches "
+                        "HBM and frac can exceed 1 -- DRAM traffic proper is `traffic`",
+            },
+            "mix": {k: step_counters[k] for k in ("pass", "comp", "inc", "int", "sack", "run", "td", "fga", "fg", "punt", "go")},
+            "device": eng.ctx.device_name,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(ms, args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
