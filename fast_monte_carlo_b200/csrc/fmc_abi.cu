@@ -28,7 +28,7 @@ struct PredictArgs {
     double *out;            // [n][n_outputs]
     long long n;
     const uint2 *slots;
-    const uint32_t *roots;
+    const uint4 *roots;
     int n_outputs, rounds_padded, max_depth, n_num;
     int zero_is_missing;
     double base[8];
@@ -67,15 +67,15 @@ __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs
         }
         __syncthreads();
         const bool live = base + tid < a.n;
-        const float *frow = rows + (live ? tid : 0) * kPredStride;
+        const uint32_t frow = (uint32_t)__cvta_generic_to_shared(rows + (live ? tid : 0) * kPredStride);
         for (int o = 0; o < a.n_outputs; ++o) {
-            const uint32_t *roots = a.roots + (size_t)o * a.rounds_padded;
+            const uint4 *roots = a.roots + (size_t)o * (a.rounds_padded / 3);
             double v;
             if (SKL) {
-                v = (a.max_depth <= 3) ? walk_output<true, 5, true, 3>(a.slots, roots, a.rounds_padded, frow, a.base[o])
-                                       : walk_output<true, 5, true, 99>(a.slots, roots, a.rounds_padded, frow, a.base[o]);
+                v = (a.max_depth <= 3) ? walk_output<true, 3>(a.slots, roots, a.rounds_padded, frow, a.base[o])
+                                       : walk_output<true, 99>(a.slots, roots, a.rounds_padded, frow, a.base[o]);
             } else {
-                v = walk_output<false, 5, true, 99>(a.slots, roots, a.rounds_padded, frow, a.base[o]);
+                v = walk_output<false, 99>(a.slots, roots, a.rounds_padded, frow, a.base[o]);
             }
             if (live) a.out[(base + tid) * a.n_outputs + o] = v;
         }
@@ -95,14 +95,14 @@ struct fmc_ctx {
     bool tables_dirty = true;
     // device-side state of the last set_matchups
     uint2 *d_slots = nullptr;
-    uint32_t *d_roots = nullptr;
+    uint4 *d_roots = nullptr;
     MatchupDev *d_matchups = nullptr;
     unsigned long long *d_next = nullptr;
     std::vector<unsigned long long> h_next;
     std::vector<int32_t> packed_slots;   // [n_matchups][FMC_N_MODELS][2]
     // predict scratch
     uint2 *p_slots = nullptr;
-    uint32_t *p_roots = nullptr;
+    uint4 *p_roots = nullptr;
     size_t p_slots_cap = 0, p_roots_cap = 0;
 };
 
@@ -248,7 +248,7 @@ static int build_tables(fmc_ctx *c) {
                 TableRef &T = M.tbl[fam][off];
                 if (slots.size() + pf.slots.size() >= 0xFFFFFFFFull) return fail(FMC_ERR_CAPACITY, "slot buffer too large");
                 T.slots_off = (uint32_t)slots.size();
-                T.roots_off = (uint32_t)roots.size();
+                T.roots_off = (uint32_t)(roots.size() / 4);
                 T.rounds_padded = (uint16_t)pf.rounds_padded;
                 T.n_outputs = (uint8_t)pf.n_outputs;
                 T.max_depth = (uint8_t)pf.max_depth;

@@ -101,69 +101,80 @@ __device__ __forceinline__ float expf_cr(float x) { return (float)exp((double)x)
 // ---------------------------------------------------------------------------------------------
 // Tree walker.  One lane = one row; all 32 lanes of a warp walk the SAME tree at the same time
 // (different paths), so the slots a warp touches per level sit inside one small tree (at most
-// 2^level distinct 8-byte words) -- broadcast-friendly in shared memory and in L1.  Three trees
-// are in flight per lane for instruction-level parallelism.
+// 2^level distinct 8-byte words) -- broadcast-friendly in L1.  Three trees are in flight per lane
+// for instruction-level parallelism.
 //
-// Table formats (fmc_pack.hpp):  SKL: hi32 = 0x7FF00000 | row << CB | child, leaf = float64 bits.
-//                                XGB: hi32 = 0x80000000 | row << 23 | child, leaf = float32 in lo32.
+// Slot format (fmc_pack.hpp): internal iff (int)hi >= 0x50000000; hi = tag | (4*row) << 20 | child;
+// lo = float threshold.  Leaf: sklearn = the float64 itself, xgboost = float32 in lo.
+//
+// The feature row lives in shared memory and is addressed with a 32-bit shared-window address
+// (`frow`, from __cvta_generic_to_shared) so that the per-level address math is one integer add;
+// the table is addressed as base + 32-bit byte offset.
 // ---------------------------------------------------------------------------------------------
-template <bool SKL, int FEAT_BITS>
-struct Fmt {
-    static constexpr int CB = SKL ? 20 - FEAT_BITS : 23;
-    __device__ static __forceinline__ bool internal(uint32_t hi) {
-        return SKL ? ((int)hi >= 0x7FF00000) : ((int)hi < 0);
-    }
-    __device__ static __forceinline__ uint32_t row(uint32_t hi) {
-        return SKL ? ((hi >> CB) & ((1u << FEAT_BITS) - 1u)) : ((hi >> 23) & 0xFFu);
-    }
-    __device__ static __forceinline__ uint32_t child(uint32_t hi) { return hi & ((1u << CB) - 1u); }
-};
+constexpr uint32_t kTag = 0x50000000u;
 
-template <bool GLOBAL>
-__device__ __forceinline__ uint2 load_slot(const uint2 *p) {
-    if (GLOBAL) return __ldg(p);
-    return *p;
+__device__ __forceinline__ uint2 ldg_slot(const char *tbl, uint32_t slot) {
+    uint2 v;
+    asm("{\n\t.reg .u64 ad;\n\t"
+        "mad.wide.u32 ad, %2, 8, %3;\n\t"
+        "ld.global.nc.v2.u32 {%0, %1}, [ad];\n\t}"
+        : "=r"(v.x), "=r"(v.y) : "r"(slot), "l"(tbl));
+    return v;
 }
+__device__ __forceinline__ bool slot_internal(uint32_t hi) { return (int)hi >= (int)kTag; }
 
-template <bool SKL, int FEAT_BITS, bool GLOBAL>
-__device__ __forceinline__ void walk_step(uint2 &n, bool &act, const uint2 *__restrict__ slots,
-                                          const float *__restrict__ frow) {
-    using F = Fmt<SKL, FEAT_BITS>;
-    if (act) {
-        const uint32_t hi = n.y;
-        const float fv = frow[F::row(hi)];
-        const float thr = __uint_as_float(n.x);
-        const bool right = SKL ? !(fv <= thr) : !(fv < thr);
-        n = load_slot<GLOBAL>(slots + F::child(hi) + (right ? 1u : 0u));
-        act = F::internal(n.y);
+// One level of one tree for this lane; does nothing once the lane holds a leaf.
+//   frow_biased = shared-window address of the lane's feature row minus 0x500 (tag bits of hi >> 20)
+// Target per level: ISETP, LEA.HI (row address), LDS, FSET (0 / 0xFFFFFFFF), LOP3, IADD, IMAD.WIDE, LDG.
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+template <bool SKL>
+__device__ __forceinline__ void walk_step(uint2 &n, const char *__restrict__ tbl, uint32_t frow_biased) {
+    if (slot_internal(n.y)) {
+        const float fv = lds_f32(frow_biased + (n.y >> 20));
+        uint32_t m;   // 0xFFFFFFFF when the lane goes right
+        if (SKL) asm("set.gtu.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(fv), "f"(__uint_as_float(n.x)));   // !(fv <= thr)
+        else asm("set.geu.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(fv), "f"(__uint_as_float(n.x)));        // !(fv < thr)
+        n = ldg_slot(tbl, (n.y & 0xFFFFFu) - m);
     }
 }
 
 // Sum one output of a packed forest over `rounds_padded` trees (multiple of 3), in tree order.
 // SKL: float64 accumulate of pre-scaled leaves; XGB: float32 accumulate (returned widened).
-template <bool SKL, int FEAT_BITS, bool GLOBAL, int MAX_DEPTH>
-__device__ __forceinline__ double walk_output(const uint2 *__restrict__ slots, const uint32_t *__restrict__ roots,
-                                              int rounds_padded, const float *__restrict__ frow, double base) {
-    using F = Fmt<SKL, FEAT_BITS>;
+// `frow` is the 32-bit shared address of this lane's feature row; `roots` holds one uint4 per
+// three trees (root slots, fourth word unused) so a warp fetches them with one broadcast load.
+template <bool SKL, int MAX_DEPTH>
+__device__ __forceinline__ double walk_output(const uint2 *__restrict__ slots, const uint4 *__restrict__ roots,
+                                              int rounds_padded, uint32_t frow, double base) {
+    const char *tbl = reinterpret_cast<const char *>(slots);
+    uint32_t fb = frow - 0x500u;
+    asm volatile("" : "+r"(fb));          // keep the row address in a register (no re-materialisation)
     double acc64 = base;
     float acc32 = (float)base;
-    for (int t = 0; t < rounds_padded; t += 3) {
-        uint2 n0 = load_slot<GLOBAL>(slots + (GLOBAL ? __ldg(roots + t) : roots[t]));
-        uint2 n1 = load_slot<GLOBAL>(slots + (GLOBAL ? __ldg(roots + t + 1) : roots[t + 1]));
-        uint2 n2 = load_slot<GLOBAL>(slots + (GLOBAL ? __ldg(roots + t + 2) : roots[t + 2]));
-        bool a0 = F::internal(n0.y), a1 = F::internal(n1.y), a2 = F::internal(n2.y);
+    const int triples = rounds_padded / 3;
+#pragma unroll 1
+    for (int t = 0; t < triples; ++t) {
+        const uint4 r = __ldg(roots + t);
+        uint2 n0 = ldg_slot(tbl, r.x);
+        uint2 n1 = ldg_slot(tbl, r.y);
+        uint2 n2 = ldg_slot(tbl, r.z);
         if (MAX_DEPTH <= 4) {
 #pragma unroll
             for (int d = 0; d < MAX_DEPTH; ++d) {
-                walk_step<SKL, FEAT_BITS, GLOBAL>(n0, a0, slots, frow);
-                walk_step<SKL, FEAT_BITS, GLOBAL>(n1, a1, slots, frow);
-                walk_step<SKL, FEAT_BITS, GLOBAL>(n2, a2, slots, frow);
+                walk_step<SKL>(n0, tbl, fb);
+                walk_step<SKL>(n1, tbl, fb);
+                walk_step<SKL>(n2, tbl, fb);
             }
         } else {
-            while (__any_sync(0xFFFFFFFFu, a0 | a1 | a2)) {
-                walk_step<SKL, FEAT_BITS, GLOBAL>(n0, a0, slots, frow);
-                walk_step<SKL, FEAT_BITS, GLOBAL>(n1, a1, slots, frow);
-                walk_step<SKL, FEAT_BITS, GLOBAL>(n2, a2, slots, frow);
+            // xgboost leaves carry hi == 0, so OR-ing the three words keeps the test exact there
+            while (__any_sync(0xFFFFFFFFu, SKL ? (slot_internal(n0.y) | slot_internal(n1.y) | slot_internal(n2.y))
+                                               : slot_internal(n0.y | n1.y | n2.y))) {
+                walk_step<SKL>(n0, tbl, fb);
+                walk_step<SKL>(n1, tbl, fb);
+                walk_step<SKL>(n2, tbl, fb);
             }
         }
         if (SKL) {

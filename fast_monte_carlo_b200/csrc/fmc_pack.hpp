@@ -14,11 +14,11 @@
 //     exact zero is a MISSING value and takes the node's default branch.
 //  2. Re-layout.  Each surviving tree is written breadth-first into 8-byte slots with the two
 //     children of a node adjacent (left at c, right at c+1):
-//        internal slot : lo32 = float threshold, hi32 = tag | feature row | child slot
+//        internal slot : lo32 = float threshold, hi32 = 0x50000000 | (4 * feature row) << 20 | child slot
 //        leaf slot     : the value itself (sklearn: the float64; xgboost: float32 in lo32, hi32 = 0)
-//     sklearn tables use tag 0x7FF00000 (a float64 leaf can never carry an all-ones exponent), with
-//     FEAT_BITS row bits above (20 - FEAT_BITS) child bits; xgboost tables use tag 0x80000000,
-//     8 row bits and 23 child bits.
+//     A slot is internal iff (int32)hi32 >= 0x50000000: as the high word of a float64 that range
+//     means a positive value >= 2^257, which no leaf holds (checked at pack time).  20 child bits
+//     (1 M slots per table) and 8 bits of byte offset into the feature row (64 rows).
 //
 // "Feature rows" are the columns of the per-lane feature record the kernels build in shared
 // memory.  For CSR-fed boosters a non-flag numeric that may be exactly zero gets two rows: row A
@@ -39,6 +39,8 @@ namespace fmc {
 
 constexpr int kNumMax = 17;
 constexpr int kIlp = 3;  // trees walked together per lane; rounds are padded to a multiple
+constexpr int kChildBits = 20;
+constexpr uint32_t kInternalTag = 0x50000000u;
 
 struct PackSpec {
     int32_t active[2] = {-1, -1};   // hot one-hot columns
@@ -47,7 +49,6 @@ struct PackSpec {
     int8_t row[kNumMax];            // feature row of numeric k (A view)
     int8_t row_b[kNumMax];          // B view row, or -1
     uint8_t is_flag[kNumMax];       // 0/1 valued numeric
-    int feat_bits = 4;              // sklearn tables only
     int tree_begin = 0, tree_end = -1;
     // play_model: fold values are standardised first
     int n_scaled = 0;
@@ -86,7 +87,7 @@ struct HostForest {
 };
 
 struct PackedForest {
-    std::vector<uint32_t> roots;   // [n_outputs][rounds_padded] slot index
+    std::vector<uint32_t> roots;   // [n_outputs][rounds_padded / 3][4]: root slots of three trees + one unused word
     std::vector<uint64_t> slots;
     int n_outputs = 0;
     int rounds = 0;                // real boosting rounds per output in range
@@ -110,7 +111,6 @@ inline void preset_sim(PackSpec &s) {
     const uint8_t fl[kNumMax] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 1};
     std::memcpy(s.row, row, sizeof(row)); std::memcpy(s.row_b, rb, sizeof(rb)); std::memcpy(s.is_flag, fl, sizeof(fl));
     s.fold_mask = 0xFC0;  // numerics 6..11
-    s.feat_bits = 4;
 }
 inline void preset_predict(PackSpec &s) {
     const uint8_t fl[kNumMax] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 1};
@@ -121,7 +121,6 @@ inline void preset_predict(PackSpec &s) {
         s.row_b[k] = fl[k] ? -1 : (int8_t)nb++;
     }
     s.fold_mask = 0;
-    s.feat_bits = 5;
 }
 
 namespace detail {
@@ -223,12 +222,10 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
     out.rounds = (int)rounds;
     out.rounds_padded = (int)((rounds + kIlp - 1) / kIlp * kIlp);
     if (out.rounds_padded == 0) out.rounds_padded = kIlp;
-    out.roots.assign((size_t)f.n_outputs * out.rounds_padded, 0);
+    out.roots.assign((size_t)f.n_outputs * (out.rounds_padded / kIlp) * 4, 0);
 
-    const bool skl = f.kind == FMC_KIND_SKL;
-    const int child_bits = skl ? 20 - s.feat_bits : 23;
-    const uint32_t child_cap = 1u << child_bits;
-    const int feat_cap = skl ? (1 << s.feat_bits) : 256;
+    const uint32_t child_cap = 1u << kChildBits;
+    const int feat_cap = 64;
 
     out.slots.clear();
     out.slots.push_back(leaf_slot(f.kind, 0.0));  // slot 0: the zero leaf used by padding trees
@@ -251,6 +248,7 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
                 const detail::PNode &n = b.nodes[order[q]];
                 uint32_t me = slot_of[q];
                 if (n.leaf) {
+                    if (!(std::fabs(n.value) < 1e60)) return "leaf value out of range for the slot format";
                     out.slots[me] = leaf_slot(f.kind, n.value);
                     out.leaves++;
                     if (depth[q] > out.max_depth) out.max_depth = depth[q];
@@ -263,14 +261,13 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
                 out.slots.push_back(0);
                 uint32_t lo, hi;
                 std::memcpy(&lo, &n.thr, 4);
-                if (skl) hi = 0x7FF00000u | ((uint32_t)n.row << child_bits) | c;
-                else hi = 0x80000000u | ((uint32_t)n.row << 23) | c;
+                hi = kInternalTag | ((uint32_t)(n.row * 4) << kChildBits) | c;
                 out.slots[me] = ((uint64_t)hi << 32) | lo;
                 out.internal++;
                 order.push_back(n.l); slot_of.push_back(c); depth.push_back(depth[q] + 1);
                 order.push_back(n.r); slot_of.push_back(c + 1); depth.push_back(depth[q] + 1);
             }
-            out.roots[(size_t)k * out.rounds_padded + j] = root_slot;
+            out.roots[((size_t)k * (out.rounds_padded / kIlp) + j / kIlp) * 4 + j % kIlp] = root_slot;
         }
     }
     return "";

@@ -31,7 +31,7 @@ constexpr int kNumKeys = kNumFam * 2;
 
 struct TableRef {
     uint32_t slots_off;     // in 8-byte slots, into the global slot buffer
-    uint32_t roots_off;     // in uint32, into the global roots buffer
+    uint32_t roots_off;     // in uint4 (one per three trees), into the global roots buffer
     uint16_t rounds_padded;
     uint8_t n_outputs;
     uint8_t max_depth;
@@ -50,7 +50,7 @@ struct SimKernelArgs {
     int n_matchups;
     unsigned long long *next_game;     // [n_matchups] global work counters (start at game_begin)
     const uint2 *slots;
-    const uint32_t *roots;
+    const uint4 *roots;
     uint32_t seed_lo, seed_hi;
     int policy, sampler, stage2_mode;
     float play_temp;
@@ -487,16 +487,15 @@ __device__ __forceinline__ void write_features(float *row, const Lane &L, int fa
     }
 }
 
-template <bool GLOBAL>
 __device__ __forceinline__ double eval_output(int fam, const TableRef &T, int out, const uint2 *slots_base,
-                                              const uint32_t *roots_base, const float *frow) {
+                                              const uint4 *roots_base, uint32_t frow) {
     const uint2 *slots = slots_base + T.slots_off;
-    const uint32_t *roots = roots_base + T.roots_off + (size_t)out * T.rounds_padded;
+    const uint4 *roots = roots_base + T.roots_off + (size_t)out * (T.rounds_padded / 3);
     if (fam >= 2 && fam <= 4) {
-        if (T.max_depth <= 3) return walk_output<true, 4, GLOBAL, 3>(slots, roots, T.rounds_padded, frow, T.base64[out]);
-        return walk_output<true, 4, GLOBAL, 99>(slots, roots, T.rounds_padded, frow, T.base64[out]);
+        if (T.max_depth <= 3) return walk_output<true, 3>(slots, roots, T.rounds_padded, frow, T.base64[out]);
+        return walk_output<true, 99>(slots, roots, T.rounds_padded, frow, T.base64[out]);
     }
-    return walk_output<false, 4, GLOBAL, 99>(slots, roots, T.rounds_padded, frow, (double)T.base[out]);
+    return walk_output<false, 99>(slots, roots, T.rounds_padded, frow, (double)T.base[out]);
 }
 
 __global__ void __launch_bounds__(kSimThreads, 1) sim_kernel(const SimKernelArgs a) {
@@ -505,6 +504,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_kernel(const SimKernelArgs
     float *feats = reinterpret_cast<float *>(smem_raw + kSimSharedBytes);
     double *results = reinterpret_cast<double *>(smem_raw + kSimSharedBytes + kSimFeatBytes);
 
+    const uint32_t feats_saddr = (uint32_t)__cvta_generic_to_shared(feats);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     if (tid < FMC_N_COUNTERS) sh.stat[tid] = 0ULL;
@@ -595,7 +595,8 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_kernel(const SimKernelArgs
                 const unsigned int idx = chunk * 32u + (unsigned int)lane;
                 const bool live = idx < c;
                 const unsigned int p = sh.off[k] + (live ? idx : chunk * 32u);
-                const double v = eval_output<true>(fam, sh.M.tbl[fam][k & 1], out, a.slots, a.roots, feats + (size_t)p * kSimStride);
+                const double v = eval_output(fam, sh.M.tbl[fam][k & 1], out, a.slots, a.roots,
+                                             feats_saddr + p * (uint32_t)(kSimStride * 4));
                 if (live) {
                     if (fam >= 2 && fam <= 4) results[(size_t)p * 3 + out] = v;
                     else reinterpret_cast<float *>(results + (size_t)p * 3)[out] = (float)v;

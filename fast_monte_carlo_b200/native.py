@@ -163,7 +163,7 @@ def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begi
         ns = int(sc.shape[0])
     info = np.zeros(4, dtype=np.int32)
     cap_s = int(f.n_nodes) + 8
-    cap_r = int(f.n_trees) + 8 * int(f.n_outputs)
+    cap_r = 2 * int(f.n_trees) + 16 * int(f.n_outputs)
     slots = np.zeros(cap_s, dtype=np.uint64)
     roots = np.zeros(cap_r, dtype=np.uint32)
     n = L.fmc_pack_forest_host(
@@ -174,7 +174,7 @@ def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begi
     if n < 0:
         _check(int(n))
     meta = dict(rounds=int(info[0]), rounds_padded=int(info[1]), max_depth=int(info[2]), n_outputs=int(info[3]))
-    return slots[:n].copy(), roots[:meta["rounds_padded"] * meta["n_outputs"]].copy(), meta
+    return slots[:n].copy(), roots[:(meta["rounds_padded"] // 3) * 4 * meta["n_outputs"]].copy(), meta
 
 
 class Context:

@@ -55,14 +55,9 @@ def walk(slots, roots, meta, rows, skl, feat_bits, base):
     n = rows.shape[0]
     lo = (slots & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     hi = (slots >> np.uint64(32)).astype(np.uint32)
-    cb = 20 - feat_bits if skl else 23
-    if skl:
-        internal = hi.view(np.int32) >= 0x7FF00000
-        row_of = (hi >> np.uint32(cb)) & np.uint32((1 << feat_bits) - 1)
-    else:
-        internal = hi.view(np.int32) < 0
-        row_of = (hi >> np.uint32(23)) & np.uint32(0xFF)
-    child = hi & np.uint32((1 << cb) - 1)
+    internal = hi.view(np.int32) >= 0x50000000
+    row_of = ((hi >> np.uint32(20)) & np.uint32(0xFF)) // np.uint32(4)
+    child = hi & np.uint32((1 << 20) - 1)
     thr = lo.view(np.float32)
     leaf64 = slots.view(np.float64)
     leaf32 = lo.view(np.float32)
@@ -72,7 +67,7 @@ def walk(slots, roots, meta, rows, skl, feat_bits, base):
     for o in range(meta["n_outputs"]):
         acc = np.full(n, base[o], dtype=np.float64 if skl else np.float32)
         for t in range(rp):
-            idx = np.full(n, roots[o * rp + t], dtype=np.int64)
+            idx = np.full(n, roots[(o * (rp // 3) + t // 3) * 4 + t % 3], dtype=np.int64)
             live = internal[idx]
             while live.any():
                 i = idx[live]

@@ -85,5 +85,5 @@ def test_padding_trees_are_exact_zero(models_s2, native_lib):
     f = models_s2["pass_yards"]
     slots, roots, meta = native.pack_forest_host(f, mode=1, cols=(491, 2877))
     assert meta["rounds"] == 400 and meta["rounds_padded"] == 402
-    r = roots.reshape(3, 402)
-    assert np.all(r[:, 400:] == 0) and slots[0] == 0      # +0.0 leaf
+    r = roots.reshape(3, 134, 4)
+    assert np.all(r[:, 133, 1:] == 0) and np.all(r[:, :, 3] == 0) and slots[0] == 0      # +0.0 leaf
