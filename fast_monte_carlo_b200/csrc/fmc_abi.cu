@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs
         const bool live = base + tid < a.n;
         const uint32_t frow = (uint32_t)__cvta_generic_to_shared(rows + (live ? tid : 0) * kPredStride);
         for (int o = 0; o < a.n_outputs; ++o) {
-            const uint4 *roots = a.roots + (size_t)o * (a.rounds_padded / 3);
+            const uint4 *roots = a.roots + (size_t)o * (a.rounds_padded / 2);
             double v;
             if (SKL) {
                 v = (a.max_depth <= 3) ? walk_output<true, 3>(a.slots, roots, a.rounds_padded, frow, a.base[o])
@@ -489,7 +489,8 @@ extern "C" int64_t fmc_pack_forest_host(const fmc_forest_desc *d, int32_t mode, 
     PackedForest pf;
     const std::string err = pack_forest(f, s, pf);
     if (!err.empty()) return fail(FMC_ERR_CAPACITY, err);
-    if (info_out) { info_out[0] = pf.rounds; info_out[1] = pf.rounds_padded; info_out[2] = pf.max_depth; info_out[3] = pf.n_outputs; }
+    if (info_out) { info_out[0] = pf.rounds; info_out[1] = pf.rounds_padded; info_out[2] = pf.max_depth; info_out[3] = pf.n_outputs;
+                    info_out[4] = kIlp; info_out[5] = kRootWords; }
     if (slots_out && (int64_t)pf.slots.size() <= slots_cap) std::memcpy(slots_out, pf.slots.data(), pf.slots.size() * 8);
     if (roots_out && (int64_t)pf.roots.size() <= roots_cap) std::memcpy(roots_out, pf.roots.data(), pf.roots.size() * 4);
     return (int64_t)pf.slots.size();

@@ -7,6 +7,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "fmc_pack.hpp"   // kIlp, kRootWords, slot format constants
+
 namespace fmc {
 
 // ---------------------------------------------------------------------------------------------
@@ -142,49 +144,68 @@ __device__ __forceinline__ void walk_step(uint2 &n, const char *__restrict__ tbl
     }
 }
 
-// Sum one output of a packed forest over `rounds_padded` trees (multiple of 3), in tree order.
+// Sum one output of a packed forest over `rounds_padded` trees (a multiple of kIlp), in tree order.
 // SKL: float64 accumulate of pre-scaled leaves; XGB: float32 accumulate (returned widened).
-// `frow` is the 32-bit shared address of this lane's feature row; `roots` holds one uint4 per
-// three trees (root slots, fourth word unused) so a warp fetches them with one broadcast load.
+// `frow` is the 32-bit shared address of this lane's feature row.  `roots` is the inline copy of the
+// root slots, two trees per uint4, in tree order: every lane of the warp reads the same words (one
+// broadcast load per two trees) and the next group is fetched while the current one is walked.
 template <bool SKL, int MAX_DEPTH>
 __device__ __forceinline__ double walk_output(const uint2 *__restrict__ slots, const uint4 *__restrict__ roots,
                                               int rounds_padded, uint32_t frow, double base) {
+    constexpr int I = kIlp;
+    static_assert(I % 2 == 0, "kIlp must be even (two root slots per uint4)");
     const char *tbl = reinterpret_cast<const char *>(slots);
     uint32_t fb = frow - 0x500u;
     asm volatile("" : "+r"(fb));          // keep the row address in a register (no re-materialisation)
     double acc64 = base;
     float acc32 = (float)base;
-    const int triples = rounds_padded / 3;
+    const int groups = rounds_padded / I;
+    uint2 n[I];
+#pragma unroll
+    for (int q = 0; q < I / 2; ++q) {
+        const uint4 v = __ldg(roots + q);
+        n[2 * q] = make_uint2(v.x, v.y);
+        n[2 * q + 1] = make_uint2(v.z, v.w);
+    }
 #pragma unroll 1
-    for (int t = 0; t < triples; ++t) {
-        const uint4 r = __ldg(roots + t);
-        uint2 n0 = ldg_slot(tbl, r.x);
-        uint2 n1 = ldg_slot(tbl, r.y);
-        uint2 n2 = ldg_slot(tbl, r.z);
+    for (int t = 0; t < groups; ++t) {
+        uint2 nx[I];
+        const uint4 *next = roots + (size_t)(t + 1 < groups ? t + 1 : t) * (I / 2);
+#pragma unroll
+        for (int q = 0; q < I / 2; ++q) {
+            const uint4 v = __ldg(next + q);
+            nx[2 * q] = make_uint2(v.x, v.y);
+            nx[2 * q + 1] = make_uint2(v.z, v.w);
+        }
         if (MAX_DEPTH <= 4) {
 #pragma unroll
             for (int d = 0; d < MAX_DEPTH; ++d) {
-                walk_step<SKL>(n0, tbl, fb);
-                walk_step<SKL>(n1, tbl, fb);
-                walk_step<SKL>(n2, tbl, fb);
+#pragma unroll
+                for (int i = 0; i < I; ++i) walk_step<SKL>(n[i], tbl, fb);
             }
         } else {
-            // xgboost leaves carry hi == 0, so OR-ing the three words keeps the test exact there
-            while (__any_sync(0xFFFFFFFFu, SKL ? (slot_internal(n0.y) | slot_internal(n1.y) | slot_internal(n2.y))
-                                               : slot_internal(n0.y | n1.y | n2.y))) {
-                walk_step<SKL>(n0, tbl, fb);
-                walk_step<SKL>(n1, tbl, fb);
-                walk_step<SKL>(n2, tbl, fb);
+            for (;;) {
+                bool any;
+                if (SKL) {
+                    any = false;
+#pragma unroll
+                    for (int i = 0; i < I; ++i) any |= slot_internal(n[i].y);
+                } else {          // xgboost leaves carry hi == 0, so OR-ing the words keeps the test exact
+                    uint32_t o = 0;
+#pragma unroll
+                    for (int i = 0; i < I; ++i) o |= n[i].y;
+                    any = slot_internal(o);
+                }
+                if (!__any_sync(0xFFFFFFFFu, any)) break;
+#pragma unroll
+                for (int i = 0; i < I; ++i) walk_step<SKL>(n[i], tbl, fb);
             }
         }
-        if (SKL) {
-            acc64 = __dadd_rn(acc64, __hiloint2double((int)n0.y, (int)n0.x));
-            acc64 = __dadd_rn(acc64, __hiloint2double((int)n1.y, (int)n1.x));
-            acc64 = __dadd_rn(acc64, __hiloint2double((int)n2.y, (int)n2.x));
-        } else {
-            acc32 = __fadd_rn(acc32, __uint_as_float(n0.x));
-            acc32 = __fadd_rn(acc32, __uint_as_float(n1.x));
-            acc32 = __fadd_rn(acc32, __uint_as_float(n2.x));
+#pragma unroll
+        for (int i = 0; i < I; ++i) {
+            if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)n[i].y, (int)n[i].x));
+            else acc32 = __fadd_rn(acc32, __uint_as_float(n[i].x));
+            n[i] = nx[i];
         }
     }
     return SKL ? acc64 : (double)acc32;

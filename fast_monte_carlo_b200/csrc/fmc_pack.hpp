@@ -38,7 +38,11 @@
 namespace fmc {
 
 constexpr int kNumMax = 17;
-constexpr int kIlp = 3;  // trees walked together per lane; rounds are padded to a multiple
+#ifndef FMC_ILP
+#define FMC_ILP 4
+#endif
+constexpr int kIlp = FMC_ILP;             // trees walked together per lane; rounds are padded to a multiple
+constexpr int kRootWords = kIlp * 2;      // one group = the kIlp root SLOTS themselves (8 bytes each), copied inline
 constexpr int kChildBits = 20;
 constexpr uint32_t kInternalTag = 0x50000000u;
 
@@ -87,7 +91,7 @@ struct HostForest {
 };
 
 struct PackedForest {
-    std::vector<uint32_t> roots;   // [n_outputs][rounds_padded / 3][4]: root slots of three trees + one unused word
+    std::vector<uint32_t> roots;   // [n_outputs][rounds_padded][2]: a COPY of every tree's root slot (lo, hi), in tree order
     std::vector<uint64_t> slots;
     int n_outputs = 0;
     int rounds = 0;                // real boosting rounds per output in range
@@ -222,7 +226,7 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
     out.rounds = (int)rounds;
     out.rounds_padded = (int)((rounds + kIlp - 1) / kIlp * kIlp);
     if (out.rounds_padded == 0) out.rounds_padded = kIlp;
-    out.roots.assign((size_t)f.n_outputs * (out.rounds_padded / kIlp) * 4, 0);
+    out.roots.assign((size_t)f.n_outputs * out.rounds_padded * 2, 0);   // padding trees: the +0.0 leaf
 
     const uint32_t child_cap = 1u << kChildBits;
     const int feat_cap = 64;
@@ -267,7 +271,8 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
                 order.push_back(n.l); slot_of.push_back(c); depth.push_back(depth[q] + 1);
                 order.push_back(n.r); slot_of.push_back(c + 1); depth.push_back(depth[q] + 1);
             }
-            out.roots[((size_t)k * (out.rounds_padded / kIlp) + j / kIlp) * 4 + j % kIlp] = root_slot;
+            out.roots[((size_t)k * out.rounds_padded + j) * 2] = (uint32_t)out.slots[root_slot];
+            out.roots[((size_t)k * out.rounds_padded + j) * 2 + 1] = (uint32_t)(out.slots[root_slot] >> 32);
         }
     }
     return "";

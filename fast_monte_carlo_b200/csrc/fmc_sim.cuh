@@ -31,7 +31,7 @@ constexpr int kNumKeys = kNumFam * 2;
 
 struct TableRef {
     uint32_t slots_off;     // in 8-byte slots, into the global slot buffer
-    uint32_t roots_off;     // in uint4 (one per three trees), into the global roots buffer
+    uint32_t roots_off;     // in uint4, into the global roots buffer
     uint16_t rounds_padded;
     uint8_t n_outputs;
     uint8_t max_depth;
@@ -490,7 +490,7 @@ __device__ __forceinline__ void write_features(float *row, const Lane &L, int fa
 __device__ __forceinline__ double eval_output(int fam, const TableRef &T, int out, const uint2 *slots_base,
                                               const uint4 *roots_base, uint32_t frow) {
     const uint2 *slots = slots_base + T.slots_off;
-    const uint4 *roots = roots_base + T.roots_off + (size_t)out * (T.rounds_padded / 3);
+    const uint4 *roots = roots_base + T.roots_off + (size_t)out * (T.rounds_padded / 2);
     if (fam >= 2 && fam <= 4) {
         if (T.max_depth <= 3) return walk_output<true, 3>(slots, roots, T.rounds_padded, frow, T.base64[out]);
         return walk_output<true, 99>(slots, roots, T.rounds_padded, frow, T.base64[out]);

@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfmc_b200.so")
+LIB_PATH = os.environ.get("FMC_LIB_PATH") or os.path.join(HERE, "libfmc_b200.so")
 
 N_MODELS = 7
 HIST_BINS = 128
@@ -161,9 +161,9 @@ def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begi
         sm = np.ascontiguousarray(f.scaler_mean, np.float64)
         ss = np.ascontiguousarray(f.scaler_scale, np.float64)
         ns = int(sc.shape[0])
-    info = np.zeros(4, dtype=np.int32)
+    info = np.zeros(6, dtype=np.int32)
     cap_s = int(f.n_nodes) + 8
-    cap_r = 2 * int(f.n_trees) + 16 * int(f.n_outputs)
+    cap_r = 4 * int(f.n_trees) + 64 * int(f.n_outputs)
     slots = np.zeros(cap_s, dtype=np.uint64)
     roots = np.zeros(cap_r, dtype=np.uint32)
     n = L.fmc_pack_forest_host(
@@ -173,8 +173,9 @@ def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begi
         slots.ctypes.data, cap_s, roots.ctypes.data, cap_r, info.ctypes.data)
     if n < 0:
         _check(int(n))
-    meta = dict(rounds=int(info[0]), rounds_padded=int(info[1]), max_depth=int(info[2]), n_outputs=int(info[3]))
-    return slots[:n].copy(), roots[:(meta["rounds_padded"] // 3) * 4 * meta["n_outputs"]].copy(), meta
+    meta = dict(rounds=int(info[0]), rounds_padded=int(info[1]), max_depth=int(info[2]), n_outputs=int(info[3]),
+                ilp=int(info[4]), root_words=int(info[5]))
+    return slots[:n].copy(), roots[:meta["rounds_padded"] * 2 * meta["n_outputs"]].copy(), meta
 
 
 class Context:

@@ -176,7 +176,8 @@ int fmc_sync(fmc_ctx *ctx);
  * evaluates nothing; CPU tests walk the returned slots themselves, and DESIGN.md's table-size
  * figures come from it.  mode 0 = simulation preset (numerics 6..11 folded to fold_value17[]),
  * 1 = predict preset.  Returns the slot count (>= 0) or a negative fmc_status; buffers that are too
- * small are left untouched.  info_out = {rounds, rounds_padded, max_depth, n_outputs}. */
+ * small are left untouched.  info_out[6] = {rounds, rounds_padded, max_depth, n_outputs, trees per
+ * group, root words per group}. */
 int64_t fmc_pack_forest_host(const fmc_forest_desc *desc, int32_t mode, int32_t col0, int32_t col1,
                              const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
                              const double *scaler_mean, const double *scaler_scale, int32_t tree_begin,

@@ -67,7 +67,12 @@ def walk(slots, roots, meta, rows, skl, feat_bits, base):
     for o in range(meta["n_outputs"]):
         acc = np.full(n, base[o], dtype=np.float64 if skl else np.float32)
         for t in range(rp):
-            idx = np.full(n, roots[(o * (rp // 3) + t // 3) * 4 + t % 3], dtype=np.int64)
+            # the walk starts from the inline COPY of the root slot (roots[o][t] = lo, hi)
+            r_lo, r_hi = roots[(o * rp + t) * 2], roots[(o * rp + t) * 2 + 1]
+            root = np.uint64(r_lo) | (np.uint64(r_hi) << np.uint64(32))
+            hits = np.flatnonzero(slots == root)
+            assert hits.size, "inline root slot is not a copy of a table slot"
+            idx = np.full(n, hits[0], dtype=np.int64)
             live = internal[idx]
             while live.any():
                 i = idx[live]

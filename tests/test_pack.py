@@ -84,6 +84,7 @@ def test_tree_range_and_named_player(models_s2, native_lib):
 def test_padding_trees_are_exact_zero(models_s2, native_lib):
     f = models_s2["pass_yards"]
     slots, roots, meta = native.pack_forest_host(f, mode=1, cols=(491, 2877))
-    assert meta["rounds"] == 400 and meta["rounds_padded"] == 402
-    r = roots.reshape(3, 134, 4)
-    assert np.all(r[:, 133, 1:] == 0) and np.all(r[:, :, 3] == 0) and slots[0] == 0      # +0.0 leaf
+    il = meta["ilp"]
+    assert meta["rounds"] == 400 and meta["rounds_padded"] == -(-400 // il) * il
+    r = roots.reshape(3, meta["rounds_padded"], 2)
+    assert np.all(r[:, 400:] == 0) and slots[0] == 0      # padding trees are the +0.0 leaf
