@@ -325,7 +325,7 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
     }
     a.scores = g->scores_dev; a.hist = g->hist_dev; a.counters = (unsigned long long *)g->counters_dev;
     a.stream = g->stream_dev; a.trace = g->trace_dev; a.iters = g->iters_dev;
-    const int grid = c->prop.multiProcessorCount;
+    const int grid = c->prop.multiProcessorCount * kSimCtasPerSm;
     sim_kernel<<<grid, kSimThreads, sim_smem_bytes(), st>>>(a);
     CK(cudaGetLastError());
     return FMC_OK;

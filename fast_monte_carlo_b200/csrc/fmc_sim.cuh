@@ -25,7 +25,14 @@
 
 namespace fmc {
 
-constexpr int kSimThreads = 1024;
+#ifndef FMC_SIM_THREADS
+#define FMC_SIM_THREADS 1024
+#endif
+#ifndef FMC_SIM_CTAS_PER_SM
+#define FMC_SIM_CTAS_PER_SM 1
+#endif
+constexpr int kSimThreads = FMC_SIM_THREADS;
+constexpr int kSimCtasPerSm = FMC_SIM_CTAS_PER_SM;
 constexpr int kNumFam = 6;           // S1, S2, PQ, RQ, SQ, PM  (== model ids 0..5)
 constexpr int kNumKeys = kNumFam * 2;
 
@@ -498,7 +505,7 @@ __device__ __forceinline__ double eval_output(int fam, const TableRef &T, int ou
     return walk_output<false, 99>(slots, roots, T.rounds_padded, frow, (double)T.base[out]);
 }
 
-__global__ void __launch_bounds__(kSimThreads, 1) sim_kernel(const SimKernelArgs a) {
+__global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const SimKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SimShared &sh = *reinterpret_cast<SimShared *>(smem_raw);
     float *feats = reinterpret_cast<float *>(smem_raw + kSimSharedBytes);
