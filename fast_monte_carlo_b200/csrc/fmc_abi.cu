@@ -27,9 +27,11 @@ struct PredictArgs {
     const double *rows;     // [n][17]
     double *out;            // [n][n_outputs]
     long long n;
-    const uint2 *slots;
-    const uint4 *roots;
-    int n_outputs, rounds_padded, max_depth, n_num;
+    uint32_t win_lo, win_hi;
+    const uint4 *stream;
+    const uint2 *consts;
+    uint32_t stream_off[8], consts_off[8], n_groups[8];
+    int n_outputs, n_num;
     int zero_is_missing;
     double base[8];
     int n_scaled;
@@ -38,12 +40,15 @@ struct PredictArgs {
 };
 
 constexpr int kPredThreads = 256;
+constexpr int kPredChunkFloats = kPredRows * 32;
 
 template <bool SKL>
 __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs a) {
-    __shared__ float rows[kPredThreads * kPredStride];
-    const int tid = threadIdx.x;
+    __shared__ float rows[(kPredThreads / 32) * kPredChunkFloats];   // [warp][feature][lane]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float inf = __int_as_float(0x7f800000);
+    for (int i = tid; i < (kPredThreads / 32) * 32; i += kPredThreads)
+        rows[(i >> 5) * kPredChunkFloats + kPredNinfRow * 32 + (i & 31)] = -inf;
     for (long long base = (long long)blockIdx.x * kPredThreads; base < a.n; base += (long long)gridDim.x * kPredThreads) {
         for (int i = tid; i < kPredThreads * kNumMax; i += kPredThreads) {
             const int r = i / kNumMax, k = i - r * kNumMax;
@@ -54,34 +59,104 @@ __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs
                 if (a.scaler_cols[j] == k) x = (x - a.scaler_mean[j]) / a.scaler_scale[j];
             const float v = (float)x;
             const bool flag = (k == 3 || k == 12 || k == 13 || k == 14 || k == 16);
-            float *row = rows + r * kPredStride;
+            float *col = rows + (r >> 5) * kPredChunkFloats + (r & 31);
             if (flag || !a.zero_is_missing) {
-                row[k] = v;
+                col[k * 32] = v;
             } else {
                 // rows of the B views follow the 17 numerics in the order of the non-flag columns
                 int nb = kNumMax;
                 for (int q = 0; q < k; ++q) nb += !(q == 3 || q == 12 || q == 13 || q == 14 || q == 16);
-                row[k] = v == 0.f ? -inf : v;
-                row[nb] = v == 0.f ? inf : v;
+                col[k * 32] = v == 0.f ? -inf : v;
+                col[nb * 32] = v == 0.f ? inf : v;
             }
         }
         __syncthreads();
         const bool live = base + tid < a.n;
-        const uint32_t frow = (uint32_t)__cvta_generic_to_shared(rows + (live ? tid : 0) * kPredStride);
+        const uint32_t fcol = (uint32_t)__cvta_generic_to_shared(rows + warp * kPredChunkFloats + lane);
         for (int o = 0; o < a.n_outputs; ++o) {
-            const uint4 *roots = a.roots + (size_t)o * (a.rounds_padded / 2);
-            double v;
-            if (SKL) {
-                v = (a.max_depth <= 3) ? walk_output<true, 3>(a.slots, roots, a.rounds_padded, frow, a.base[o])
-                                       : walk_output<true, 99>(a.slots, roots, a.rounds_padded, frow, a.base[o]);
-            } else {
-                v = walk_output<false, 99>(a.slots, roots, a.rounds_padded, frow, a.base[o]);
-            }
+            ForestView F;
+            F.win_lo = a.win_lo; F.win_hi = a.win_hi;
+            F.stream = a.stream + a.stream_off[o];
+            F.consts = a.consts + a.consts_off[o];
+            F.n_groups = a.n_groups[o];
+            const double v = walk_output<SKL>(F, fcol, lane, a.base[o]);
             if (live) a.out[(base + tid) * a.n_outputs + o] = v;
         }
         __syncthreads();
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Device placement of packed forests: node tables go into 1 MiB-aligned windows (a table never
+// straddles a window, see fmc_pack.hpp), root streams and constants side streams are concatenated.
+// ---------------------------------------------------------------------------------------------
+struct TablePlacement {
+    uint64_t window_addr;                 // device address of the table's window
+    uint32_t stream_off[8], consts_off[8], n_groups[8];   // in uint4 / uint2 / groups
+};
+
+struct TableArena {
+    std::vector<uint64_t> h_nodes, h_stream, h_consts;
+    std::vector<size_t> win_index;        // window of each placed table, resolved to an address at upload
+    char *d_raw = nullptr, *d_nodes = nullptr;
+    uint4 *d_stream = nullptr;
+    uint2 *d_consts = nullptr;
+    size_t cap_nodes = 0, cap_stream = 0, cap_consts = 0;
+
+    void clear() { h_nodes.clear(); h_stream.clear(); h_consts.clear(); win_index.clear(); }
+    // Relocates `pf` to its place and appends it; returns the table id.
+    int place(PackedForest &pf, TablePlacement &pl) {
+        size_t cursor = (h_nodes.size() * 8 + 127) / 128 * 128;
+        const size_t bytes = pf.slots.size() * 8;
+        if (cursor % kWindowBytes + bytes > kWindowBytes) cursor = (cursor + kWindowBytes - 1) / kWindowBytes * kWindowBytes;
+        pf.relocate((uint32_t)(cursor % kWindowBytes));
+        h_nodes.resize(cursor / 8, 0);
+        h_nodes.insert(h_nodes.end(), pf.slots.begin(), pf.slots.end());
+        while (h_stream.size() % 2) h_stream.push_back(0);
+        const size_t s0 = h_stream.size(), c0 = h_consts.size();
+        h_stream.insert(h_stream.end(), pf.stream.begin(), pf.stream.end());
+        h_consts.insert(h_consts.end(), pf.consts.begin(), pf.consts.end());
+        for (int k = 0; k < 8; ++k) {
+            pl.stream_off[k] = (uint32_t)((s0 + pf.stream_off[k]) / 2);
+            pl.consts_off[k] = (uint32_t)(c0 + pf.consts_off[k]);
+            pl.n_groups[k] = pf.n_groups[k];
+        }
+        win_index.push_back(cursor / kWindowBytes);
+        pl.window_addr = 0;
+        return (int)win_index.size() - 1;
+    }
+    uint64_t window_addr(int table) const { return (uint64_t)(uintptr_t)d_nodes + win_index[table] * kWindowBytes; }
+    cudaError_t upload(cudaStream_t st, bool sync_copy) {
+        cudaError_t e;
+        const size_t nb = h_nodes.size() * 8 + kWindowBytes, sb = (h_stream.size() + 2) * 8, cb = (h_consts.size() + 1) * 8;
+        if (nb > cap_nodes) {
+            cudaFree(d_raw); d_raw = nullptr; cap_nodes = 0;
+            if ((e = cudaMalloc(&d_raw, nb)) != cudaSuccess) return e;
+            cap_nodes = nb;
+        }
+        d_nodes = (char *)(((uintptr_t)d_raw + kWindowBytes - 1) / kWindowBytes * kWindowBytes);
+        if (sb > cap_stream) {
+            cudaFree(d_stream); d_stream = nullptr; cap_stream = 0;
+            if ((e = cudaMalloc(&d_stream, sb)) != cudaSuccess) return e;
+            cap_stream = sb;
+        }
+        if (cb > cap_consts) {
+            cudaFree(d_consts); d_consts = nullptr; cap_consts = 0;
+            if ((e = cudaMalloc(&d_consts, cb)) != cudaSuccess) return e;
+            cap_consts = cb;
+        }
+        (void)st; (void)sync_copy;
+        if (!h_nodes.empty() && (e = cudaMemcpy(d_nodes, h_nodes.data(), h_nodes.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        if (!h_stream.empty() && (e = cudaMemcpy(d_stream, h_stream.data(), h_stream.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        if (!h_consts.empty() && (e = cudaMemcpy(d_consts, h_consts.data(), h_consts.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) return e;
+        return cudaSuccess;
+    }
+    void release() {
+        cudaFree(d_raw); cudaFree(d_stream); cudaFree(d_consts);
+        d_raw = d_nodes = nullptr; d_stream = nullptr; d_consts = nullptr;
+        cap_nodes = cap_stream = cap_consts = 0;
+    }
+};
 
 // ---------------------------------------------------------------------------------------------
 // context
@@ -94,16 +169,13 @@ struct fmc_ctx {
     std::vector<fmc_matchup> matchups;
     bool tables_dirty = true;
     // device-side state of the last set_matchups
-    uint2 *d_slots = nullptr;
-    uint4 *d_roots = nullptr;
+    TableArena sim_tables;
     MatchupDev *d_matchups = nullptr;
     unsigned long long *d_next = nullptr;
     std::vector<unsigned long long> h_next;
     std::vector<int32_t> packed_slots;   // [n_matchups][FMC_N_MODELS][2]
     // predict scratch
-    uint2 *p_slots = nullptr;
-    uint4 *p_roots = nullptr;
-    size_t p_slots_cap = 0, p_roots_cap = 0;
+    TableArena pred_tables;
 };
 
 extern "C" const char *fmc_last_error(void) { return g_err.c_str(); }
@@ -140,8 +212,8 @@ extern "C" int fmc_create(int device, fmc_ctx **out) {
 extern "C" void fmc_destroy(fmc_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaFree(c->d_slots); cudaFree(c->d_roots); cudaFree(c->d_matchups); cudaFree(c->d_next);
-    cudaFree(c->p_slots); cudaFree(c->p_roots);
+    c->sim_tables.release(); c->pred_tables.release();
+    cudaFree(c->d_matchups); cudaFree(c->d_next);
     delete c;
 }
 
@@ -214,9 +286,11 @@ static int build_tables(fmc_ctx *c) {
         if (family_needed(c, fam) && !c->forest[fam].loaded)
             return fail(FMC_ERR_INVALID, "model " + std::to_string(fam) + " is required by the current fmc_params but not loaded");
     const int n = (int)c->matchups.size();
-    std::vector<uint64_t> slots;
-    std::vector<uint32_t> roots;
     std::vector<MatchupDev> md(n);
+    struct Pending { int matchup, fam, off, table; };
+    std::vector<Pending> placed;
+    TableArena &A = c->sim_tables;
+    A.clear();
     c->packed_slots.assign((size_t)n * FMC_N_MODELS * 2, 0);
     for (int i = 0; i < n; ++i) {
         const fmc_matchup &mu = c->matchups[i];
@@ -245,30 +319,34 @@ static int build_tables(fmc_ctx *c) {
                 PackedForest pf;
                 const std::string err = pack_forest(f, s, pf);
                 if (!err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(fam) + ": " + err);
+                if (pf.n_outputs > 5) return fail(FMC_ERR_CAPACITY, "more than 5 outputs in a simulation model");
                 TableRef &T = M.tbl[fam][off];
-                if (slots.size() + pf.slots.size() >= 0xFFFFFFFFull) return fail(FMC_ERR_CAPACITY, "slot buffer too large");
-                T.slots_off = (uint32_t)slots.size();
-                T.roots_off = (uint32_t)(roots.size() / 4);
-                T.rounds_padded = (uint16_t)pf.rounds_padded;
+                TablePlacement pl;
+                const int table = A.place(pf, pl);
+                for (int k = 0; k < pf.n_outputs; ++k) {
+                    if (pl.n_groups[k] > 0xFFFFu) return fail(FMC_ERR_CAPACITY, "too many tree groups in one output");
+                    T.stream_off[k] = pl.stream_off[k]; T.consts_off[k] = pl.consts_off[k]; T.n_groups[k] = (uint16_t)pl.n_groups[k];
+                }
                 T.n_outputs = (uint8_t)pf.n_outputs;
                 T.max_depth = (uint8_t)pf.max_depth;
                 for (int k = 0; k < 5 && k < f.n_outputs; ++k) T.base[k] = (float)f.base[k];
                 for (int k = 0; k < 3 && k < f.n_outputs; ++k) T.base64[k] = f.base[k];
-                slots.insert(slots.end(), pf.slots.begin(), pf.slots.end());
-                roots.insert(roots.end(), pf.roots.begin(), pf.roots.end());
+                placed.push_back({i, fam, off, table});
                 c->packed_slots[((size_t)i * FMC_N_MODELS + fam) * 2 + off] = (int32_t)pf.slots.size();
             }
         }
     }
     CK(cudaSetDevice(c->device));
-    cudaFree(c->d_slots); cudaFree(c->d_roots); cudaFree(c->d_matchups); cudaFree(c->d_next);
-    c->d_slots = nullptr; c->d_roots = nullptr; c->d_matchups = nullptr; c->d_next = nullptr;
-    CK(cudaMalloc(&c->d_slots, slots.size() * 8));
-    CK(cudaMalloc(&c->d_roots, roots.size() * 4));
+    CK(A.upload(nullptr, true));
+    for (const Pending &q : placed) {
+        const uint64_t w = A.window_addr(q.table);
+        TableRef &T = md[q.matchup].tbl[q.fam][q.off];
+        T.win_lo = (uint32_t)w; T.win_hi = (uint32_t)(w >> 32);
+    }
+    cudaFree(c->d_matchups); cudaFree(c->d_next);
+    c->d_matchups = nullptr; c->d_next = nullptr;
     CK(cudaMalloc(&c->d_matchups, md.size() * sizeof(MatchupDev)));
     CK(cudaMalloc(&c->d_next, (size_t)n * 8));
-    CK(cudaMemcpy(c->d_slots, slots.data(), slots.size() * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->d_roots, roots.data(), roots.size() * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_matchups, md.data(), md.size() * sizeof(MatchupDev), cudaMemcpyHostToDevice));
     c->h_next.resize(n);
     c->tables_dirty = false;
@@ -312,7 +390,7 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
     SimKernelArgs a;
     std::memset(&a, 0, sizeof(a));
     a.matchups = c->d_matchups; a.n_matchups = (int)c->matchups.size(); a.next_game = c->d_next;
-    a.slots = c->d_slots; a.roots = c->d_roots;
+    a.root_stream = c->sim_tables.d_stream; a.consts = c->sim_tables.d_consts;
     a.seed_lo = (uint32_t)g->seed; a.seed_hi = (uint32_t)(g->seed >> 32);
     a.policy = c->params.policy; a.sampler = c->params.sampler; a.stage2_mode = c->params.stage2_mode;
     a.play_temp = (float)c->params.play_temp; a.qy_noise = c->params.qy_noise;
@@ -404,25 +482,20 @@ extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, 
     const std::string err = pack_forest(f, s, pf);
     if (!err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(id) + ": " + err);
     cudaStream_t st = (cudaStream_t)stream;
-    if (pf.slots.size() > c->p_slots_cap) {
-        cudaFree(c->p_slots);
-        c->p_slots = nullptr; c->p_slots_cap = 0;
-        CK(cudaMalloc(&c->p_slots, pf.slots.size() * 8));
-        c->p_slots_cap = pf.slots.size();
-    }
-    if (pf.roots.size() > c->p_roots_cap) {
-        cudaFree(c->p_roots);
-        c->p_roots = nullptr; c->p_roots_cap = 0;
-        CK(cudaMalloc(&c->p_roots, pf.roots.size() * 4));
-        c->p_roots_cap = pf.roots.size();
-    }
     CK(cudaStreamSynchronize(st));   // a previous launch may still read the scratch tables
-    CK(cudaMemcpy(c->p_slots, pf.slots.data(), pf.slots.size() * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(c->p_roots, pf.roots.data(), pf.roots.size() * 4, cudaMemcpyHostToDevice));
+    TableArena &A = c->pred_tables;
+    A.clear();
+    TablePlacement pl;
+    const int table = A.place(pf, pl);
+    CK(A.upload(st, true));
     PredictArgs a;
     std::memset(&a, 0, sizeof(a));
-    a.rows = rows_dev; a.out = out_dev; a.n = n; a.slots = c->p_slots; a.roots = c->p_roots;
-    a.n_outputs = f.n_outputs; a.rounds_padded = pf.rounds_padded; a.max_depth = pf.max_depth; a.n_num = f.n_num;
+    a.rows = rows_dev; a.out = out_dev; a.n = n;
+    const uint64_t w = A.window_addr(table);
+    a.win_lo = (uint32_t)w; a.win_hi = (uint32_t)(w >> 32);
+    a.stream = A.d_stream; a.consts = A.d_consts;
+    for (int k = 0; k < 8; ++k) { a.stream_off[k] = pl.stream_off[k]; a.consts_off[k] = pl.consts_off[k]; a.n_groups[k] = pl.n_groups[k]; }
+    a.n_outputs = f.n_outputs; a.n_num = f.n_num;
     a.zero_is_missing = (f.kind == FMC_KIND_XGB && f.zero_is_missing) ? 1 : 0;
     for (int k = 0; k < 8; ++k) a.base[k] = f.base[k];
     a.n_scaled = f.n_scaled;
@@ -467,14 +540,14 @@ extern "C" int fmc_sync(fmc_ctx *c) {
 }
 
 // Host-only packing entry point: lets CPU tests inspect the specialised tables without a GPU.  It
-// performs no evaluation -- tests walk the returned slots themselves.
+// performs no evaluation -- tests walk the returned tables themselves.
 //   mode 0 = simulation preset (timeouts + SP+ folded to `fold_value`), 1 = predict preset.
-// Returns the number of slots, or a negative status; fills up to the given capacities.
+// Returns the number of node slots, or a negative status; fills up to the given capacities.
 extern "C" int64_t fmc_pack_forest_host(const fmc_forest_desc *d, int32_t mode, int32_t col0, int32_t col1,
                                         const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
                                         const double *scaler_mean, const double *scaler_scale, int32_t tree_begin,
-                                        int32_t tree_end, uint64_t *slots_out, int64_t slots_cap, uint32_t *roots_out,
-                                        int64_t roots_cap, int32_t *info_out /* rounds, rounds_padded, max_depth, n_outputs */) {
+                                        int32_t tree_end, uint64_t *slots_out, int64_t slots_cap, uint64_t *stream_out,
+                                        int64_t stream_cap, uint64_t *consts_out, int64_t consts_cap, int32_t *info_out) {
     if (!d) return fail(FMC_ERR_INVALID, "fmc_pack_forest_host: desc is NULL");
     HostForest f;
     f.assign(*d);
@@ -489,9 +562,17 @@ extern "C" int64_t fmc_pack_forest_host(const fmc_forest_desc *d, int32_t mode, 
     PackedForest pf;
     const std::string err = pack_forest(f, s, pf);
     if (!err.empty()) return fail(FMC_ERR_CAPACITY, err);
-    if (info_out) { info_out[0] = pf.rounds; info_out[1] = pf.rounds_padded; info_out[2] = pf.max_depth; info_out[3] = pf.n_outputs;
-                    info_out[4] = kIlp; info_out[5] = kRootWords; }
+    if (info_out) {
+        info_out[0] = pf.rounds; info_out[1] = pf.max_depth; info_out[2] = pf.n_outputs; info_out[3] = kIlp;
+        info_out[4] = s.ninf_row; info_out[5] = (int32_t)pf.stream.size(); info_out[6] = (int32_t)pf.consts.size();
+        info_out[7] = (int32_t)pf.constants;
+        for (int k = 0; k < 8; ++k) {
+            info_out[8 + k] = (int32_t)pf.stream_off[k]; info_out[16 + k] = (int32_t)pf.n_groups[k];
+            info_out[24 + k] = (int32_t)pf.consts_off[k];
+        }
+    }
     if (slots_out && (int64_t)pf.slots.size() <= slots_cap) std::memcpy(slots_out, pf.slots.data(), pf.slots.size() * 8);
-    if (roots_out && (int64_t)pf.roots.size() <= roots_cap) std::memcpy(roots_out, pf.roots.data(), pf.roots.size() * 4);
+    if (stream_out && (int64_t)pf.stream.size() <= stream_cap) std::memcpy(stream_out, pf.stream.data(), pf.stream.size() * 8);
+    if (consts_out && (int64_t)pf.consts.size() <= consts_cap) std::memcpy(consts_out, pf.consts.data(), pf.consts.size() * 8);
     return (int64_t)pf.slots.size();
 }

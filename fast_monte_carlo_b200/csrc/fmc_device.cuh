@@ -7,7 +7,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#include "fmc_pack.hpp"   // kIlp, kRootWords, slot format constants
+#include "fmc_pack.hpp"   // kIlp, slot format constants
 
 namespace fmc {
 
@@ -101,112 +101,118 @@ __device__ __noinline__ double ppnd16(double p) {
 __device__ __forceinline__ float expf_cr(float x) { return (float)exp((double)x); }
 
 // ---------------------------------------------------------------------------------------------
-// Tree walker.  One lane = one row; all 32 lanes of a warp walk the SAME tree at the same time
-// (different paths), so the slots a warp touches per level sit inside one small tree (at most
-// 2^level distinct 8-byte words) -- broadcast-friendly in L1.  Three trees are in flight per lane
-// for instruction-level parallelism.
+// Tree walker.  One lane = one request; all 32 lanes of a warp walk the SAME trees at the same
+// time (different paths), kIlp trees in flight per lane.  Layout of the node table, the root
+// stream and the constants side stream: fmc_pack.hpp.
 //
-// Slot format (fmc_pack.hpp): internal iff (int)hi >= 0x50000000; hi = tag | (4*row) << 20 | child;
-// lo = float threshold.  Leaf: sklearn = the float64 itself, xgboost = float32 in lo.
-//
-// The feature row lives in shared memory and is addressed with a 32-bit shared-window address
-// (`frow`, from __cvta_generic_to_shared) so that the per-level address math is one integer add;
-// the table is addressed as base + 32-bit byte offset.
+// The walk is branch-free per lane: a group of kIlp trees is walked for exactly D levels (D is in
+// the group's metadata, warp-uniform), leaves keep a lane in place (xgboost: self-pointing leaf;
+// sklearn: pass-through chain), so one level of one tree is
+//      LEA.HI   feature address  = chunk column of the lane + (hi >> 20)
+//      LDS      feature value                       (feature-major rows: never a bank conflict)
+//      LOP3     left-child address = (hi & mask) | window base
+//      FSETP + predicated add of 8 (right child)
+//      MOV      high half of the 64-bit address      (the window's, constant)
+//      LDG.64   next slot                            (L1/L2-resident table, read-only path)
+// The feature rows of a 32-request chunk live in shared memory as [feature][lane]; `fcol` is the
+// 32-bit shared-window address of the lane's column (chunk base + 4 * lane).
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t kTag = 0x50000000u;
+struct ForestView {          // everything here is warp-uniform
+    uint32_t win_lo, win_hi; // address of the table's 1 MiB window
+    const uint4 *stream;     // root stream of ONE output: 2 x uint4 (kIlp root slots) per group
+    const uint2 *consts;     // side stream of that output
+    uint32_t n_groups;
+};
 
-__device__ __forceinline__ uint2 ldg_slot(const char *tbl, uint32_t slot) {
-    uint2 v;
-    asm("{\n\t.reg .u64 ad;\n\t"
-        "mad.wide.u32 ad, %2, 8, %3;\n\t"
-        "ld.global.nc.v2.u32 {%0, %1}, [ad];\n\t}"
-        : "=r"(v.x), "=r"(v.y) : "r"(slot), "l"(tbl));
-    return v;
-}
-__device__ __forceinline__ bool slot_internal(uint32_t hi) { return (int)hi >= (int)kTag; }
-
-// One level of one tree for this lane; does nothing once the lane holds a leaf.
-//   frow_biased = shared-window address of the lane's feature row minus 0x500 (tag bits of hi >> 20)
-// Target per level: ISETP, LEA.HI (row address), LDS, FSET (0 / 0xFFFFFFFF), LOP3, IADD, IMAD.WIDE, LDG.
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
     float v;
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
-template <bool SKL>
-__device__ __forceinline__ void walk_step(uint2 &n, const char *__restrict__ tbl, uint32_t frow_biased) {
-    if (slot_internal(n.y)) {
-        const float fv = lds_f32(frow_biased + (n.y >> 20));
-        uint32_t m;   // 0xFFFFFFFF when the lane goes right
-        if (SKL) asm("set.gtu.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(fv), "f"(__uint_as_float(n.x)));   // !(fv <= thr)
-        else asm("set.geu.u32.f32 %0, %1, %2;" : "=r"(m) : "f"(fv), "f"(__uint_as_float(n.x)));        // !(fv < thr)
-        n = ldg_slot(tbl, (n.y & 0xFFFFFu) - m);
-    }
+__device__ __forceinline__ uint2 ldg_slot(uint32_t lo, uint32_t hi) {
+    uint2 v;
+    asm("{\n\t.reg .u64 ad;\n\tmov.b64 ad, {%2, %3};\n\tld.global.nc.v2.u32 {%0, %1}, [ad];\n\t}"
+        : "=r"(v.x), "=r"(v.y) : "r"(lo), "r"(hi));
+    return v;
+}
+__device__ __forceinline__ void prefetch_l1(uint32_t lo, uint32_t hi) {
+    asm volatile("{\n\t.reg .u64 ad;\n\tmov.b64 ad, {%0, %1};\n\tprefetch.global.L1 [ad];\n\t}" :: "r"(lo), "r"(hi));
 }
 
-// Sum one output of a packed forest over `rounds_padded` trees (a multiple of kIlp), in tree order.
-// SKL: float64 accumulate of pre-scaled leaves; XGB: float32 accumulate (returned widened).
-// `frow` is the 32-bit shared address of this lane's feature row.  `roots` is the inline copy of the
-// root slots, two trees per uint4, in tree order: every lane of the warp reads the same words (one
-// broadcast load per two trees) and the next group is fetched while the current one is walked.
-template <bool SKL, int MAX_DEPTH>
-__device__ __forceinline__ double walk_output(const uint2 *__restrict__ slots, const uint4 *__restrict__ roots,
-                                              int rounds_padded, uint32_t frow, double base) {
+template <bool SKL>
+__device__ __forceinline__ void walk_step(uint2 &n, uint32_t fcol, uint32_t win_lo, uint32_t win_hi) {
+    const float fv = lds_f32(fcol + (n.y >> kFeatShift));
+    uint32_t a = (n.y & kChildMask) | win_lo;
+    if (SKL)   // right iff !(fv <= thr)
+        asm("{\n\t.reg .pred p;\n\tsetp.gtu.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}" : "+r"(a) : "f"(fv), "f"(__uint_as_float(n.x)));
+    else       // right iff !(fv < thr)
+        asm("{\n\t.reg .pred p;\n\tsetp.geu.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}" : "+r"(a) : "f"(fv), "f"(__uint_as_float(n.x)));
+    n = ldg_slot(a, win_hi);
+}
+
+#ifndef FMC_PREFETCH
+#define FMC_PREFETCH 1
+#endif
+
+// Sum one output of a packed forest in tree order.  SKL: float64 accumulate of pre-scaled leaves;
+// XGB: float32 accumulate (returned widened).
+template <bool SKL>
+__device__ __forceinline__ double walk_output(const ForestView &F, uint32_t fcol, int lane, double base) {
     constexpr int I = kIlp;
-    static_assert(I % 2 == 0, "kIlp must be even (two root slots per uint4)");
-    const char *tbl = reinterpret_cast<const char *>(slots);
-    uint32_t fb = frow - 0x500u;
-    asm volatile("" : "+r"(fb));          // keep the row address in a register (no re-materialisation)
     double acc64 = base;
     float acc32 = (float)base;
-    const int groups = rounds_padded / I;
+    if (F.n_groups == 0) return SKL ? acc64 : (double)acc32;
+    const uint4 *sp = F.stream;
+    const uint2 *cp = F.consts;
     uint2 n[I];
-#pragma unroll
-    for (int q = 0; q < I / 2; ++q) {
-        const uint4 v = __ldg(roots + q);
-        n[2 * q] = make_uint2(v.x, v.y);
-        n[2 * q + 1] = make_uint2(v.z, v.w);
+    {
+        const uint4 a = __ldg(sp), b = __ldg(sp + 1);
+        n[0] = make_uint2(a.x, a.y); n[1] = make_uint2(a.z, a.w);
+        n[2] = make_uint2(b.x, b.y); n[3] = make_uint2(b.z, b.w);
     }
 #pragma unroll 1
-    for (int t = 0; t < groups; ++t) {
-        uint2 nx[I];
-        const uint4 *next = roots + (size_t)(t + 1 < groups ? t + 1 : t) * (I / 2);
-#pragma unroll
-        for (int q = 0; q < I / 2; ++q) {
-            const uint4 v = __ldg(next + q);
-            nx[2 * q] = make_uint2(v.x, v.y);
-            nx[2 * q + 1] = make_uint2(v.z, v.w);
+    for (uint32_t g = 0; g < F.n_groups; ++g) {
+        // the next group's roots arrive while this group is walked
+        const uint4 *nx = sp + 2 * (g + 1 < F.n_groups ? g + 1 : g);
+        const uint4 xa = __ldg(nx), xb = __ldg(nx + 1);
+        const uint32_t depth = (n[0].y & 7u) | ((n[1].y & 1u) << 3);
+        const bool has_consts = (n[1].y & 2u) != 0;
+#if FMC_PREFETCH
+        {   // pull the next group's node lines into L1 ahead of its walk
+            const uint32_t lines = (xb.y & 7u) | ((xb.w & 3u) << 3);
+            if ((uint32_t)lane < lines) prefetch_l1((((xa.y & kChildMask) | F.win_lo) & ~127u) + 128u * (uint32_t)lane, F.win_hi);
         }
-        if (MAX_DEPTH <= 4) {
+#endif
+#pragma unroll 1
+        for (uint32_t d = 0; d < depth; ++d) {
 #pragma unroll
-            for (int d = 0; d < MAX_DEPTH; ++d) {
+            for (int i = 0; i < I; ++i) walk_step<SKL>(n[i], fcol, F.win_lo, F.win_hi);
+        }
+        if (!has_consts) {
 #pragma unroll
-                for (int i = 0; i < I; ++i) walk_step<SKL>(n[i], tbl, fb);
+            for (int i = 0; i < I; ++i) {
+                if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)n[i].y, (int)n[i].x));
+                else acc32 = __fadd_rn(acc32, __uint_as_float(n[i].x));
             }
         } else {
-            for (;;) {
-                bool any;
-                if (SKL) {
-                    any = false;
+            // constants (trees folded to one leaf) take their place in the tree order
+            const uint32_t counts = __ldg(cp).x;
+            ++cp;
 #pragma unroll
-                    for (int i = 0; i < I; ++i) any |= slot_internal(n[i].y);
-                } else {          // xgboost leaves carry hi == 0, so OR-ing the words keeps the test exact
-                    uint32_t o = 0;
-#pragma unroll
-                    for (int i = 0; i < I; ++i) o |= n[i].y;
-                    any = slot_internal(o);
+            for (int i = 0; i < I; ++i) {
+                const uint32_t c = (counts >> (8 * i)) & 0xFFu;
+                for (uint32_t j = 0; j < c; ++j) {
+                    const uint2 v = __ldg(cp);
+                    ++cp;
+                    if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)v.y, (int)v.x));
+                    else acc32 = __fadd_rn(acc32, __uint_as_float(v.x));
                 }
-                if (!__any_sync(0xFFFFFFFFu, any)) break;
-#pragma unroll
-                for (int i = 0; i < I; ++i) walk_step<SKL>(n[i], tbl, fb);
+                if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)n[i].y, (int)n[i].x));
+                else acc32 = __fadd_rn(acc32, __uint_as_float(n[i].x));
             }
         }
-#pragma unroll
-        for (int i = 0; i < I; ++i) {
-            if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)n[i].y, (int)n[i].x));
-            else acc32 = __fadd_rn(acc32, __uint_as_float(n[i].x));
-            n[i] = nx[i];
-        }
+        n[0] = make_uint2(xa.x, xa.y); n[1] = make_uint2(xa.z, xa.w);
+        n[2] = make_uint2(xb.x, xb.y); n[3] = make_uint2(xb.z, xb.w);
     }
     return SKL ? acc64 : (double)acc32;
 }

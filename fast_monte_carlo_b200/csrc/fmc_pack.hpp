@@ -1,10 +1,10 @@
 // Host-side forest specialiser + packer.
 //
-// Takes one tree ensemble in the SoA form of fmc_forest_desc and produces the 8-byte-slot node
-// table the sm_100a kernels walk.  Two things happen here, both exact (they never change which
-// leaf a row reaches, so margins are bit-identical to walking the original trees in the same
-// tree order -- the oracle walks the ORIGINAL trees, which is what makes the parity tests
-// meaningful):
+// Takes one tree ensemble in the SoA form of fmc_forest_desc and produces the node table and the
+// root stream the sm_100a kernels walk.  Two things happen here, both exact (they never change
+// which leaf a row reaches, and they keep the reference's tree order, so margins are bit-identical
+// to walking the original trees -- the oracle walks the ORIGINAL trees, which is what makes the
+// parity tests meaningful):
 //
 //  1. Constant folding.  Columns whose value is the same for every row of a launch are resolved
 //     at pack time: all one-hot columns (the OneHotEncoder half of ColumnTransformer.transform,
@@ -12,19 +12,36 @@
 //     mode, the six numerics that are constant per (offense, defense) orientation: both timeouts
 //     (never spent, FMC:911-912) and the four SP+ ratings (FMC:1001-1004).  For CSR-fed boosters an
 //     exact zero is a MISSING value and takes the node's default branch.
-//  2. Re-layout.  Each surviving tree is written breadth-first into 8-byte slots with the two
-//     children of a node adjacent (left at c, right at c+1):
-//        internal slot : lo32 = float threshold, hi32 = 0x50000000 | (4 * feature row) << 20 | child slot
-//        leaf slot     : the value itself (sklearn: the float64; xgboost: float32 in lo32, hi32 = 0)
-//     A slot is internal iff (int32)hi32 >= 0x50000000: as the high word of a float64 that range
-//     means a positive value >= 2^257, which no leaf holds (checked at pack time).  20 child bits
-//     (1 M slots per table) and 8 bits of byte offset into the feature row (64 rows).
+//     A tree that folds to a single leaf becomes a CONSTANT: it is not walked, its value is added
+//     at its place in the tree order.
 //
-// "Feature rows" are the columns of the per-lane feature record the kernels build in shared
-// memory.  For CSR-fed boosters a non-flag numeric that may be exactly zero gets two rows: row A
-// holds -inf when the value is 0 (used by default-left nodes: -inf < thr is always true) and
-// row B holds +inf (default-right nodes).  0/1 flags need no second row: their node is rewritten
-// as `flag < 0.5` with the children placed so that "absent" follows the default branch.
+//  2. Re-layout for a branch-free, lock-step walk.  Surviving trees are taken kIlp at a time, in
+//     tree order ("group").  All trees of a group are walked for exactly D levels, D = the deepest
+//     tree of the group, with no per-lane leaf test:
+//        node slot (8 bytes): lo32 = float threshold
+//                             hi32 = (feature byte offset) << 20 | byte offset of the LEFT child
+//                                    inside the table's 1 MiB window (8-byte aligned; the right
+//                                    child is the next slot)
+//        xgboost leaf        : lo32 = the float32 leaf value, hi32 = a node that tests the "-inf"
+//                              feature column and points at ITSELF -> a lane that reaches a leaf
+//                              early stays there (-inf < value is always true => left => self)
+//        sklearn leaf        : the float64 value itself (pre-multiplied by the learning rate);
+//                              a leaf above level D is reached through a chain of pass-through
+//                              nodes (again testing the "-inf" column), so that after D levels
+//                              every lane holds leaf bits.
+//     "feature byte offset": the kernels keep the feature rows of 32 requests FEATURE-MAJOR in
+//     shared memory ([feature][lane], 128 bytes per feature), so a lane's load of any feature hits
+//     its own bank -- conflict-free whatever node each lane is at.
+//     The walk starts from the ROOT STREAM: the root slots of the groups, kIlp x 8 bytes per group,
+//     in tree order, read with warp-uniform 16-byte loads.  The low three bits of the four child
+//     fields of a group carry its metadata (D, "has constants", lines to prefetch).  Constants live
+//     in a side stream that is only touched by groups that have them.
+//
+// "Feature rows" are the columns of the per-request feature record.  For CSR-fed boosters a
+// non-flag numeric that may be exactly zero gets two rows: row A holds -inf when the value is 0
+// (used by default-left nodes: -inf < thr is always true) and row B holds +inf (default-right
+// nodes).  0/1 flags need no second row: their node is rewritten as `flag < 0.5` with the children
+// placed so that "absent" follows the default branch.
 #pragma once
 
 #include <cmath>
@@ -41,10 +58,14 @@ constexpr int kNumMax = 17;
 #ifndef FMC_ILP
 #define FMC_ILP 4
 #endif
-constexpr int kIlp = FMC_ILP;             // trees walked together per lane; rounds are padded to a multiple
-constexpr int kRootWords = kIlp * 2;      // one group = the kIlp root SLOTS themselves (8 bytes each), copied inline
-constexpr int kChildBits = 20;
-constexpr uint32_t kInternalTag = 0x50000000u;
+constexpr int kIlp = FMC_ILP;              // trees walked together per lane (one group)
+static_assert(kIlp == 4, "the group metadata layout (3 spare bits x 4 roots) assumes 4 trees per group");
+constexpr int kFeatShift = 20;             // hi32 >> 20 = byte offset of the feature inside a 32-request chunk
+constexpr int kFeatBytes = 128;            // one feature of a chunk = 32 lanes x 4 bytes
+constexpr uint32_t kChildMask = 0x000FFFF8u;   // byte offset of the left child inside the window
+constexpr uint32_t kMetaMask = 0x7u;
+constexpr size_t kWindowBytes = 1u << 20;  // a table must sit inside one 1 MiB-aligned window
+constexpr int kMaxGroupDepth = 15;
 
 struct PackSpec {
     int32_t active[2] = {-1, -1};   // hot one-hot columns
@@ -53,6 +74,7 @@ struct PackSpec {
     int8_t row[kNumMax];            // feature row of numeric k (A view)
     int8_t row_b[kNumMax];          // B view row, or -1
     uint8_t is_flag[kNumMax];       // 0/1 valued numeric
+    int ninf_row = 0;               // feature row that always holds -inf
     int tree_begin = 0, tree_end = -1;
     // play_model: fold values are standardised first
     int n_scaled = 0;
@@ -91,23 +113,36 @@ struct HostForest {
 };
 
 struct PackedForest {
-    std::vector<uint32_t> roots;   // [n_outputs][rounds_padded][2]: a COPY of every tree's root slot (lo, hi), in tree order
-    std::vector<uint64_t> slots;
+    std::vector<uint64_t> slots;        // node table; child offsets are relative to the table start until relocate()
+    std::vector<uint8_t> slot_is_node;  // 1: hi32 carries a child offset (relocatable), 0: raw float64 leaf
+    std::vector<uint64_t> stream;       // root slots, kIlp per group, outputs concatenated
+    std::vector<uint8_t> stream_is_node;
+    std::vector<uint64_t> consts;       // side stream: per group with constants, 1 count word + the values
+    uint32_t stream_off[8] = {0};       // first stream word (8 bytes) of each output
+    uint32_t n_groups[8] = {0};
+    uint32_t consts_off[8] = {0};       // first side-stream word of each output
     int n_outputs = 0;
-    int rounds = 0;                // real boosting rounds per output in range
-    int rounds_padded = 0;
+    int rounds = 0;                     // real boosting rounds per output in range
     int max_depth = 0;
-    uint64_t internal = 0, leaves = 0;
+    uint64_t internal = 0, leaves = 0, constants = 0, pass_through = 0;
+
+    // Add the table's byte offset inside its window to every child field.
+    void relocate(uint32_t base) {
+        for (size_t i = 0; i < slots.size(); ++i)
+            if (slot_is_node[i]) slots[i] += (uint64_t)base << 32;
+        for (size_t i = 0; i < stream.size(); ++i)
+            if (stream_is_node[i]) stream[i] += (uint64_t)base << 32;
+    }
 };
 
 // Feature-row presets -------------------------------------------------------------------------
 // NUM order (FMC:676-682): 0 down 1 distance 2 yardsToGoal 3 is_red_zone 4 score_diff
 // 5 seconds_remaining 6 offenseTimeouts 7 defenseTimeouts 8..11 SP+ 12 goal_to_go
 // 13 fourth_and_short 14 fg_range 15 half 16 two_minute
-constexpr int kSimRows = 14;      // 11 varying numerics + B views of distance, yardsToGoal, score_diff
-constexpr int kSimStride = 15;    // odd => conflict-free shared-memory rows
-constexpr int kPredRows = 29;     // 17 numerics + 12 B views
-constexpr int kPredStride = 29;
+constexpr int kSimNinfRow = 14;   // 11 varying numerics + B views of distance, yardsToGoal, score_diff, then -inf
+constexpr int kSimRows = 15;
+constexpr int kPredNinfRow = 29;  // 17 numerics + 12 B views, then -inf
+constexpr int kPredRows = 30;
 
 inline void preset_sim(PackSpec &s) {
     const int8_t row[kNumMax] = {0, 1, 2, 3, 4, 5, -1, -1, -1, -1, -1, -1, 6, 7, 8, 9, 10};
@@ -115,6 +150,7 @@ inline void preset_sim(PackSpec &s) {
     const uint8_t fl[kNumMax] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 1};
     std::memcpy(s.row, row, sizeof(row)); std::memcpy(s.row_b, rb, sizeof(rb)); std::memcpy(s.is_flag, fl, sizeof(fl));
     s.fold_mask = 0xFC0;  // numerics 6..11
+    s.ninf_row = kSimNinfRow;
 }
 inline void preset_predict(PackSpec &s) {
     const uint8_t fl[kNumMax] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 1};
@@ -125,6 +161,7 @@ inline void preset_predict(PackSpec &s) {
         s.row_b[k] = fl[k] ? -1 : (int8_t)nb++;
     }
     s.fold_mask = 0;
+    s.ninf_row = kPredNinfRow;
 }
 
 namespace detail {
@@ -195,84 +232,179 @@ struct Builder {
         nodes.push_back({false, 0.0, row, f.thr[i], l, r});
         return (int)nodes.size() - 1;
     }
+    int depth_of(int i) const {
+        const PNode &n = nodes[i];
+        if (n.leaf) return 0;
+        int a = depth_of(n.l), b = depth_of(n.r);
+        return 1 + (a > b ? a : b);
+    }
 };
+
+inline uint64_t f64_bits(double v) { uint64_t u; std::memcpy(&u, &v, 8); return u; }
+inline uint32_t f32_bits(float v) { uint32_t u; std::memcpy(&u, &v, 4); return u; }
 }  // namespace detail
 
-inline uint64_t leaf_slot(int kind, double v) {
-    uint64_t u;
-    if (kind == FMC_KIND_SKL) {
-        std::memcpy(&u, &v, 8);
-    } else {
-        float fv = (float)v;
-        uint32_t lo;
-        std::memcpy(&lo, &fv, 4);
-        u = lo;
-    }
-    return u;
+// Value word of a constant / leaf as the kernels add it: sklearn the float64, xgboost float32 in lo32.
+inline uint64_t value_word(int kind, double v) {
+    if (kind == FMC_KIND_SKL) return detail::f64_bits(v);
+    return (uint64_t)detail::f32_bits((float)v);
 }
 
 // Returns "" on success, otherwise an error message.
 inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedForest &out) {
+    using namespace detail;
     if (!f.loaded) return "model not loaded";
-    int n_trees = (int)f.root.size();
-    int tb = s.tree_begin, te = (s.tree_end < 0 || s.tree_end > n_trees) ? n_trees : s.tree_end;
+    const int n_trees = (int)f.root.size();
+    const int tb = s.tree_begin, te = (s.tree_end < 0 || s.tree_end > n_trees) ? n_trees : s.tree_end;
     if (tb < 0 || tb > te) return "bad tree range";
+    if (f.n_outputs > 8) return "too many outputs";
     out = PackedForest();
     out.n_outputs = f.n_outputs;
+    const bool skl = f.kind == FMC_KIND_SKL;
+    if (s.ninf_row < 0 || s.ninf_row * kFeatBytes >= (1 << (32 - kFeatShift))) return "-inf feature row out of range";
+    const uint32_t ninf_hi = (uint32_t)(s.ninf_row * kFeatBytes) << kFeatShift;
+
+    auto push_slot = [&](uint64_t w, bool node) -> uint32_t {
+        out.slots.push_back(w);
+        out.slot_is_node.push_back(node ? 1 : 0);
+        return (uint32_t)(out.slots.size() - 1);
+    };
+    auto node_word = [&](uint32_t lo, uint32_t feat_hi, uint32_t child_slot) -> uint64_t {
+        return ((uint64_t)(feat_hi | (child_slot * 8u)) << 32) | lo;
+    };
+    // table head: the +0.0 leaf every padding tree ends in.  sklearn: slot 0 is the float64 0.0 and slot j
+    // (1..15) passes through to slot j-1, so a padding tree of a depth-D group starts at slot D.
+    // xgboost: slot 0 is a self-pointing 0.0f leaf.
+    if (skl) {
+        push_slot(f64_bits(0.0), false);
+        for (int j = 1; j <= kMaxGroupDepth; ++j) push_slot(node_word(0, ninf_hi, (uint32_t)(j - 1)), true);
+    } else {
+        push_slot(node_word(f32_bits(0.0f), ninf_hi, 0), true);
+    }
+
     std::vector<std::vector<int>> per_out(f.n_outputs);
-    for (int t = tb; t < te; ++t) per_out[f.out[t]].push_back(t);
+    for (int t = tb; t < te; ++t) {
+        if (f.out[t] < 0 || f.out[t] >= f.n_outputs) return "tree output index out of range";
+        per_out[f.out[t]].push_back(t);
+    }
     size_t rounds = 0;
     for (auto &v : per_out) rounds = v.size() > rounds ? v.size() : rounds;
     out.rounds = (int)rounds;
-    out.rounds_padded = (int)((rounds + kIlp - 1) / kIlp * kIlp);
-    if (out.rounds_padded == 0) out.rounds_padded = kIlp;
-    out.roots.assign((size_t)f.n_outputs * out.rounds_padded * 2, 0);   // padding trees: the +0.0 leaf
 
-    const uint32_t child_cap = 1u << kChildBits;
-    const int feat_cap = 64;
-
-    out.slots.clear();
-    out.slots.push_back(leaf_slot(f.kind, 0.0));  // slot 0: the zero leaf used by padding trees
-    for (auto &r : out.roots) r = 0;
-
-    detail::Builder b(f, s);
-    std::vector<int> order, depth;  // BFS queue of PNode ids, slot of each queued node
+    Builder b(f, s);
+    struct Entry { std::vector<PNode> nodes; int root = -1; int depth = 0; std::vector<uint64_t> pre; };   // root < 0: padding tree
+    std::vector<int> order, depth_q;
     std::vector<uint32_t> slot_of;
+
     for (int k = 0; k < f.n_outputs; ++k) {
+        out.stream_off[k] = (uint32_t)out.stream.size();
+        out.consts_off[k] = (uint32_t)out.consts.size();
+        // ---- trees of this output in order: constants attach to the next walked tree
+        std::vector<Entry> entries;
+        std::vector<uint64_t> pending;
+        auto flush_padding_for_pending = [&]() {   // a run of more than 255 constants needs a padding tree to carry it
+            Entry e;
+            e.pre.swap(pending);
+            entries.push_back(std::move(e));
+        };
         for (size_t j = 0; j < per_out[k].size(); ++j) {
             b.nodes.clear();
-            int root = b.build(f.root[per_out[k][j]]);
-            // breadth-first layout
-            uint32_t root_slot = (uint32_t)out.slots.size();
-            out.slots.push_back(0);
-            order.assign(1, root);
-            slot_of.assign(1, root_slot);
-            depth.assign(1, 0);
-            for (size_t q = 0; q < order.size(); ++q) {
-                const detail::PNode &n = b.nodes[order[q]];
-                uint32_t me = slot_of[q];
-                if (n.leaf) {
-                    if (!(std::fabs(n.value) < 1e60)) return "leaf value out of range for the slot format";
-                    out.slots[me] = leaf_slot(f.kind, n.value);
-                    out.leaves++;
-                    if (depth[q] > out.max_depth) out.max_depth = depth[q];
+            const int root = b.build(f.root[per_out[k][j]]);
+            if (b.nodes[root].leaf) {
+                if (!(std::fabs(b.nodes[root].value) < 1e60)) return "leaf value out of range";
+                if (pending.size() == 255) flush_padding_for_pending();
+                pending.push_back(value_word(f.kind, b.nodes[root].value));
+                out.constants++;
+                continue;
+            }
+            Entry e;
+            e.nodes = b.nodes;
+            e.root = root;
+            e.depth = b.depth_of(root);
+            if (e.depth > kMaxGroupDepth) return "tree deeper than the walk supports (15 levels)";
+            e.pre.swap(pending);
+            entries.push_back(std::move(e));
+        }
+        if (!pending.empty()) flush_padding_for_pending();
+        while (entries.size() % kIlp) entries.push_back(Entry());
+        out.n_groups[k] = (uint32_t)(entries.size() / kIlp);
+
+        // ---- groups
+        for (size_t g = 0; g < entries.size(); g += kIlp) {
+            int D = 0;
+            size_t n_pre = 0;
+            for (int q = 0; q < kIlp; ++q) {
+                if (entries[g + q].depth > D) D = entries[g + q].depth;
+                n_pre += entries[g + q].pre.size();
+            }
+            if (skl && D == 0) D = 1;    // a float64 root cannot carry the group metadata: an all-padding group walks one pass-through level
+            if (D > out.max_depth) out.max_depth = D;
+            const uint32_t first_slot = (uint32_t)out.slots.size();
+            uint64_t rootw[kIlp];
+            bool root_node[kIlp];
+            for (int q = 0; q < kIlp; ++q) {
+                const Entry &e = entries[g + q];
+                if (e.root < 0) {                         // padding tree: D levels down to the +0.0 leaf
+                    rootw[q] = out.slots[skl ? (size_t)D : 0];
+                    root_node[q] = skl ? (D > 0) : true;
                     continue;
                 }
-                uint32_t c = (uint32_t)out.slots.size();
-                if (c + 1 >= child_cap) return "packed table exceeds the child-index range";
-                if (n.row < 0 || n.row >= feat_cap) return "feature row out of range for the table format";
-                out.slots.push_back(0);
-                out.slots.push_back(0);
-                uint32_t lo, hi;
-                std::memcpy(&lo, &n.thr, 4);
-                hi = kInternalTag | ((uint32_t)(n.row * 4) << kChildBits) | c;
-                out.slots[me] = ((uint64_t)hi << 32) | lo;
-                out.internal++;
-                order.push_back(n.l); slot_of.push_back(c); depth.push_back(depth[q] + 1);
-                order.push_back(n.r); slot_of.push_back(c + 1); depth.push_back(depth[q] + 1);
+                // breadth-first layout, children adjacent; the root lives only in the stream
+                order.assign(1, e.root);
+                slot_of.assign(1, 0xFFFFFFFFu);
+                depth_q.assign(1, 0);
+                for (size_t qi = 0; qi < order.size(); ++qi) {
+                    const PNode &n = e.nodes[order[qi]];
+                    uint64_t w;
+                    bool is_node = true;
+                    if (n.leaf) {
+                        if (!(std::fabs(n.value) < 1e60)) return "leaf value out of range";
+                        out.leaves++;
+                        if (skl) {
+                            // pass-through chain so that the float64 is reached after exactly D levels
+                            const int extra = D - depth_q[qi];
+                            if (extra == 0) { w = f64_bits(n.value); is_node = false; }
+                            else {
+                                uint32_t next = push_slot(f64_bits(n.value), false);
+                                for (int x = 1; x < extra; ++x) next = push_slot(node_word(0, ninf_hi, next), true);
+                                w = node_word(0, ninf_hi, next);
+                                out.pass_through += (uint64_t)extra;
+                            }
+                        } else {
+                            // self-pointing leaf; its own slot index is patched below
+                            w = node_word(f32_bits((float)n.value), ninf_hi, slot_of[qi] == 0xFFFFFFFFu ? 0 : slot_of[qi]);
+                        }
+                    } else {
+                        if (n.row < 0 || n.row * kFeatBytes >= (1 << (32 - kFeatShift))) return "feature row out of range for the table format";
+                        const uint32_t c = push_slot(0, true);
+                        push_slot(0, true);
+                        w = node_word(f32_bits(n.thr), (uint32_t)(n.row * kFeatBytes) << kFeatShift, c);
+                        out.internal++;
+                        order.push_back(n.l); slot_of.push_back(c); depth_q.push_back(depth_q[qi] + 1);
+                        order.push_back(n.r); slot_of.push_back(c + 1); depth_q.push_back(depth_q[qi] + 1);
+                    }
+                    if (qi == 0) { rootw[q] = w; root_node[q] = is_node; }
+                    else { out.slots[slot_of[qi]] = w; out.slot_is_node[slot_of[qi]] = is_node ? 1 : 0; }
+                }
             }
-            out.roots[((size_t)k * out.rounds_padded + j) * 2] = (uint32_t)out.slots[root_slot];
-            out.roots[((size_t)k * out.rounds_padded + j) * 2 + 1] = (uint32_t)(out.slots[root_slot] >> 32);
+            if (out.slots.size() * 8 > kWindowBytes) return "packed table exceeds the 1 MiB window of the node format";
+            // ---- group metadata in the three spare low bits of the four child fields
+            const uint32_t bytes = (uint32_t)(out.slots.size() - first_slot) * 8u;
+            uint32_t lines = bytes ? ((first_slot * 8u + bytes + 127u) / 128u - (first_slot * 8u) / 128u) : 0;
+            if (lines > 31) lines = 31;
+            const uint32_t meta[kIlp] = {(uint32_t)D & 7u, (((uint32_t)D >> 3) & 1u) | (n_pre ? 2u : 0u), lines & 7u, (lines >> 3) & 3u};
+            for (int q = 0; q < kIlp; ++q) {
+                if (!root_node[q]) return "internal error: a root slot must be a node";
+                out.stream.push_back(rootw[q] | ((uint64_t)meta[q] << 32));
+                out.stream_is_node.push_back(1);
+            }
+            if (n_pre) {
+                uint64_t cw = 0;
+                for (int q = 0; q < kIlp; ++q) cw |= (uint64_t)entries[g + q].pre.size() << (8 * q);
+                out.consts.push_back(cw);
+                for (int q = 0; q < kIlp; ++q)
+                    for (uint64_t v : entries[g + q].pre) out.consts.push_back(v);
+            }
         }
     }
     return "";

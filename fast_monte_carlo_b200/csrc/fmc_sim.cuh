@@ -37,13 +37,14 @@ constexpr int kNumFam = 6;           // S1, S2, PQ, RQ, SQ, PM  (== model ids 0.
 constexpr int kNumKeys = kNumFam * 2;
 
 struct TableRef {
-    uint32_t slots_off;     // in 8-byte slots, into the global slot buffer
-    uint32_t roots_off;     // in uint4, into the global roots buffer
-    uint16_t rounds_padded;
+    uint32_t win_lo, win_hi;    // address of the 1 MiB window the node table sits in
+    uint32_t stream_off[5];     // per output: first uint4 of its root stream in the global stream buffer
+    uint32_t consts_off[5];     // per output: first uint2 of its constants side stream
+    uint16_t n_groups[5];
     uint8_t n_outputs;
     uint8_t max_depth;
-    float base[5];          // xgb margin offsets (f32-exact) ...
-    double base64[3];       // ... or sklearn init constants
+    float base[5];              // xgb margin offsets (f32-exact) ...
+    double base64[3];           // ... or sklearn init constants
 };
 
 struct MatchupDev {
@@ -56,8 +57,8 @@ struct SimKernelArgs {
     const MatchupDev *matchups;
     int n_matchups;
     unsigned long long *next_game;     // [n_matchups] global work counters (start at game_begin)
-    const uint2 *slots;
-    const uint4 *roots;
+    const uint4 *root_stream;          // root streams of every table (fmc_pack.hpp)
+    const uint2 *consts;               // constants side streams
     uint32_t seed_lo, seed_hi;
     int policy, sampler, stage2_mode;
     float play_temp;
@@ -227,8 +228,13 @@ struct SimShared {
     unsigned long long stat[FMC_N_COUNTERS];
 };
 
+// Requests are kept in 32-request chunks, feature-major ([feature][lane]); every key's list starts on
+// a chunk boundary, so at most kSimThreads/32 + kNumKeys chunks are in use.
+constexpr int kSimChunks = kSimThreads / 32 + kNumKeys;
+constexpr int kChunkFloats = kSimRows * 32;
 constexpr size_t kSimSharedBytes = ((sizeof(SimShared) + 15) / 16) * 16;
-constexpr size_t kSimFeatBytes = (size_t)kSimThreads * kSimStride * 4;   // 61,440: a multiple of 16
+constexpr size_t kSimFeatBytes = (size_t)kSimChunks * kChunkFloats * 4;
+constexpr size_t kSimResultBytes = (size_t)kSimChunks * 32 * 3 * 8;
 
 // keys in processing order, heaviest family first (LPT-style dynamic scheduling):
 // PQ, RQ (1200 depth-3 trees x3 outputs), S2, PM, SQ, S1
@@ -457,10 +463,11 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
     }
 }
 
-// Feature row of a request (FMC:996-1021 `_fill_row`, reduced to the columns that vary inside one
-// orientation).  Rows: 0 down 1 distance 2 yardsToGoal 3 is_red_zone 4 score_diff 5 seconds
-// 6 goal_to_go 7 fourth_and_short 8 fg_range 9 half 10 two_minute 11..13 "B" views of 1, 2, 4.
-__device__ __forceinline__ void write_features(float *row, const Lane &L, int fam, const SimKernelArgs &a) {
+// Feature column of a request (FMC:996-1021 `_fill_row`, reduced to the numerics that vary inside one
+// orientation), written feature-major: col[k * 32] is feature row k of this request.  Rows: 0 down
+// 1 distance 2 yardsToGoal 3 is_red_zone 4 score_diff 5 seconds 6 goal_to_go 7 fourth_and_short
+// 8 fg_range 9 half 10 two_minute 11..13 "B" views of 1, 2, 4; row 14 (-inf) is set once per chunk.
+__device__ __forceinline__ void write_features(float *col, const Lane &L, int fam, const SimKernelArgs &a) {
     const int team = L.offense;
     const int sd = L.score[team] - L.score[team ^ 1];
     float v[6];
@@ -472,37 +479,37 @@ __device__ __forceinline__ void write_features(float *row, const Lane &L, int fa
         for (int k = 0; k < 6; ++k)
             if (a.pm_scaled[k]) v[k] = (float)((raw[k] - a.pm_mean[k]) / a.pm_scale[k]);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) row[k] = v[k];
+        for (int k = 0; k < 6; ++k) col[k * 32] = v[k];
         return;
     }
     const bool zm = fam <= 1;   // CSR-fed boosters: exact zero == missing
     const float inf = __int_as_float(0x7f800000);
-    row[0] = v[0];
-    row[3] = v[3];
-    row[5] = v[5];
-    row[6] = (L.dist >= (L.ytg - 0.5)) ? 1.f : 0.f;
-    row[7] = (L.down == 4 && L.dist <= 2.0) ? 1.f : 0.f;
-    row[8] = (L.ytg <= 33.0) ? 1.f : 0.f;
-    row[9] = (L.sec > 1800) ? 1.f : 2.f;
-    row[10] = ((L.sec % 1800) <= 120) ? 1.f : 0.f;
+    col[0 * 32] = v[0];
+    col[3 * 32] = v[3];
+    col[5 * 32] = v[5];
+    col[6 * 32] = (L.dist >= (L.ytg - 0.5)) ? 1.f : 0.f;
+    col[7 * 32] = (L.down == 4 && L.dist <= 2.0) ? 1.f : 0.f;
+    col[8 * 32] = (L.ytg <= 33.0) ? 1.f : 0.f;
+    col[9 * 32] = (L.sec > 1800) ? 1.f : 2.f;
+    col[10 * 32] = ((L.sec % 1800) <= 120) ? 1.f : 0.f;
     if (zm) {
-        row[1] = v[1] == 0.f ? -inf : v[1]; row[11] = v[1] == 0.f ? inf : v[1];
-        row[2] = v[2] == 0.f ? -inf : v[2]; row[12] = v[2] == 0.f ? inf : v[2];
-        row[4] = v[4] == 0.f ? -inf : v[4]; row[13] = v[4] == 0.f ? inf : v[4];
+        col[1 * 32] = v[1] == 0.f ? -inf : v[1]; col[11 * 32] = v[1] == 0.f ? inf : v[1];
+        col[2 * 32] = v[2] == 0.f ? -inf : v[2]; col[12 * 32] = v[2] == 0.f ? inf : v[2];
+        col[4 * 32] = v[4] == 0.f ? -inf : v[4]; col[13 * 32] = v[4] == 0.f ? inf : v[4];
     } else {
-        row[1] = v[1]; row[2] = v[2]; row[4] = v[4];
+        col[1 * 32] = v[1]; col[2 * 32] = v[2]; col[4 * 32] = v[4];
     }
 }
 
-__device__ __forceinline__ double eval_output(int fam, const TableRef &T, int out, const uint2 *slots_base,
-                                              const uint4 *roots_base, uint32_t frow) {
-    const uint2 *slots = slots_base + T.slots_off;
-    const uint4 *roots = roots_base + T.roots_off + (size_t)out * (T.rounds_padded / 2);
-    if (fam >= 2 && fam <= 4) {
-        if (T.max_depth <= 3) return walk_output<true, 3>(slots, roots, T.rounds_padded, frow, T.base64[out]);
-        return walk_output<true, 99>(slots, roots, T.rounds_padded, frow, T.base64[out]);
-    }
-    return walk_output<false, 99>(slots, roots, T.rounds_padded, frow, (double)T.base[out]);
+__device__ __forceinline__ double eval_output(int fam, const TableRef &T, int out, const SimKernelArgs &a,
+                                              uint32_t fcol, int lane) {
+    ForestView F;
+    F.win_lo = T.win_lo; F.win_hi = T.win_hi;
+    F.stream = a.root_stream + T.stream_off[out];
+    F.consts = a.consts + T.consts_off[out];
+    F.n_groups = T.n_groups[out];
+    if (fam >= 2 && fam <= 4) return walk_output<true>(F, fcol, lane, T.base64[out]);
+    return walk_output<false>(F, fcol, lane, (double)T.base[out]);
 }
 
 __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const SimKernelArgs a) {
@@ -514,6 +521,9 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     const uint32_t feats_saddr = (uint32_t)__cvta_generic_to_shared(feats);
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    // the -inf feature row of every chunk (leaves keep lanes in place by testing it, fmc_pack.hpp)
+    for (int i = tid; i < kSimChunks * 32; i += kSimThreads)
+        feats[(size_t)(i >> 5) * kChunkFloats + kSimNinfRow * 32 + (i & 31)] = __int_as_float(0xff800000);
     if (tid < FMC_N_COUNTERS) sh.stat[tid] = 0ULL;
     if (tid < kNumKeys) { sh.cnt[0][tid] = 0; sh.cnt[1][tid] = 0; }
     if (tid == 0) sh.cur_matchup = -1;
@@ -569,7 +579,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
                     const int k = kKeyOrder[j];
                     const unsigned int c = sh.cnt[parity][k];
                     sh.off[k] = o;
-                    o += c;
+                    o += (c + 31u) & ~31u;          // lists start on chunk boundaries
                     sh.item_prefix[j] = it;
                     it += ((c + 31u) >> 5) * (unsigned int)splits_of(k >> 1);
                 }
@@ -580,7 +590,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
             __syncthreads();
             if (key >= 0) {
                 pos = (int)(sh.off[key] + rank);
-                write_features(feats + (size_t)pos * kSimStride, L, key >> 1, a);
+                write_features(feats + (size_t)(pos >> 5) * kChunkFloats + (pos & 31), L, key >> 1, a);
             }
             __syncthreads();
             // ---- C: evaluate.  Work item = (key, chunk of 32 requests, output)
@@ -601,9 +611,9 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
                 const unsigned int c = sh.cnt[parity][k];
                 const unsigned int idx = chunk * 32u + (unsigned int)lane;
                 const bool live = idx < c;
-                const unsigned int p = sh.off[k] + (live ? idx : chunk * 32u);
-                const double v = eval_output(fam, sh.M.tbl[fam][k & 1], out, a.slots, a.roots,
-                                             feats_saddr + p * (uint32_t)(kSimStride * 4));
+                const unsigned int p = sh.off[k] + idx;      // idle lanes walk whatever their column holds
+                const double v = eval_output(fam, sh.M.tbl[fam][k & 1], out, a,
+                                             feats_saddr + (p >> 5) * (uint32_t)(kChunkFloats * 4) + (uint32_t)lane * 4u, lane);
                 if (live) {
                     if (fam >= 2 && fam <= 4) results[(size_t)p * 3 + out] = v;
                     else reinterpret_cast<float *>(results + (size_t)p * 3)[out] = (float)v;
@@ -622,6 +632,6 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     if (a.counters && tid < FMC_N_COUNTERS && sh.stat[tid]) atomicAdd(&a.counters[tid], sh.stat[tid]);
 }
 
-inline size_t sim_smem_bytes() { return kSimSharedBytes + kSimFeatBytes + (size_t)kSimThreads * 3 * 8; }
+inline size_t sim_smem_bytes() { return kSimSharedBytes + kSimFeatBytes + kSimResultBytes; }
 
 }  // namespace fmc

@@ -103,7 +103,7 @@ def load_library():
     L.fmc_pack_forest_host.restype = C.c_int64
     L.fmc_pack_forest_host.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
-                                       C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+                                       C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     _lib = L
     return L
 
@@ -147,7 +147,8 @@ def forest_desc(f) -> tuple:
 
 
 def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begin=0, tree_end=-1):
-    """Host-only: run the specialiser/packer and return (slots u64[], roots u32[], info dict).
+    """Host-only: run the specialiser/packer and return (slots u64[], stream u64[], consts u64[], info dict)
+    -- the node table, the root stream and the constants side stream of csrc/fmc_pack.hpp.
     Evaluates nothing; used by the CPU tests and for table-size accounting."""
     L = load_library()
     d, keep = forest_desc(f)
@@ -161,21 +162,27 @@ def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begi
         sm = np.ascontiguousarray(f.scaler_mean, np.float64)
         ss = np.ascontiguousarray(f.scaler_scale, np.float64)
         ns = int(sc.shape[0])
-    info = np.zeros(6, dtype=np.int32)
-    cap_s = int(f.n_nodes) + 8
-    cap_r = 4 * int(f.n_trees) + 64 * int(f.n_outputs)
+    info = np.zeros(32, dtype=np.int32)
+    cap_s = 16 * int(f.n_nodes) + 64                    # pass-through chains can outnumber the original nodes
+    cap_r = int(f.n_trees) + 8 * int(f.n_outputs) + 64
+    cap_c = 2 * int(f.n_trees) + 64
     slots = np.zeros(cap_s, dtype=np.uint64)
-    roots = np.zeros(cap_r, dtype=np.uint32)
+    stream = np.zeros(cap_r, dtype=np.uint64)
+    consts = np.zeros(cap_c, dtype=np.uint64)
     n = L.fmc_pack_forest_host(
         C.byref(d), int(mode), int(cols[0]), int(cols[1]), fv.ctypes.data, ns,
         None if sc is None else sc.ctypes.data, None if sm is None else sm.ctypes.data,
         None if ss is None else ss.ctypes.data, int(tree_begin), int(tree_end),
-        slots.ctypes.data, cap_s, roots.ctypes.data, cap_r, info.ctypes.data)
+        slots.ctypes.data, cap_s, stream.ctypes.data, cap_r, consts.ctypes.data, cap_c, info.ctypes.data)
     if n < 0:
         _check(int(n))
-    meta = dict(rounds=int(info[0]), rounds_padded=int(info[1]), max_depth=int(info[2]), n_outputs=int(info[3]),
-                ilp=int(info[4]), root_words=int(info[5]))
-    return slots[:n].copy(), roots[:meta["rounds_padded"] * 2 * meta["n_outputs"]].copy(), meta
+    if n > cap_s or int(info[5]) > cap_r or int(info[6]) > cap_c:
+        raise FmcError("pack_forest_host: capacity estimate too small")
+    meta = dict(rounds=int(info[0]), max_depth=int(info[1]), n_outputs=int(info[2]), ilp=int(info[3]),
+                ninf_row=int(info[4]), constants=int(info[7]),
+                stream_off=[int(x) for x in info[8:16]], n_groups=[int(x) for x in info[16:24]],
+                consts_off=[int(x) for x in info[24:32]])
+    return slots[:n].copy(), stream[:int(info[5])].copy(), consts[:int(info[6])].copy(), meta
 
 
 class Context:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FMC_ABI_VERSION 1
+#define FMC_ABI_VERSION 2
 
 typedef enum {
     FMC_OK = 0,
@@ -171,18 +171,20 @@ int fmc_packed_slots(fmc_ctx *ctx, int32_t m, int32_t *out);
 
 int fmc_sync(fmc_ctx *ctx);
 
-/* Host-only, needs no context and no GPU: runs the forest specialiser/packer and returns the
- * 8-byte slot table the kernels walk (layout: fast_monte_carlo_b200/csrc/fmc_pack.hpp).  It
- * evaluates nothing; CPU tests walk the returned slots themselves, and DESIGN.md's table-size
+/* Host-only, needs no context and no GPU: runs the forest specialiser/packer and returns the node
+ * table, the root stream and the constants side stream the kernels walk (layout:
+ * fast_monte_carlo_b200/csrc/fmc_pack.hpp; child offsets relative to the table start).  It
+ * evaluates nothing; CPU tests walk the returned tables themselves, and DESIGN.md's table-size
  * figures come from it.  mode 0 = simulation preset (numerics 6..11 folded to fold_value17[]),
  * 1 = predict preset.  Returns the slot count (>= 0) or a negative fmc_status; buffers that are too
- * small are left untouched.  info_out[6] = {rounds, rounds_padded, max_depth, n_outputs, trees per
- * group, root words per group}. */
+ * small are left untouched.  info_out[32] = {rounds, max group depth, n_outputs, trees per group,
+ * "-inf" feature row, stream words, side-stream words, constant trees, stream_off[8] (8-byte words),
+ * n_groups[8], consts_off[8]}. */
 int64_t fmc_pack_forest_host(const fmc_forest_desc *desc, int32_t mode, int32_t col0, int32_t col1,
                              const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
                              const double *scaler_mean, const double *scaler_scale, int32_t tree_begin,
-                             int32_t tree_end, uint64_t *slots_out, int64_t slots_cap, uint32_t *roots_out,
-                             int64_t roots_cap, int32_t *info_out);
+                             int32_t tree_end, uint64_t *slots_out, int64_t slots_cap, uint64_t *stream_out,
+                             int64_t stream_cap, uint64_t *consts_out, int64_t consts_cap, int32_t *info_out);
 
 #ifdef __cplusplus
 }

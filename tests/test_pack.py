@@ -43,8 +43,8 @@ def _setup(models_s2, name, player="Unknown"):
 def test_predict_preset(models_s2, native_lib, name):
     f, cols, skl, zm, scaler = _setup(models_s2, name)
     num = _rows(96, 1)[:, :f.n_num]
-    slots, roots, meta = native.pack_forest_host(f, mode=1, cols=cols)
-    got = pw.walk(slots, roots, meta, pw.predict_rows(num, zm, scaler), skl, 5, f.base_margin)
+    slots, stream, consts, meta = native.pack_forest_host(f, mode=1, cols=cols)
+    got = pw.walk(slots, stream, consts, meta, pw.predict_rows(num, zm, scaler), skl, f.base_margin)
     x = to.play_model_features(f, num) if scaler else num
     ref = to.raw_margin(f, x, np.tile(np.array(cols), (num.shape[0], 1)))
     assert np.array_equal(got, ref)
@@ -59,13 +59,13 @@ def test_sim_preset_folds_orientation_constants(models_s2, native_lib, name, off
     fv[6] = fv[7] = 3.0
     fv[8], fv[9], fv[10], fv[11] = off[0], off[1], de[2], de[0]
     num[:, 6:12] = fv[6:12]
-    slots, roots, meta = native.pack_forest_host(f, mode=0, cols=cols, fold_values=fv)
-    got = pw.walk(slots, roots, meta, pw.sim_rows(num, zm, scaler), skl, 4, f.base_margin)
+    slots, stream, consts, meta = native.pack_forest_host(f, mode=0, cols=cols, fold_values=fv)
+    got = pw.walk(slots, stream, consts, meta, pw.sim_rows(num, zm, scaler), skl, f.base_margin)
     x = to.play_model_features(f, num) if scaler else num
     ref = to.raw_margin(f, x, np.tile(np.array(cols), (num.shape[0], 1)))
     assert np.array_equal(got, ref)
-    # specialisation must shrink the table, never grow it
-    assert len(slots) <= f.n_nodes + 1
+    # specialisation must shrink the table (pass-through chains included), never grow it
+    assert len(slots) <= f.n_nodes + 16
 
 
 def test_tree_range_and_named_player(models_s2, native_lib):
@@ -74,17 +74,29 @@ def test_tree_range_and_named_player(models_s2, native_lib):
     col = f.groups[0].column_of("Caleb Williams")
     assert col == 82
     num = _rows(40, 3)
-    slots, roots, meta = native.pack_forest_host(f, mode=1, cols=(col, -1), tree_begin=0, tree_end=68)
+    slots, stream, consts, meta = native.pack_forest_host(f, mode=1, cols=(col, -1), tree_begin=0, tree_end=68)
     assert meta["rounds"] == 68
-    got = pw.walk(slots, roots, meta, pw.predict_rows(num, zm, None), skl, 5, f.base_margin)
+    got = pw.walk(slots, stream, consts, meta, pw.predict_rows(num, zm, None), skl, f.base_margin)
     ref = to.raw_margin(f, num, np.tile(np.array([col, -1]), (40, 1)), 0, 68)
     assert np.array_equal(got, ref)
 
 
-def test_padding_trees_are_exact_zero(models_s2, native_lib):
-    f = models_s2["pass_yards"]
-    slots, roots, meta = native.pack_forest_host(f, mode=1, cols=(491, 2877))
-    il = meta["ilp"]
-    assert meta["rounds"] == 400 and meta["rounds_padded"] == -(-400 // il) * il
-    r = roots.reshape(3, meta["rounds_padded"], 2)
-    assert np.all(r[:, 400:] == 0) and slots[0] == 0      # padding trees are the +0.0 leaf
+def test_constant_trees_and_group_padding(models_s2, native_lib):
+    """Trees that fold to one leaf leave the walk (they become ordered constants); the last group of an
+    output is completed with padding trees that end in the +0.0 leaf."""
+    f = models_s2["sack_yards"]
+    fv = np.zeros(17)
+    fv[6] = fv[7] = 3.0
+    fv[8], fv[9], fv[10], fv[11] = KSU[0], KSU[1], ISU[2], ISU[0]
+    cols = [g.column_of("Unknown") for g in f.groups] + [-1, -1]
+    slots, stream, consts, meta = native.pack_forest_host(f, mode=0, cols=cols[:2], fold_values=fv)
+    assert meta["rounds"] == 400 and meta["ilp"] == 4
+    walked = 4 * sum(meta["n_groups"][:3])
+    assert meta["constants"] > 0 and meta["constants"] + walked >= 1200 and walked < 1200
+    assert len(stream) == walked
+    assert slots[0] == 0                                  # the +0.0 float64 leaf every padding tree ends in
+    # a model with nothing to fold keeps every tree
+    f1 = models_s2["pass_yards"]
+    cols1 = [g.column_of("Unknown") for g in f1.groups] + [-1, -1]
+    _, stream1, _, meta1 = native.pack_forest_host(f1, mode=1, cols=cols1[:2])
+    assert meta1["constants"] + len(stream1) >= 1200
