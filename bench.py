@@ -148,7 +148,7 @@ def measured_peaks():
 
 def ncu_traffic():
     """dram bytes per launch of sim_kernel from the committed ncu --set full capture, if any."""
-    p = os.path.join(ROOT, "profiles", "sim_kernel_ncu_summary.json")
+    p = os.path.join(ROOT, "profiles", "sim_kernel_ncu_latest.json")
     if os.path.exists(p):
         try:
             return json.load(open(p)).get("dram_bytes_per_launch")
@@ -337,6 +337,14 @@ def run_ours(args):
     e2e_value = e2e_plays / e2e_t if e2e_t > 0 else None
 
     if rank == 0:
+        # achievable gather rates on this GPU (8-byte dependent gathers, fmc_gather_probe): the denominators the
+        # north star asks for ("tree-eval kernels as a fraction of achievable L2 bandwidth")
+        try:
+            l1_gbs = eng.ctx.gather_probe(64 << 10, 4000)
+            l2_gbs = eng.ctx.gather_probe(8 << 20, 1000)
+        except Exception as exc:                       # pragma: no cover
+            l1_gbs = l2_gbs = None
+            print(f"gather probe failed: {exc}", file=sys.stderr)
         peak, peak_src = measured_peaks()
         algo = step_algorithmic_bytes(ms, step_counters, args.stage2 == "synthetic") / world   # per launch (one GPU)
         kern_s = (kernel_ms / args.steps) / 1e3
@@ -361,6 +369,16 @@ def run_ours(args):
                 "note": "algorithmic bytes = SURVEY 8(d) per-row figures on the unpruned forests x requests per "
                         "family; the node tables are L1/L2-resident by design, so this gather traffic never reaches "
                         "HBM and frac can exceed 1 -- DRAM traffic proper is `traffic`",
+            },
+            "gather": {
+                "node_slots_gathered_per_launch": step_counters["visits"] / world,
+                "achieved_gbs": step_counters["visits"] / world * 8.0 / kern_s / 1e9,
+                "probe_l1_gbs": l1_gbs, "probe_l2_gbs": l2_gbs,
+                "frac_of_l2_probe": (step_counters["visits"] / world * 8.0 / kern_s / 1e9 / l2_gbs) if l2_gbs else None,
+                "frac_of_l1_probe": (step_counters["visits"] / world * 8.0 / kern_s / 1e9 / l1_gbs) if l1_gbs else None,
+                "note": "8 B x node slots actually gathered by live requests on the SPECIALISED tables (counter "
+                        "FMC_C_VISITS) / kernel time, against fmc_gather_probe: dependent 8-byte read-only gathers "
+                        "through a 64 KiB (L1-resident) and an 8 MiB (L2-resident) random cyclic table",
             },
             "mix": {k: step_counters[k] for k in ("pass", "comp", "inc", "int", "sack", "run", "td", "fga", "fg", "punt", "go")},
             "device": eng.ctx.device_name,

@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs
             F.stream = a.stream + a.stream_off[o];
             F.consts = a.consts + a.consts_off[o];
             F.n_groups = a.n_groups[o];
-            const double v = walk_output<SKL>(F, fcol, lane, a.base[o]);
+            uint32_t levels;
+            const double v = walk_output<SKL>(F, fcol, lane, a.base[o], levels);
             if (live) a.out[(base + tid) * a.n_outputs + o] = v;
         }
         __syncthreads();
@@ -536,6 +537,77 @@ extern "C" int fmc_sync(fmc_ctx *c) {
     if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(c->device));
     CK(cudaDeviceSynchronize());
+    return FMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Achievable gather bandwidth (the roofline denominator SURVEY 8(d) asks for): every lane runs
+// kProbeChains dependent chains of 8-byte read-only gathers through a table of `table_bytes`
+// (each slot holds the index of the next one: a random cyclic permutation), the access pattern of a
+// tree walk with no arithmetic around it.  table_bytes well below the L1 size measures the L1 gather
+// rate, a few MiB the L2 gather rate.
+// ---------------------------------------------------------------------------------------------
+constexpr int kProbeChains = 8;
+__global__ void __launch_bounds__(1024, 1) gather_probe_kernel(const uint2 *__restrict__ tbl, uint32_t n_slots, int iters,
+                                                              unsigned int *sink) {
+    uint32_t idx[kProbeChains];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) idx[c] = (t * 2654435761u + (uint32_t)c * 40503u) % n_slots;
+    uint32_t acc = 0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kProbeChains; ++c) {
+            const uint2 v = __ldg(tbl + idx[c]);
+            idx[c] = v.x;
+            acc ^= v.y;
+        }
+    }
+    if (acc == 0x12345678u) atomicAdd(sink, 1u);
+}
+
+extern "C" int fmc_gather_probe(fmc_ctx *c, int64_t table_bytes, int32_t iters, double *gbytes_per_s) {
+    if (!c || !gbytes_per_s || table_bytes < 1024 || iters <= 0) return fail(FMC_ERR_INVALID, "fmc_gather_probe: bad argument");
+    CK(cudaSetDevice(c->device));
+    const uint32_t n = (uint32_t)(table_bytes / 8);
+    std::vector<uint2> h(n);
+    // random cyclic permutation (Sattolo) so that every chain visits the whole table
+    std::vector<uint32_t> perm(n);
+    for (uint32_t i = 0; i < n; ++i) perm[i] = i;
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    for (uint32_t i = n - 1; i > 0; --i) {
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        const uint32_t j = (uint32_t)((s >> 33) % i);
+        std::swap(perm[i], perm[j]);
+    }
+    for (uint32_t i = 0; i < n; ++i) h[i] = make_uint2(perm[i], i);
+    uint2 *d = nullptr;
+    unsigned int *sink = nullptr;
+    CK(cudaMalloc(&d, (size_t)n * 8));
+    cudaError_t e = cudaMalloc(&sink, 4);
+    if (e != cudaSuccess) { cudaFree(d); return fail(FMC_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaMemcpy(d, h.data(), (size_t)n * 8, cudaMemcpyHostToDevice);
+    cudaMemset(sink, 0, 4);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = c->prop.multiProcessorCount;
+    gather_probe_kernel<<<grid, 1024>>>(d, n, iters / 4 + 1, sink);      // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        cudaEventRecord(e0);
+        gather_probe_kernel<<<grid, 1024>>>(d, n, iters, sink);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d); cudaFree(sink);
+    if (e != cudaSuccess) return fail(FMC_ERR_CUDA, std::string("gather_probe_kernel: ") + cudaGetErrorString(e));
+    const double loads = (double)grid * 1024.0 * kProbeChains * (double)iters;
+    *gbytes_per_s = loads * 8.0 / ((double)best * 1e-3) / 1e9;
     return FMC_OK;
 }
 

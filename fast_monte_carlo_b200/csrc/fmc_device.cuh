@@ -151,36 +151,133 @@ __device__ __forceinline__ void walk_step(uint2 &n, uint32_t fcol, uint32_t win_
 }
 
 #ifndef FMC_PREFETCH
-#define FMC_PREFETCH 1
+#define FMC_PREFETCH 0      // 1: CCTL.PF1 the next group's node lines, 2: touch them with a plain load
 #endif
+#ifndef FMC_GROUPS_IN_FLIGHT
+#define FMC_GROUPS_IN_FLIGHT 2
+#endif
+
+// Adds the leaves the lanes hold after a group's walk (plus the group's constants) in tree order.
+template <bool SKL>
+__device__ __forceinline__ void accumulate_group(const uint2 (&n)[kIlp], bool has_consts, const uint2 *&cp,
+                                                 double &acc64, float &acc32) {
+    if (!has_consts) {
+#pragma unroll
+        for (int i = 0; i < kIlp; ++i) {
+            if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)n[i].y, (int)n[i].x));
+            else acc32 = __fadd_rn(acc32, __uint_as_float(n[i].x));
+        }
+        return;
+    }
+    // constants (trees folded to one leaf) take their place in the tree order
+    const uint32_t counts = __ldg(cp).x;
+    ++cp;
+#pragma unroll
+    for (int i = 0; i < kIlp; ++i) {
+        const uint32_t c = (counts >> (8 * i)) & 0xFFu;
+        for (uint32_t j = 0; j < c; ++j) {
+            const uint2 v = __ldg(cp);
+            ++cp;
+            if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)v.y, (int)v.x));
+            else acc32 = __fadd_rn(acc32, __uint_as_float(v.x));
+        }
+        if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)n[i].y, (int)n[i].x));
+        else acc32 = __fadd_rn(acc32, __uint_as_float(n[i].x));
+    }
+}
+
+__device__ __forceinline__ void load_roots(const uint4 *sp, uint2 (&n)[kIlp]) {
+    const uint4 a = __ldg(sp), b = __ldg(sp + 1);
+    n[0] = make_uint2(a.x, a.y); n[1] = make_uint2(a.z, a.w);
+    n[2] = make_uint2(b.x, b.y); n[3] = make_uint2(b.z, b.w);
+}
+__device__ __forceinline__ uint32_t group_depth(const uint2 (&n)[kIlp]) { return (n[0].y & 7u) | ((n[1].y & 1u) << 3); }
+__device__ __forceinline__ bool group_has_consts(const uint2 (&n)[kIlp]) { return (n[1].y & 2u) != 0; }
 
 // Sum one output of a packed forest in tree order.  SKL: float64 accumulate of pre-scaled leaves;
 // XGB: float32 accumulate (returned widened).
+// `levels` returns the number of tree levels the walk issued per tree slot (sum of the group depths).
 template <bool SKL>
-__device__ __forceinline__ double walk_output(const ForestView &F, uint32_t fcol, int lane, double base) {
+__device__ __forceinline__ double walk_output(const ForestView &F, uint32_t fcol, int lane, double base, uint32_t &levels) {
     constexpr int I = kIlp;
     double acc64 = base;
     float acc32 = (float)base;
+    levels = 0;
     if (F.n_groups == 0) return SKL ? acc64 : (double)acc32;
     const uint4 *sp = F.stream;
     const uint2 *cp = F.consts;
-    uint2 n[I];
-    {
-        const uint4 a = __ldg(sp), b = __ldg(sp + 1);
-        n[0] = make_uint2(a.x, a.y); n[1] = make_uint2(a.z, a.w);
-        n[2] = make_uint2(b.x, b.y); n[3] = make_uint2(b.z, b.w);
+#if FMC_GROUPS_IN_FLIGHT == 2
+    // Two groups (2 x kIlp trees) in flight per lane: both are walked together for the depth they share
+    // (8 independent gather chains, no branch inside), then the deeper one finishes alone -- a sklearn
+    // lane must not step past its float64 leaf.  The roots are fetched at the top of each pass.
+    uint32_t g = 0;
+#pragma unroll 1
+    for (; g + 1 < F.n_groups; g += 2) {
+        uint2 n0[I], n1[I];
+        load_roots(sp + 2 * g, n0);
+        load_roots(sp + 2 * g + 2, n1);
+        const uint32_t d0 = group_depth(n0), d1 = group_depth(n1);
+        const bool c0 = group_has_consts(n0), c1 = group_has_consts(n1);   // the metadata leaves with the root slots
+        const uint32_t dmin = d0 < d1 ? d0 : d1, dmax = d0 < d1 ? d1 : d0;
+        levels += d0 + d1;
+#pragma unroll 1
+        for (uint32_t d = 0; d < dmin; ++d) {
+#pragma unroll
+            for (int i = 0; i < I; ++i) walk_step<SKL>(n0[i], fcol, F.win_lo, F.win_hi);
+#pragma unroll
+            for (int i = 0; i < I; ++i) walk_step<SKL>(n1[i], fcol, F.win_lo, F.win_hi);
+        }
+        if (d0 > d1) {
+#pragma unroll 1
+            for (uint32_t d = dmin; d < dmax; ++d)
+#pragma unroll
+                for (int i = 0; i < I; ++i) walk_step<SKL>(n0[i], fcol, F.win_lo, F.win_hi);
+        } else {
+#pragma unroll 1
+            for (uint32_t d = dmin; d < dmax; ++d)
+#pragma unroll
+                for (int i = 0; i < I; ++i) walk_step<SKL>(n1[i], fcol, F.win_lo, F.win_hi);
+        }
+        accumulate_group<SKL>(n0, c0, cp, acc64, acc32);
+        accumulate_group<SKL>(n1, c1, cp, acc64, acc32);
     }
+    if (g < F.n_groups) {
+        uint2 n0[I];
+        load_roots(sp + 2 * g, n0);
+        const uint32_t d0 = group_depth(n0);
+        const bool c0 = group_has_consts(n0);
+        levels += d0;
+#pragma unroll 1
+        for (uint32_t d = 0; d < d0; ++d)
+#pragma unroll
+            for (int i = 0; i < I; ++i) walk_step<SKL>(n0[i], fcol, F.win_lo, F.win_hi);
+        accumulate_group<SKL>(n0, c0, cp, acc64, acc32);
+    }
+    (void)lane;
+#else
+    uint2 n[I];
+    load_roots(sp, n);
+#if FMC_PREFETCH == 2
+    uint32_t touched = 0;
+#endif
 #pragma unroll 1
     for (uint32_t g = 0; g < F.n_groups; ++g) {
         // the next group's roots arrive while this group is walked
         const uint4 *nx = sp + 2 * (g + 1 < F.n_groups ? g + 1 : g);
         const uint4 xa = __ldg(nx), xb = __ldg(nx + 1);
-        const uint32_t depth = (n[0].y & 7u) | ((n[1].y & 1u) << 3);
-        const bool has_consts = (n[1].y & 2u) != 0;
+        const uint32_t depth = group_depth(n);
+        const bool has_consts = group_has_consts(n);
+        levels += depth;
 #if FMC_PREFETCH
+        uint32_t pf = 0;
         {   // pull the next group's node lines into L1 ahead of its walk
             const uint32_t lines = (xb.y & 7u) | ((xb.w & 3u) << 3);
-            if ((uint32_t)lane < lines) prefetch_l1((((xa.y & kChildMask) | F.win_lo) & ~127u) + 128u * (uint32_t)lane, F.win_hi);
+            const uint32_t a = (((xa.y & kChildMask) | F.win_lo) & ~127u) + 128u * (uint32_t)lane;
+#if FMC_PREFETCH == 1
+            if ((uint32_t)lane < lines) prefetch_l1(a, F.win_hi);
+#else
+            if ((uint32_t)lane < lines) pf = ldg_slot(a, F.win_hi).x;
+#endif
         }
 #endif
 #pragma unroll 1
@@ -188,32 +285,18 @@ __device__ __forceinline__ double walk_output(const ForestView &F, uint32_t fcol
 #pragma unroll
             for (int i = 0; i < I; ++i) walk_step<SKL>(n[i], fcol, F.win_lo, F.win_hi);
         }
-        if (!has_consts) {
-#pragma unroll
-            for (int i = 0; i < I; ++i) {
-                if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)n[i].y, (int)n[i].x));
-                else acc32 = __fadd_rn(acc32, __uint_as_float(n[i].x));
-            }
-        } else {
-            // constants (trees folded to one leaf) take their place in the tree order
-            const uint32_t counts = __ldg(cp).x;
-            ++cp;
-#pragma unroll
-            for (int i = 0; i < I; ++i) {
-                const uint32_t c = (counts >> (8 * i)) & 0xFFu;
-                for (uint32_t j = 0; j < c; ++j) {
-                    const uint2 v = __ldg(cp);
-                    ++cp;
-                    if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)v.y, (int)v.x));
-                    else acc32 = __fadd_rn(acc32, __uint_as_float(v.x));
-                }
-                if (SKL) acc64 = __dadd_rn(acc64, __hiloint2double((int)n[i].y, (int)n[i].x));
-                else acc32 = __fadd_rn(acc32, __uint_as_float(n[i].x));
-            }
-        }
+        accumulate_group<SKL>(n, has_consts, cp, acc64, acc32);
+#if FMC_PREFETCH == 2
+        touched ^= pf;
+#endif
         n[0] = make_uint2(xa.x, xa.y); n[1] = make_uint2(xa.z, xa.w);
         n[2] = make_uint2(xb.x, xb.y); n[3] = make_uint2(xb.z, xb.w);
     }
+#if FMC_PREFETCH == 2
+    if (touched == 0x9e3779b9u && F.n_groups == 0xFFFFFFFFu) acc32 += 1.0f;   // keeps the touches alive; never true
+#endif
+    (void)lane;
+#endif
     return SKL ? acc64 : (double)acc32;
 }
 

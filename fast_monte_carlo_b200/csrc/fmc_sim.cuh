@@ -502,14 +502,14 @@ __device__ __forceinline__ void write_features(float *col, const Lane &L, int fa
 }
 
 __device__ __forceinline__ double eval_output(int fam, const TableRef &T, int out, const SimKernelArgs &a,
-                                              uint32_t fcol, int lane) {
+                                              uint32_t fcol, int lane, uint32_t &levels) {
     ForestView F;
     F.win_lo = T.win_lo; F.win_hi = T.win_hi;
     F.stream = a.root_stream + T.stream_off[out];
     F.consts = a.consts + T.consts_off[out];
     F.n_groups = T.n_groups[out];
-    if (fam >= 2 && fam <= 4) return walk_output<true>(F, fcol, lane, T.base64[out]);
-    return walk_output<false>(F, fcol, lane, (double)T.base[out]);
+    if (fam >= 2 && fam <= 4) return walk_output<true>(F, fcol, lane, T.base64[out], levels);
+    return walk_output<false>(F, fcol, lane, (double)T.base[out], levels);
 }
 
 __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const SimKernelArgs a) {
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
 
     Lane L;
     L.stage = ST_IDLE;
-    unsigned long long rounds = 0, requests = 0;
+    unsigned long long rounds = 0, requests = 0, visits = 0;
 
     for (int visit = 0;; ++visit) {
         // ---- pick the next matchup that still has games; CTAs start at different matchups so that a
@@ -612,8 +612,10 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
                 const unsigned int idx = chunk * 32u + (unsigned int)lane;
                 const bool live = idx < c;
                 const unsigned int p = sh.off[k] + idx;      // idle lanes walk whatever their column holds
+                uint32_t levels;
                 const double v = eval_output(fam, sh.M.tbl[fam][k & 1], out, a,
-                                             feats_saddr + (p >> 5) * (uint32_t)(kChunkFloats * 4) + (uint32_t)lane * 4u, lane);
+                                             feats_saddr + (p >> 5) * (uint32_t)(kChunkFloats * 4) + (uint32_t)lane * 4u, lane, levels);
+                visits += (unsigned long long)levels * (live ? kIlp : 0);
                 if (live) {
                     if (fam >= 2 && fam <= 4) results[(size_t)p * 3 + out] = v;
                     else reinterpret_cast<float *>(results + (size_t)p * 3)[out] = (float)v;
@@ -627,6 +629,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     }
     // ---- flush counters
     atomicAdd(&sh.stat[FMC_C_REQUESTS], requests);
+    atomicAdd(&sh.stat[FMC_C_VISITS], visits);
     if (tid == 0) sh.stat[FMC_C_ROUNDS] = rounds;
     __syncthreads();
     if (a.counters && tid < FMC_N_COUNTERS && sh.stat[tid]) atomicAdd(&a.counters[tid], sh.stat[tid]);

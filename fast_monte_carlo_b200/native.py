@@ -22,7 +22,7 @@ N_SLOTS = 16
 MAX_ITERS = 360
 TRACE_COLS = 8
 COUNTER_NAMES = ("games", "plays", "iters", "pass", "comp", "inc", "int", "sack", "run", "td", "fga", "fg",
-                 "punt", "go", "hist_overflow", "rounds", "requests")
+                 "punt", "go", "hist_overflow", "rounds", "requests", "visits")
 
 
 class FmcError(RuntimeError):
@@ -100,6 +100,7 @@ def load_library():
                                         C.c_int32, C.c_int32]
     L.fmc_packed_slots.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
     L.fmc_sync.argtypes = [C.c_void_p]
+    L.fmc_gather_probe.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_double)]
     L.fmc_pack_forest_host.restype = C.c_int64
     L.fmc_pack_forest_host.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
@@ -112,6 +113,7 @@ EXPORTED_SYMBOLS = (
     "fmc_last_error", "fmc_abi_version", "fmc_create", "fmc_destroy", "fmc_device_info", "fmc_load_forest",
     "fmc_set_scaler", "fmc_set_active_columns", "fmc_set_params", "fmc_set_matchups", "fmc_simulate",
     "fmc_simulate_host", "fmc_tree_predict", "fmc_tree_predict_host", "fmc_packed_slots", "fmc_sync",
+    "fmc_gather_probe",
     "fmc_pack_forest_host",
 )
 
@@ -316,3 +318,9 @@ class Context:
 
     def sync(self) -> None:
         _check(self._L.fmc_sync(self._h))
+
+    def gather_probe(self, table_bytes: int, iters: int = 2000) -> float:
+        """GB/s of dependent 8-byte gathers through a cache-resident table (roofline denominator)."""
+        v = C.c_double()
+        _check(self._L.fmc_gather_probe(self._h, int(table_bytes), int(iters), C.byref(v)))
+        return float(v.value)

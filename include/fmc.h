@@ -102,7 +102,8 @@ typedef struct {
 enum {
     FMC_C_GAMES = 0, FMC_C_PLAYS, FMC_C_ITERS, FMC_C_PASS, FMC_C_COMP, FMC_C_INC, FMC_C_INT, FMC_C_SACK,
     FMC_C_RUN, FMC_C_TD, FMC_C_FGA, FMC_C_FG, FMC_C_PUNT, FMC_C_GO, FMC_C_HIST_OVERFLOW,
-    FMC_C_ROUNDS, FMC_C_REQUESTS
+    FMC_C_ROUNDS, FMC_C_REQUESTS,
+    FMC_C_VISITS /* 8-byte node slots gathered for live requests (tree levels walked x lanes) */
 };
 
 #define FMC_N_SLOTS 16           /* injected-draw record per (game, loop iteration); see DESIGN.md */
@@ -170,6 +171,12 @@ int fmc_tree_predict_host(fmc_ctx *ctx, int32_t model_id, const double *rows_hos
 int fmc_packed_slots(fmc_ctx *ctx, int32_t m, int32_t *out);
 
 int fmc_sync(fmc_ctx *ctx);
+
+/* Measurement helper for the roofline: achievable rate of dependent 8-byte read-only
+ * gathers through a random cyclic table of `table_bytes` (L1-resident when small, L2-resident at a
+ * few MiB), 8 chains per lane, one 1024-lane CTA per SM -- a tree walk with nothing around it.
+ * Synchronous; returns GB/s of gathered slots (8 bytes each). */
+int fmc_gather_probe(fmc_ctx *ctx, int64_t table_bytes, int32_t iters, double *gbytes_per_s);
 
 /* Host-only, needs no context and no GPU: runs the forest specialiser/packer and returns the node
  * table, the root stream and the constants side stream the kernels walk (layout:
