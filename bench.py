@@ -44,7 +44,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--games", type=int, default=10_000_000, help="games per GPU per step")
+    ap.add_argument("--games", type=int, default=10_000_000, help="games per GPU per step (matchup workload)")
+    ap.add_argument("--workload", default="matchup", choices=["matchup", "slate"],
+                    help="matchup = BASELINE configs[1] (default, the headline); slate = configs[3]: 60 matchups x "
+                         "--slate-games games each, sharded over the GPUs by contiguous game-id ranges (strong scaling)")
+    ap.add_argument("--slate-games", type=int, default=1_000_000, help="games per matchup of the slate workload")
     ap.add_argument("--stage2", default="synthetic", choices=["synthetic", "standin"])
     ap.add_argument("--cpu-games", type=int, default=0, help="games of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -52,7 +56,29 @@ def parse():
     return ap.parse_args()
 
 
+def slate_pairs():
+    """the first 120 teams of the priors CSV paired (2i, 2i+1)."""
+    from fast_monte_carlo_b200 import priors
+    sp = priors.load_sp_flex(priors.packaged_priors_path())
+    teams = list(sp["team"])[:120]
+    return [(teams[2 * i], teams[2 * i + 1]) for i in range(60)], sp
+
+
 def workload(args, n_gpus):
+    if args.workload == "slate":
+        return {
+            "workload": "configs[3]: full-slate run, 60 matchups (first 120 teams of PregameSPPlus2025_1 paired) x "
+                        f"{args.slate_games:,} simulated games each, contiguous game-id shards over {n_gpus} GPU(s), "
+                        f"Philox seed {SEED}",
+            "total_games_per_step": 60 * args.slate_games,
+            "play_call": "pass_prob_v1 heuristic (reference behaviour when play_model.json is absent)",
+            "stage2": ("synthetic booster of the trained shape (1086 trees, depth<=7)" if args.stage2 == "synthetic"
+                       else "fixed stand-in probabilities"),
+            "players": "Unknown (no usage tables shipped)",
+            "parallelism": f"every matchup's games sharded over {n_gpus} GPU(s); one NCCL all-reduce of the "
+                           "[60][2][128][128] histograms per step",
+            "l2": "flushed between timed steps (256 MiB write); node tables (60 matchups x ~0.6 MB) are L2-resident",
+        }
     return {
         "workload": "configs[1]: Kansas State vs Iowa State (PregameSPPlus2025_1 priors), "
                     f"{args.games:,} simulated games per GPU per step, Philox seed {SEED}",
@@ -243,16 +269,25 @@ def run_ours(args):
     from fast_monte_carlo_b200.engine import Engine, MatchupSpec
     ms = load_models(args.stage2)
     eng = Engine(ms, device=local, stage2="booster" if args.stage2 == "synthetic" else "standin")
-    G = args.games
-    g0, g1 = rank * G, (rank + 1) * G
-    spec = [MatchupSpec(KSU[0], ISU[0], KSU[1], ISU[1], G * world, g0, g1, 0)]
+    if args.workload == "slate":
+        from fast_monte_carlo_b200 import api
+        pairs, sp_df = slate_pairs()
+        spec = api.slate_specs(pairs, args.slate_games, sp_df, rank, world)
+        G = sum(m.game_end - m.game_begin for m in spec)          # this rank's games per step
+        total_games = 60 * args.slate_games
+    else:
+        G = args.games
+        g0, g1 = rank * G, (rank + 1) * G
+        spec = [MatchupSpec(KSU[0], ISU[0], KSU[1], ISU[1], G * world, g0, g1, 0)]
+        total_games = G * world
+    n_m = len(spec)
     eng.set_matchups(spec)
     eng.ctx.packed_slots(0)          # forces the specialise + upload now, outside the timed region
 
     dev = torch.device("cuda", local)
     scores = torch.empty(G, dtype=torch.int32, device=dev)
-    hist = torch.zeros((1, 2, native.HIST_BINS, native.HIST_BINS), dtype=torch.int32, device=dev)
-    hist64 = torch.zeros((1, 2, native.HIST_BINS, native.HIST_BINS), dtype=torch.int64, device=dev)
+    hist = torch.zeros((n_m, 2, native.HIST_BINS, native.HIST_BINS), dtype=torch.int32, device=dev)
+    hist64 = torch.zeros((n_m, 2, native.HIST_BINS, native.HIST_BINS), dtype=torch.int64, device=dev)
     counters = torch.zeros(native.N_COUNTERS, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
@@ -303,14 +338,13 @@ def run_ours(args):
     total_ms, kernel_ms = float(t[0]), float(t[1])
     plays_step = step_counters["plays"]
     games_step = step_counters["games"]
-    assert games_step == G * world, (games_step, G, world)
+    assert games_step == total_games, (games_step, total_games)
     value = plays_step * args.steps / (total_ms / 1e3)
 
     # ---- end-to-end through the C-ABI host-buffer call --------------------------------------------------
     e2e_plays, e2e_t = 0, 0.0
     h2d = d2h = 0
-    slots = eng.ctx.packed_slots(0)
-    table_bytes = int(slots.sum()) * 8
+    table_bytes = sum(int(eng.ctx.packed_slots(i).sum()) for i in range(n_m)) * 8
     for i in range(args.e2e_steps + 1):
         if world > 1:
             dist.barrier()
@@ -352,8 +386,8 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload(args, n_gpus),
+            "scaling": "strong" if args.workload == "slate" else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload(args, n_gpus),
             "games_per_sec": games_step * args.steps / (total_ms / 1e3),
             "plays_per_game": plays_step / games_step,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
