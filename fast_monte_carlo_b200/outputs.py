@@ -149,3 +149,45 @@ def summary_from_hist(hist2: np.ndarray, team_a: str, team_b: str) -> pd.DataFra
     df = pd.DataFrame.from_dict(rows, orient="index")
     df.index.name = "team"
     return df.sort_index()
+
+
+# ---------------------------------------------------------------------------------------------
+# literal score tables at scale: the file edge_finder.py opens
+# ---------------------------------------------------------------------------------------------
+def write_scores_table(path: str, team_a: str, team_b: str, scores: np.ndarray, first_game: int = 0,
+                       chunk_rows: int = 4_000_000) -> int:
+    """Writes `scores_<base>.parquet|csv` (columns team, opp, pts, opp_pts; rows alternate A-first /
+    B-first exactly like FMC:1501-1509) straight from the per-game (A, B) score array, in row-group
+    chunks, with the two team-name columns dictionary-encoded -- a 10 M-game table is ~25 MB of parquet
+    and never exists as a pandas object frame.  Returns the number of rows written."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    n = int(scores.shape[0])
+    names = pa.array([team_a, team_b], type=pa.string())
+    schema = pa.schema([("team", pa.dictionary(pa.int8(), pa.string())), ("opp", pa.dictionary(pa.int8(), pa.string())),
+                        ("pts", pa.int64()), ("opp_pts", pa.int64())])
+    is_parquet = path.lower().endswith(".parquet")
+    writer = pq.ParquetWriter(path, schema, compression="zstd") if is_parquet else None
+    try:
+        for lo in range(0, max(n, 1), chunk_rows):
+            sc = scores[lo:lo + chunk_rows]
+            g = np.arange(first_game + lo, first_game + lo + sc.shape[0])
+            b_first = (g & 1).astype(np.int8)
+            pts = np.where(b_first == 0, sc[:, 0], sc[:, 1]).astype(np.int64)
+            opp = np.where(b_first == 0, sc[:, 1], sc[:, 0]).astype(np.int64)
+            tbl = pa.table({
+                "team": pa.DictionaryArray.from_arrays(pa.array(b_first), names),
+                "opp": pa.DictionaryArray.from_arrays(pa.array((1 - b_first).astype(np.int8)), names),
+                "pts": pa.array(pts), "opp_pts": pa.array(opp)}, schema=schema)
+            if is_parquet:
+                writer.write_table(tbl)
+            else:
+                import pyarrow.csv as pacsv
+                cols = {c: (tbl[c].cast(pa.string()) if c in ("team", "opp") else tbl[c]) for c in tbl.column_names}
+                plain = pa.table(cols)
+                with open(path, "ab" if lo else "wb") as fh:
+                    pacsv.write_csv(plain, fh, write_options=pacsv.WriteOptions(include_header=(lo == 0)))
+    finally:
+        if writer is not None:
+            writer.close()
+    return n
