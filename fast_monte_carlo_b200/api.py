@@ -70,9 +70,9 @@ def simulate_matchup(teamA: TeamContext, teamB: TeamContext, n: int = 100, seed:
         res = eng.simulate_host(_fresh_seed() if seed is None else int(seed), want_scores=True, want_hist=True)
         sims_df = outputs.sims_frame(teamA.name, teamB.name, res["scores"])
         sims_df.attrs["counters"] = dict(res["counters"])
-        sims_df.attrs["scores"] = res["scores"]
         LAST_RUN.clear()
-        LAST_RUN.update(hist=res["hist"][0], counters=dict(res["counters"]), teams=(teamA.name, teamB.name))
+        LAST_RUN.update(hist=res["hist"][0], counters=dict(res["counters"]), teams=(teamA.name, teamB.name),
+                        scores=res["scores"])
     players_df = None
     if collect_players:
         players_df = pd.DataFrame(columns=PLAYER_COLS)
@@ -104,8 +104,8 @@ def simulate_upcoming_matchup(teamA: str, teamB: str, *, year: int = 2025, week:
         tw = time.perf_counter()
         try:
             if save_csv.lower().endswith(".parquet"):
-                raw = sims_df.attrs.get("scores")
-                if raw is not None:      # chunked, dictionary-encoded writer straight from the score array
+                raw = LAST_RUN.get("scores") if LAST_RUN.get("teams") == (A.name, B.name) else None
+                if raw is not None and len(raw) == len(sims_df):   # chunked, dictionary-encoded writer straight from the score array
                     outputs.write_scores_table(f"scores_{save_csv}", A.name, B.name, raw)
                 else:
                     sims_df.to_parquet(f"scores_{save_csv}", index=False)

@@ -31,7 +31,7 @@ struct PredictArgs {
     const uint4 *stream;
     const uint2 *consts;
     uint32_t stream_off[8], consts_off[8], n_groups[8];
-    int n_outputs, n_num;
+    int n_outputs, n_num, multi_window;
     int zero_is_missing;
     double base[8];
     int n_scaled;
@@ -79,8 +79,10 @@ __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs
             F.stream = a.stream + a.stream_off[o];
             F.consts = a.consts + a.consts_off[o];
             F.n_groups = a.n_groups[o];
+            F.multi_window = a.multi_window != 0;
             uint32_t levels;
-            const double v = walk_output<SKL>(F, fcol, lane, a.base[o], levels);
+            const double v = a.multi_window ? walk_output<SKL, true>(F, fcol, lane, a.base[o], levels)
+                                            : walk_output<SKL, false>(F, fcol, lane, a.base[o], levels);
             if (live) a.out[(base + tid) * a.n_outputs + o] = v;
         }
         __syncthreads();
@@ -109,7 +111,10 @@ struct TableArena {
     int place(PackedForest &pf, TablePlacement &pl) {
         size_t cursor = (h_nodes.size() * 8 + 127) / 128 * 128;
         const size_t bytes = pf.slots.size() * 8;
-        if (cursor % kWindowBytes + bytes > kWindowBytes) cursor = (cursor + kWindowBytes - 1) / kWindowBytes * kWindowBytes;
+        // a table of at most one window must not straddle a window boundary; larger tables start on one (their
+        // groups were laid out against 1 MiB boundaries of the table by the packer)
+        if (bytes > kWindowBytes || cursor % kWindowBytes + bytes > kWindowBytes)
+            cursor = (cursor + kWindowBytes - 1) / kWindowBytes * kWindowBytes;
         pf.relocate((uint32_t)(cursor % kWindowBytes));
         h_nodes.resize(cursor / 8, 0);
         h_nodes.insert(h_nodes.end(), pf.slots.begin(), pf.slots.end());
@@ -330,6 +335,7 @@ static int build_tables(fmc_ctx *c) {
                 }
                 T.n_outputs = (uint8_t)pf.n_outputs;
                 T.max_depth = (uint8_t)pf.max_depth;
+                T.multi_window = pf.table_bytes() > kWindowBytes ? 1 : 0;
                 for (int k = 0; k < 5 && k < f.n_outputs; ++k) T.base[k] = (float)f.base[k];
                 for (int k = 0; k < 3 && k < f.n_outputs; ++k) T.base64[k] = f.base[k];
                 placed.push_back({i, fam, off, table});
@@ -497,6 +503,7 @@ extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, 
     a.stream = A.d_stream; a.consts = A.d_consts;
     for (int k = 0; k < 8; ++k) { a.stream_off[k] = pl.stream_off[k]; a.consts_off[k] = pl.consts_off[k]; a.n_groups[k] = pl.n_groups[k]; }
     a.n_outputs = f.n_outputs; a.n_num = f.n_num;
+    a.multi_window = pf.table_bytes() > kWindowBytes ? 1 : 0;
     a.zero_is_missing = (f.kind == FMC_KIND_XGB && f.zero_is_missing) ? 1 : 0;
     for (int k = 0; k < 8; ++k) a.base[k] = f.base[k];
     a.n_scaled = f.n_scaled;

@@ -122,6 +122,7 @@ struct ForestView {          // everything here is warp-uniform
     const uint4 *stream;     // root stream of ONE output: 2 x uint4 (kIlp root slots) per group
     const uint2 *consts;     // side stream of that output
     uint32_t n_groups;
+    bool multi_window;       // the node table spans more than one window
 };
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {
@@ -135,9 +136,6 @@ __device__ __forceinline__ uint2 ldg_slot(uint32_t lo, uint32_t hi) {
         : "=r"(v.x), "=r"(v.y) : "r"(lo), "r"(hi));
     return v;
 }
-__device__ __forceinline__ void prefetch_l1(uint32_t lo, uint32_t hi) {
-    asm volatile("{\n\t.reg .u64 ad;\n\tmov.b64 ad, {%0, %1};\n\tprefetch.global.L1 [ad];\n\t}" :: "r"(lo), "r"(hi));
-}
 
 template <bool SKL>
 __device__ __forceinline__ void walk_step(uint2 &n, uint32_t fcol, uint32_t win_lo, uint32_t win_hi) {
@@ -150,12 +148,6 @@ __device__ __forceinline__ void walk_step(uint2 &n, uint32_t fcol, uint32_t win_
     n = ldg_slot(a, win_hi);
 }
 
-#ifndef FMC_PREFETCH
-#define FMC_PREFETCH 0      // 1: CCTL.PF1 the next group's node lines, 2: touch them with a plain load
-#endif
-#ifndef FMC_GROUPS_IN_FLIGHT
-#define FMC_GROUPS_IN_FLIGHT 2
-#endif
 
 // Adds the leaves the lanes hold after a group's walk (plus the group's constants) in tree order.
 template <bool SKL>
@@ -192,12 +184,22 @@ __device__ __forceinline__ void load_roots(const uint4 *sp, uint2 (&n)[kIlp]) {
     n[2] = make_uint2(b.x, b.y); n[3] = make_uint2(b.z, b.w);
 }
 __device__ __forceinline__ uint32_t group_depth(const uint2 (&n)[kIlp]) { return (n[0].y & 7u) | ((n[1].y & 1u) << 3); }
+// 64-bit address of the 1 MiB window a group's nodes sit in.  MW = false: the table fits one window (every
+// table of the simulation so far); MW = true: tables above 1 MiB span several windows.
+template <bool MW>
+__device__ __forceinline__ void group_window(const uint2 (&n)[kIlp], const ForestView &F, uint32_t &lo, uint32_t &hi) {
+    if (!MW) { lo = F.win_lo; hi = F.win_hi; return; }
+    const uint32_t w = (n[2].y & 7u) | ((n[3].y & 7u) << 3);
+    const unsigned long long a = (((unsigned long long)F.win_hi << 32) | F.win_lo) + ((unsigned long long)w << 20);
+    lo = (uint32_t)a;
+    hi = (uint32_t)(a >> 32);
+}
 __device__ __forceinline__ bool group_has_consts(const uint2 (&n)[kIlp]) { return (n[1].y & 2u) != 0; }
 
 // Sum one output of a packed forest in tree order.  SKL: float64 accumulate of pre-scaled leaves;
 // XGB: float32 accumulate (returned widened).
 // `levels` returns the number of tree levels the walk issued per tree slot (sum of the group depths).
-template <bool SKL>
+template <bool SKL, bool MW>
 __device__ __forceinline__ double walk_output(const ForestView &F, uint32_t fcol, int lane, double base, uint32_t &levels) {
     constexpr int I = kIlp;
     double acc64 = base;
@@ -206,7 +208,6 @@ __device__ __forceinline__ double walk_output(const ForestView &F, uint32_t fcol
     if (F.n_groups == 0) return SKL ? acc64 : (double)acc32;
     const uint4 *sp = F.stream;
     const uint2 *cp = F.consts;
-#if FMC_GROUPS_IN_FLIGHT == 2
     // Two groups (2 x kIlp trees) in flight per lane: both are walked together for the depth they share
     // (8 independent gather chains, no branch inside), then the deeper one finishes alone -- a sklearn
     // lane must not step past its float64 leaf.  The roots are fetched at the top of each pass.
@@ -218,25 +219,28 @@ __device__ __forceinline__ double walk_output(const ForestView &F, uint32_t fcol
         load_roots(sp + 2 * g + 2, n1);
         const uint32_t d0 = group_depth(n0), d1 = group_depth(n1);
         const bool c0 = group_has_consts(n0), c1 = group_has_consts(n1);   // the metadata leaves with the root slots
+        uint32_t w0l, w0h, w1l, w1h;
+        group_window<MW>(n0, F, w0l, w0h);
+        group_window<MW>(n1, F, w1l, w1h);
         const uint32_t dmin = d0 < d1 ? d0 : d1, dmax = d0 < d1 ? d1 : d0;
         levels += d0 + d1;
 #pragma unroll 1
         for (uint32_t d = 0; d < dmin; ++d) {
 #pragma unroll
-            for (int i = 0; i < I; ++i) walk_step<SKL>(n0[i], fcol, F.win_lo, F.win_hi);
+            for (int i = 0; i < I; ++i) walk_step<SKL>(n0[i], fcol, w0l, w0h);
 #pragma unroll
-            for (int i = 0; i < I; ++i) walk_step<SKL>(n1[i], fcol, F.win_lo, F.win_hi);
+            for (int i = 0; i < I; ++i) walk_step<SKL>(n1[i], fcol, w1l, w1h);
         }
         if (d0 > d1) {
 #pragma unroll 1
             for (uint32_t d = dmin; d < dmax; ++d)
 #pragma unroll
-                for (int i = 0; i < I; ++i) walk_step<SKL>(n0[i], fcol, F.win_lo, F.win_hi);
+                for (int i = 0; i < I; ++i) walk_step<SKL>(n0[i], fcol, w0l, w0h);
         } else {
 #pragma unroll 1
             for (uint32_t d = dmin; d < dmax; ++d)
 #pragma unroll
-                for (int i = 0; i < I; ++i) walk_step<SKL>(n1[i], fcol, F.win_lo, F.win_hi);
+                for (int i = 0; i < I; ++i) walk_step<SKL>(n1[i], fcol, w1l, w1h);
         }
         accumulate_group<SKL>(n0, c0, cp, acc64, acc32);
         accumulate_group<SKL>(n1, c1, cp, acc64, acc32);
@@ -246,57 +250,16 @@ __device__ __forceinline__ double walk_output(const ForestView &F, uint32_t fcol
         load_roots(sp + 2 * g, n0);
         const uint32_t d0 = group_depth(n0);
         const bool c0 = group_has_consts(n0);
+        uint32_t w0l, w0h;
+        group_window<MW>(n0, F, w0l, w0h);
         levels += d0;
 #pragma unroll 1
         for (uint32_t d = 0; d < d0; ++d)
 #pragma unroll
-            for (int i = 0; i < I; ++i) walk_step<SKL>(n0[i], fcol, F.win_lo, F.win_hi);
+            for (int i = 0; i < I; ++i) walk_step<SKL>(n0[i], fcol, w0l, w0h);
         accumulate_group<SKL>(n0, c0, cp, acc64, acc32);
     }
     (void)lane;
-#else
-    uint2 n[I];
-    load_roots(sp, n);
-#if FMC_PREFETCH == 2
-    uint32_t touched = 0;
-#endif
-#pragma unroll 1
-    for (uint32_t g = 0; g < F.n_groups; ++g) {
-        // the next group's roots arrive while this group is walked
-        const uint4 *nx = sp + 2 * (g + 1 < F.n_groups ? g + 1 : g);
-        const uint4 xa = __ldg(nx), xb = __ldg(nx + 1);
-        const uint32_t depth = group_depth(n);
-        const bool has_consts = group_has_consts(n);
-        levels += depth;
-#if FMC_PREFETCH
-        uint32_t pf = 0;
-        {   // pull the next group's node lines into L1 ahead of its walk
-            const uint32_t lines = (xb.y & 7u) | ((xb.w & 3u) << 3);
-            const uint32_t a = (((xa.y & kChildMask) | F.win_lo) & ~127u) + 128u * (uint32_t)lane;
-#if FMC_PREFETCH == 1
-            if ((uint32_t)lane < lines) prefetch_l1(a, F.win_hi);
-#else
-            if ((uint32_t)lane < lines) pf = ldg_slot(a, F.win_hi).x;
-#endif
-        }
-#endif
-#pragma unroll 1
-        for (uint32_t d = 0; d < depth; ++d) {
-#pragma unroll
-            for (int i = 0; i < I; ++i) walk_step<SKL>(n[i], fcol, F.win_lo, F.win_hi);
-        }
-        accumulate_group<SKL>(n, has_consts, cp, acc64, acc32);
-#if FMC_PREFETCH == 2
-        touched ^= pf;
-#endif
-        n[0] = make_uint2(xa.x, xa.y); n[1] = make_uint2(xa.z, xa.w);
-        n[2] = make_uint2(xb.x, xb.y); n[3] = make_uint2(xb.z, xb.w);
-    }
-#if FMC_PREFETCH == 2
-    if (touched == 0x9e3779b9u && F.n_groups == 0xFFFFFFFFu) acc32 += 1.0f;   // keeps the touches alive; never true
-#endif
-    (void)lane;
-#endif
     return SKL ? acc64 : (double)acc32;
 }
 

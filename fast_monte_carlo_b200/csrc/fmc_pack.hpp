@@ -34,8 +34,9 @@
 //     its own bank -- conflict-free whatever node each lane is at.
 //     The walk starts from the ROOT STREAM: the root slots of the groups, kIlp x 8 bytes per group,
 //     in tree order, read with warp-uniform 16-byte loads.  The low three bits of the four child
-//     fields of a group carry its metadata (D, "has constants", lines to prefetch).  Constants live
-//     in a side stream that is only touched by groups that have them.
+//     fields of a group carry its metadata (D, "has constants", window of the group inside a table
+//     larger than 1 MiB).  Constants live in a side stream that is only touched by groups that have
+//     them.
 //
 // "Feature rows" are the columns of the per-request feature record.  For CSR-fed boosters a
 // non-flag numeric that may be exactly zero gets two rows: row A holds -inf when the value is 0
@@ -126,8 +127,11 @@ struct PackedForest {
     int max_depth = 0;
     uint64_t internal = 0, leaves = 0, constants = 0, pass_through = 0;
 
-    // Add the table's byte offset inside its window to every child field.
+    size_t table_bytes() const { return slots.size() * 8; }
+    // Add the table's byte offset inside its window to every child field (tables of at most one window;
+    // larger tables are placed window-aligned and need no relocation).
     void relocate(uint32_t base) {
+        if (base == 0) return;
         for (size_t i = 0; i < slots.size(); ++i)
             if (slot_is_node[i]) slots[i] += (uint64_t)base << 32;
         for (size_t i = 0; i < stream.size(); ++i)
@@ -264,23 +268,17 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
     if (s.ninf_row < 0 || s.ninf_row * kFeatBytes >= (1 << (32 - kFeatShift))) return "-inf feature row out of range";
     const uint32_t ninf_hi = (uint32_t)(s.ninf_row * kFeatBytes) << kFeatShift;
 
+    // slots of the group being laid out; child fields hold GROUP-relative slot indices until placement
+    std::vector<uint64_t> gs;
+    std::vector<uint8_t> gs_node;
     auto push_slot = [&](uint64_t w, bool node) -> uint32_t {
-        out.slots.push_back(w);
-        out.slot_is_node.push_back(node ? 1 : 0);
-        return (uint32_t)(out.slots.size() - 1);
+        gs.push_back(w);
+        gs_node.push_back(node ? 1 : 0);
+        return (uint32_t)(gs.size() - 1);
     };
     auto node_word = [&](uint32_t lo, uint32_t feat_hi, uint32_t child_slot) -> uint64_t {
         return ((uint64_t)(feat_hi | (child_slot * 8u)) << 32) | lo;
     };
-    // table head: the +0.0 leaf every padding tree ends in.  sklearn: slot 0 is the float64 0.0 and slot j
-    // (1..15) passes through to slot j-1, so a padding tree of a depth-D group starts at slot D.
-    // xgboost: slot 0 is a self-pointing 0.0f leaf.
-    if (skl) {
-        push_slot(f64_bits(0.0), false);
-        for (int j = 1; j <= kMaxGroupDepth; ++j) push_slot(node_word(0, ninf_hi, (uint32_t)(j - 1)), true);
-    } else {
-        push_slot(node_word(f32_bits(0.0f), ninf_hi, 0), true);
-    }
 
     std::vector<std::vector<int>> per_out(f.n_outputs);
     for (int t = tb; t < te; ++t) {
@@ -339,14 +337,23 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
             }
             if (skl && D == 0) D = 1;    // a float64 root cannot carry the group metadata: an all-padding group walks one pass-through level
             if (D > out.max_depth) out.max_depth = D;
-            const uint32_t first_slot = (uint32_t)out.slots.size();
+            gs.clear();
+            gs_node.clear();
             uint64_t rootw[kIlp];
-            bool root_node[kIlp];
             for (int q = 0; q < kIlp; ++q) {
                 const Entry &e = entries[g + q];
-                if (e.root < 0) {                         // padding tree: D levels down to the +0.0 leaf
-                    rootw[q] = out.slots[skl ? (size_t)D : 0];
-                    root_node[q] = skl ? (D > 0) : true;
+                if (e.root < 0) {
+                    // padding tree: D levels down to a +0.0 leaf.  xgboost: a self-pointing 0.0f leaf;
+                    // sklearn: the float64 0.0 behind a chain of D pass-through nodes (D >= 1 here)
+                    if (skl) {
+                        uint32_t next = push_slot(f64_bits(0.0), false);
+                        for (int x = 1; x < D; ++x) next = push_slot(node_word(0, ninf_hi, next), true);
+                        rootw[q] = node_word(0, ninf_hi, next);
+                    } else {
+                        const uint32_t me = push_slot(0, true);
+                        gs[me] = node_word(f32_bits(0.0f), ninf_hi, me);
+                        rootw[q] = gs[me];
+                    }
                     continue;
                 }
                 // breadth-first layout, children adjacent; the root lives only in the stream
@@ -371,8 +378,7 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
                                 out.pass_through += (uint64_t)extra;
                             }
                         } else {
-                            // self-pointing leaf; its own slot index is patched below
-                            w = node_word(f32_bits((float)n.value), ninf_hi, slot_of[qi] == 0xFFFFFFFFu ? 0 : slot_of[qi]);
+                            w = node_word(f32_bits((float)n.value), ninf_hi, slot_of[qi]);   // self-pointing leaf
                         }
                     } else {
                         if (n.row < 0 || n.row * kFeatBytes >= (1 << (32 - kFeatShift))) return "feature row out of range for the table format";
@@ -383,19 +389,33 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
                         order.push_back(n.l); slot_of.push_back(c); depth_q.push_back(depth_q[qi] + 1);
                         order.push_back(n.r); slot_of.push_back(c + 1); depth_q.push_back(depth_q[qi] + 1);
                     }
-                    if (qi == 0) { rootw[q] = w; root_node[q] = is_node; }
-                    else { out.slots[slot_of[qi]] = w; out.slot_is_node[slot_of[qi]] = is_node ? 1 : 0; }
+                    if (qi == 0) rootw[q] = w;      // a walked tree's root is always an internal node
+                    else { gs[slot_of[qi]] = w; gs_node[slot_of[qi]] = is_node ? 1 : 0; }
                 }
             }
-            if (out.slots.size() * 8 > kWindowBytes) return "packed table exceeds the 1 MiB window of the node format";
-            // ---- group metadata in the three spare low bits of the four child fields
-            const uint32_t bytes = (uint32_t)(out.slots.size() - first_slot) * 8u;
-            uint32_t lines = bytes ? ((first_slot * 8u + bytes + 127u) / 128u - (first_slot * 8u) / 128u) : 0;
-            if (lines > 31) lines = 31;
-            const uint32_t meta[kIlp] = {(uint32_t)D & 7u, (((uint32_t)D >> 3) & 1u) | (n_pre ? 2u : 0u), lines & 7u, (lines >> 3) & 3u};
+            // ---- placement: a group never straddles a 1 MiB boundary of the table (tables above 1 MiB are
+            // placed window-aligned by the arena, smaller ones are relocated as a whole)
+            const size_t gbytes = gs.size() * 8;
+            if (gbytes > kWindowBytes) return "one tree group exceeds the 1 MiB window of the node format";
+            size_t pos = out.slots.size() * 8;
+            if (pos % kWindowBytes + gbytes > kWindowBytes) {
+                const size_t pad = (kWindowBytes - pos % kWindowBytes) / 8;
+                out.slots.insert(out.slots.end(), pad, 0);
+                out.slot_is_node.insert(out.slot_is_node.end(), pad, 0);
+                pos = out.slots.size() * 8;
+            }
+            const uint32_t window = (uint32_t)(pos / kWindowBytes);
+            if (window > 63) return "packed table exceeds 64 windows of 1 MiB";
+            const uint64_t shift = (uint64_t)(pos % kWindowBytes) << 32;      // group-relative -> window-relative offsets
+            for (size_t i = 0; i < gs.size(); ++i) {
+                out.slots.push_back(gs_node[i] ? gs[i] + shift : gs[i]);
+                out.slot_is_node.push_back(gs_node[i]);
+            }
+            // ---- group metadata in the three spare low bits of the four child fields:
+            // depth (4 bits), "has constants" (1 bit), window of the group inside the table (6 bits)
+            const uint32_t meta[kIlp] = {(uint32_t)D & 7u, (((uint32_t)D >> 3) & 1u) | (n_pre ? 2u : 0u), window & 7u, (window >> 3) & 7u};
             for (int q = 0; q < kIlp; ++q) {
-                if (!root_node[q]) return "internal error: a root slot must be a node";
-                out.stream.push_back(rootw[q] | ((uint64_t)meta[q] << 32));
+                out.stream.push_back((rootw[q] + shift) | ((uint64_t)meta[q] << 32));
                 out.stream_is_node.push_back(1);
             }
             if (n_pre) {

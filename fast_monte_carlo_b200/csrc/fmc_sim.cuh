@@ -43,6 +43,7 @@ struct TableRef {
     uint16_t n_groups[5];
     uint8_t n_outputs;
     uint8_t max_depth;
+    uint8_t multi_window;       // table larger than one window: groups carry their window index
     float base[5];              // xgb margin offsets (f32-exact) ...
     double base64[3];           // ... or sklearn init constants
 };
@@ -91,6 +92,45 @@ struct Lane {
     int stage;
     int plays;                 // plays of the current game
 };
+
+// A game's state between rounds: nine registers instead of sixteen, so that the tree walk (which runs with
+// every lane's game parked) has room for its eight gather chains.
+#ifndef FMC_PACK_LANE
+#define FMC_PACK_LANE 1
+#endif
+#if !FMC_PACK_LANE
+typedef Lane PackedLane;
+__device__ __forceinline__ PackedLane pack_lane(const Lane &L) { return L; }
+__device__ __forceinline__ Lane unpack_lane(const PackedLane &P) { return P; }
+__device__ __forceinline__ void set_stage(PackedLane &P, int stage) { P.stage = stage; }
+#else
+struct PackedLane {
+    unsigned long long game;
+    double dist, ytg;
+    uint32_t a;     // sec:12 | down:10 | period:3 | offense:1 | going:1 | stage:4
+    uint32_t b;     // iter:10 | plays:10
+    uint32_t c;     // score[0]:16 | score[1]:16
+};
+__device__ __forceinline__ PackedLane pack_lane(const Lane &L) {
+    PackedLane P;
+    P.game = L.game; P.dist = L.dist; P.ytg = L.ytg;
+    P.a = (uint32_t)L.sec | ((uint32_t)L.down << 12) | ((uint32_t)L.period << 22) | ((uint32_t)L.offense << 25) |
+          ((uint32_t)L.going << 26) | ((uint32_t)L.stage << 27);
+    P.b = (uint32_t)L.iter | ((uint32_t)L.plays << 10);
+    P.c = (uint32_t)L.score[0] | ((uint32_t)L.score[1] << 16);
+    return P;
+}
+__device__ __forceinline__ Lane unpack_lane(const PackedLane &P) {
+    Lane L;
+    L.game = P.game; L.dist = P.dist; L.ytg = P.ytg;
+    L.sec = (int)(P.a & 0xFFFu); L.down = (int)((P.a >> 12) & 0x3FFu); L.period = (int)((P.a >> 22) & 7u);
+    L.offense = (int)((P.a >> 25) & 1u); L.going = (int)((P.a >> 26) & 1u); L.stage = (int)(P.a >> 27);
+    L.iter = (int)(P.b & 0x3FFu); L.plays = (int)(P.b >> 10);
+    L.score[0] = (int)(P.c & 0xFFFFu); L.score[1] = (int)(P.c >> 16);
+    return L;
+}
+__device__ __forceinline__ void set_stage(PackedLane &P, int stage) { P.a = (P.a & 0x07FFFFFFu) | ((uint32_t)stage << 27); }
+#endif
 
 // python semantics helpers (FMC:97 softclip = max(lo, min(hi, x)))
 __device__ __forceinline__ double pymax(double a, double b) { return (b > a) ? b : a; }
@@ -508,8 +548,13 @@ __device__ __forceinline__ double eval_output(int fam, const TableRef &T, int ou
     F.stream = a.root_stream + T.stream_off[out];
     F.consts = a.consts + T.consts_off[out];
     F.n_groups = T.n_groups[out];
-    if (fam >= 2 && fam <= 4) return walk_output<true>(F, fcol, lane, T.base64[out], levels);
-    return walk_output<false>(F, fcol, lane, (double)T.base[out], levels);
+    F.multi_window = T.multi_window != 0;
+    if (T.multi_window) {     // rare: a specialised table above 1 MiB
+        if (fam >= 2 && fam <= 4) return walk_output<true, true>(F, fcol, lane, T.base64[out], levels);
+        return walk_output<false, true>(F, fcol, lane, (double)T.base[out], levels);
+    }
+    if (fam >= 2 && fam <= 4) return walk_output<true, false>(F, fcol, lane, T.base64[out], levels);
+    return walk_output<false, false>(F, fcol, lane, (double)T.base[out], levels);
 }
 
 __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const SimKernelArgs a) {
@@ -529,8 +574,14 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     if (tid == 0) sh.cur_matchup = -1;
     __syncthreads();
 
-    Lane L;
-    L.stage = ST_IDLE;
+    PackedLane P;
+    {
+        Lane L0;
+        L0.game = 0; L0.dist = 0.0; L0.ytg = 0.0; L0.sec = 0; L0.down = 0; L0.offense = 0; L0.period = 0; L0.going = 0;
+        L0.iter = 0; L0.score[0] = 0; L0.score[1] = 0; L0.plays = 0;
+        L0.stage = ST_IDLE;
+        P = pack_lane(L0);
+    }
     unsigned long long rounds = 0, requests = 0, visits = 0;
 
     for (int visit = 0;; ++visit) {
@@ -554,11 +605,12 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
             for (int i = tid; i < (int)(sizeof(MatchupDev) / 4); i += kSimThreads) dst[i] = src[i];
         }
         __syncthreads();
-        L.stage = ST_NEED_GAME;
+        set_stage(P, ST_NEED_GAME);
         int pos = 0;
         int parity = 0;
         for (;;) {
             // ---- A: advance to the next request
+            Lane L = unpack_lane(P);
             const int key = advance_lane(L, a, sh, results + (size_t)pos * 3);
             __syncwarp();
             // ---- B: compaction
@@ -592,6 +644,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
                 pos = (int)(sh.off[key] + rank);
                 write_features(feats + (size_t)(pos >> 5) * kChunkFloats + (pos & 31), L, key >> 1, a);
             }
+            P = pack_lane(L);
             __syncthreads();
             // ---- C: evaluate.  Work item = (key, chunk of 32 requests, output)
             const unsigned int n_items = sh.item_prefix[kNumKeys];

@@ -83,6 +83,7 @@ def walk(slots, stream, consts, meta, rows, skl, base):
             r_hi = (roots >> np.uint64(32)).astype(np.uint32)
             depth = int(r_hi[0] & 7) | (int(r_hi[1] & 1) << 3)
             has_consts = bool(r_hi[1] & 2)
+            window = int(r_hi[2] & 7) | (int(r_hi[3] & 7) << 3)      # 1 MiB window of the group inside the table
             cur_lo = np.tile(r_lo, (n, 1))
             cur_hi = np.tile(r_hi, (n, 1))
             for _ in range(depth):
@@ -92,7 +93,7 @@ def walk(slots, stream, consts, meta, rows, skl, base):
                     fv = rows[ar, frow]
                     thr = cur_lo[:, q].view(np.float32)
                     right = ~(fv <= thr) if skl else ~(fv < thr)
-                    a = (cur_hi[:, q] & np.uint32(CHILD_MASK)).astype(np.int64) + 8 * right
+                    a = (window << 20) + (cur_hi[:, q] & np.uint32(CHILD_MASK)).astype(np.int64) + 8 * right
                     assert np.all(a % 8 == 0) and a.max() < 8 * len(slots)
                     cur_lo[:, q] = lo[a // 8]
                     cur_hi[:, q] = hi[a // 8]

@@ -26,6 +26,14 @@ def test_simulate_upcoming_matchup_drop_in(engine, tmp_path, monkeypatch):
     on_disk = pd.read_csv(tmp_path / f"scores_{base}")
     assert on_disk.equals(sims_df.reset_index(drop=True).astype(on_disk.dtypes.to_dict()))
     assert os.path.exists(tmp_path / f"players_{base}")
+    # parquet route: the chunked writer fed straight from the engine's score array
+    pq_base = base.replace(".csv", ".parquet")
+    sims2, *_ = api.simulate_upcoming_matchup(
+        "Kansas State", "Iowa State", sp_path=priors.packaged_priors_path(), n=500, show_progress=False,
+        save_csv=pq_base, seed=11, engine=engine)
+    pq = pd.read_parquet(tmp_path / f"scores_{pq_base}")
+    assert (pq["team"].astype(str) == sims2["team"]).all() and np.array_equal(pq["pts"], sims2["pts"])
+    assert np.array_equal(pq["opp_pts"], sims2["opp_pts"]) and sims2.equals(sims_df)
     # reproducible for a given seed; histogram adapter agrees with the table
     again, _ = api.simulate_matchup(A, B, n=500, seed=11, engine=engine)
     assert again.equals(sims_df)

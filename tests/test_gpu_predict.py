@@ -98,3 +98,21 @@ def test_empty_and_ragged_sizes(engine, oracle, models_s2):
     for n in (1, 31, 33, 255, 257, 1000):
         rows = _rows(n, n)
         assert np.array_equal(engine.predict("run_yards", rows), _oracle_margins(oracle, f, "run_yards", rows, cols))
+
+
+def test_forest_larger_than_one_window(models_s2, native_lib):
+    """A node table above 1 MiB spans several windows (per-group window index in the root stream)."""
+    from fast_monte_carlo_b200 import synth
+    from fast_monte_carlo_b200.engine import Engine
+    big = synth.synthetic_stage2(models_s2, seed=5, rounds=1500)
+    forests = dict(models_s2.forests)
+    forests["pass_stage2"] = big
+    e = Engine(art.ModelSet(forests, source="big-stage2"), device=0, stage2="standin")
+    try:
+        rows = _rows(4000, 21)
+        cols = [g.column_of("Unknown") for g in big.groups]
+        got = e.predict("pass_stage2", rows)
+        ref = to.raw_margin(big, rows, np.tile(np.array(cols[:2]), (rows.shape[0], 1)))
+        assert np.array_equal(got, ref)
+    finally:
+        e.close()

@@ -94,9 +94,25 @@ def test_constant_trees_and_group_padding(models_s2, native_lib):
     walked = 4 * sum(meta["n_groups"][:3])
     assert meta["constants"] > 0 and meta["constants"] + walked >= 1200 and walked < 1200
     assert len(stream) == walked
-    assert slots[0] == 0                                  # the +0.0 float64 leaf every padding tree ends in
     # a model with nothing to fold keeps every tree
     f1 = models_s2["pass_yards"]
     cols1 = [g.column_of("Unknown") for g in f1.groups] + [-1, -1]
     _, stream1, _, meta1 = native.pack_forest_host(f1, mode=1, cols=cols1[:2])
     assert meta1["constants"] + len(stream1) >= 1200
+
+
+def test_table_larger_than_one_window(models_s2, native_lib):
+    """A forest whose node table exceeds 1 MiB spans several windows: every group stays inside one and
+    carries its window index (fmc_pack.hpp)."""
+    from fast_monte_carlo_b200 import synth
+    big = synth.synthetic_stage2(models_s2, seed=5, rounds=1500)
+    cols = [g.column_of("Unknown") for g in big.groups] + [-1, -1]
+    slots, stream, consts, meta = native.pack_forest_host(big, mode=1, cols=cols[:2])
+    assert len(slots) * 8 > (1 << 20)
+    hi = (stream >> np.uint64(32)).astype(np.uint32).reshape(-1, 4)
+    windows = (hi[:, 2] & 7) | ((hi[:, 3] & 7) << 3)
+    assert windows.max() >= 1 and np.all(np.diff(windows[: meta["n_groups"][0]].astype(int)) >= 0)
+    num = _rows(8, 9)
+    got = pw.walk(slots, stream, consts, meta, pw.predict_rows(num, True, None), False, big.base_margin)
+    ref = to.raw_margin(big, num, np.tile(np.array(cols[:2]), (num.shape[0], 1)))
+    assert np.array_equal(got, ref)
