@@ -172,12 +172,16 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of sim_kernel from the committed ncu --set full capture, if any."""
+def ncu_traffic(games_per_launch: int):
+    """DRAM bytes per launch of sim_kernel, from the committed `ncu --set full` capture
+    (profiles/sim_kernel_ncu_latest.json: dram__bytes_read.sum + dram__bytes_write.sum of one launch of
+    `games_in_profiled_launch` games) scaled to this run's games per launch -- the kernel's DRAM traffic is
+    the per-game score word + histogram atomics, i.e. proportional to the games."""
     p = os.path.join(ROOT, "profiles", "sim_kernel_ncu_latest.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            d = json.load(open(p))
+            return float(d["dram_bytes_per_launch"]) / float(d["games_in_profiled_launch"]) * games_per_launch
         except Exception:
             return None
     return None
@@ -397,7 +401,7 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "fmc::sim_kernel",
+                "traffic": ncu_traffic(G), "peak_source": peak_src, "kernel": "fmc::sim_kernel",
                 "kernel_ms_per_launch": kernel_ms / args.steps,
                 "algorithmic_bytes_per_launch": algo,
                 "note": "algorithmic bytes = SURVEY 8(d) per-row figures on the unpruned forests x requests per "
