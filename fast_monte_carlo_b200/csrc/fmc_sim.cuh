@@ -263,10 +263,19 @@ struct SimShared {
     int cur_matchup;
     unsigned int cnt[2][kNumKeys];    // requests per key, double-buffered by round parity
     unsigned int off[kNumKeys];       // first position of each key's list
+    unsigned int evalc[kNumKeys];     // requests of the key that are evaluated this round (the rest wait one round)
+    unsigned int aged[kNumKeys];      // the key's tail was held back last round: evaluate everything now
     unsigned int item_prefix[kNumKeys + 1];
     unsigned int item_next;
     unsigned long long stat[FMC_N_COUNTERS];
 };
+
+// A key whose last chunk would hold fewer than this many requests holds that tail back for one round (the
+// lanes re-post the same request next round, where it joins a fuller chunk); 0 disables.
+#ifndef FMC_DEFER_BELOW
+#define FMC_DEFER_BELOW 12
+#endif
+constexpr unsigned int kDeferBelow = FMC_DEFER_BELOW;
 
 // Requests are kept in 32-request chunks, feature-major ([feature][lane]); every key's list starts on
 // a chunk boundary, so at most kSimThreads/32 + kNumKeys chunks are in use.
@@ -570,7 +579,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     for (int i = tid; i < kSimChunks * 32; i += kSimThreads)
         feats[(size_t)(i >> 5) * kChunkFloats + kSimNinfRow * 32 + (i & 31)] = __int_as_float(0xff800000);
     if (tid < FMC_N_COUNTERS) sh.stat[tid] = 0ULL;
-    if (tid < kNumKeys) { sh.cnt[0][tid] = 0; sh.cnt[1][tid] = 0; }
+    if (tid < kNumKeys) { sh.cnt[0][tid] = 0; sh.cnt[1][tid] = 0; sh.aged[tid] = 0; }
     if (tid == 0) sh.cur_matchup = -1;
     __syncthreads();
 
@@ -608,10 +617,11 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
         set_stage(P, ST_NEED_GAME);
         int pos = 0;
         int parity = 0;
+        int held = -1;                 // key of a request that was held back last round
         for (;;) {
-            // ---- A: advance to the next request
+            // ---- A: advance to the next request (a held-back lane re-posts the one it has)
             Lane L = unpack_lane(P);
-            const int key = advance_lane(L, a, sh, results + (size_t)pos * 3);
+            const int key = held >= 0 ? held : advance_lane(L, a, sh, results + (size_t)pos * 3);
             __syncwarp();
             // ---- B: compaction
             unsigned int rank = 0;
@@ -629,7 +639,11 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
                 unsigned int o = 0, it = 0;
                 for (int j = 0; j < kNumKeys; ++j) {
                     const int k = kKeyOrder[j];
-                    const unsigned int c = sh.cnt[parity][k];
+                    unsigned int c = sh.cnt[parity][k];
+                    const unsigned int tail = c & 31u;
+                    if (tail != 0 && tail < kDeferBelow && !sh.aged[k]) { c -= tail; sh.aged[k] = 1; }
+                    else sh.aged[k] = 0;
+                    sh.evalc[k] = c;
                     sh.off[k] = o;
                     o += (c + 31u) & ~31u;          // lists start on chunk boundaries
                     sh.item_prefix[j] = it;
@@ -640,9 +654,14 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
             }
             if (tid < kNumKeys) sh.cnt[parity ^ 1][tid] = 0;
             __syncthreads();
+            held = -1;
             if (key >= 0) {
-                pos = (int)(sh.off[key] + rank);
-                write_features(feats + (size_t)(pos >> 5) * kChunkFloats + (pos & 31), L, key >> 1, a);
+                if (rank < sh.evalc[key]) {
+                    pos = (int)(sh.off[key] + rank);
+                    write_features(feats + (size_t)(pos >> 5) * kChunkFloats + (pos & 31), L, key >> 1, a);
+                } else {
+                    held = key;
+                }
             }
             P = pack_lane(L);
             __syncthreads();
@@ -661,7 +680,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
                 const int ns = splits_of(fam);
                 const unsigned int chunk = local / (unsigned int)ns;
                 const int out = (int)(local - chunk * (unsigned int)ns);
-                const unsigned int c = sh.cnt[parity][k];
+                const unsigned int c = sh.evalc[k];
                 const unsigned int idx = chunk * 32u + (unsigned int)lane;
                 const bool live = idx < c;
                 const unsigned int p = sh.off[k] + idx;      // idle lanes walk whatever their column holds
@@ -677,7 +696,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
             __syncthreads();
             parity ^= 1;
             rounds += 1;
-            requests += (key >= 0) ? 1ULL : 0ULL;
+            requests += (key >= 0 && held < 0) ? 1ULL : 0ULL;
         }
     }
     // ---- flush counters

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from typing import Optional
 
 import numpy as np
@@ -290,7 +291,9 @@ class Context:
                                          vp(stream), vp(trace), vp(iters)))
         out = dict(counters={k: int(counters[i]) for i, k in enumerate(COUNTER_NAMES)})
         if scores is not None:
-            out["scores"] = np.stack([(scores & 0xFFFF).astype(np.int32), (scores >> 16).astype(np.int32)], axis=1)
+            # score word = points A | points B << 16: on a little-endian host the uint16 view IS the [n, 2] table
+            out["scores"] = (scores.view(np.uint16).reshape(n, 2).astype(np.int32) if sys.byteorder == "little" else
+                             np.stack([(scores & 0xFFFF).astype(np.int32), (scores >> 16).astype(np.int32)], axis=1))
         if hist is not None:
             out["hist"] = hist
         if trace is not None:
