@@ -187,3 +187,33 @@ def test_full_size_properties(engine):
     assert pts == int(sc.sum())
     # both orientations played equally often
     assert int(r["hist"][0, 0].sum()) == n // 2 and int(r["hist"][0, 1].sum()) == n // 2
+
+
+def test_injected_stream_across_the_slate(engine, oracle, models_s2):
+    """Every orientation folds the forests differently (SP+ constants, constant trees, group depths):
+    bit-exact trajectories for a spread of real team pairs, strongest vs weakest included."""
+    from fast_monte_carlo_b200 import priors
+    sp = priors.load_sp_flex(priors.packaged_priors_path()).drop_duplicates(subset=["RATING", "OFFENSE", "DEFENSE"])
+    sp = sp.sort_values("RATING").reset_index(drop=True)
+    t = [tuple(float(x) for x in sp.loc[i, ["RATING", "OFFENSE", "DEFENSE"]]) for i in range(len(sp))]
+    pairs = [(t[-1], t[0]), (t[0], t[-1]), (t[10], t[11]), (t[60], t[100]), (t[-2], t[-3]), (t[33], t[7])]
+    n = 1024
+    stream = oracle.make_stream(n, 99)
+    for a, b in pairs:
+        engine.set_matchups([MatchupSpec("A", "B", a, b, n, 0, n, 0)])
+        got = engine.simulate_host(0, stream=stream, want_trace=True, want_iters=True)
+        ref = oracle.simulate(oracle.make_config(models_s2, a, b), n, stream=stream, trace=True)
+        assert np.array_equal(got["scores"], ref["scores"]), (a, b)
+        assert np.array_equal(got["iters"], ref["iters"]) and _trace_equal(got["trace"], ref["trace"]), (a, b)
+
+
+def test_visit_counter_and_gather_probe(engine):
+    """FMC_C_VISITS (node slots gathered by live requests) and the roofline probe report sane values."""
+    n = 20000
+    engine.set_matchups([MatchupSpec("A", "B", KSU, ISU, n, 0, n, 0)])
+    c = engine.simulate_host(3)["counters"]
+    per_request = c["visits"] / c["requests"]
+    assert 100 < per_request < 20000 and c["requests"] >= c["plays"]
+    l1 = engine.ctx.gather_probe(64 << 10, 500)
+    l2 = engine.ctx.gather_probe(8 << 20, 200)
+    assert l1 > l2 > 100.0          # GB/s
