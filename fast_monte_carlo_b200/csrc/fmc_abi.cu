@@ -180,8 +180,20 @@ struct fmc_ctx {
     unsigned long long *d_next = nullptr;
     std::vector<unsigned long long> h_next;
     std::vector<int32_t> packed_slots;   // [n_matchups][FMC_N_MODELS][2]
-    // predict scratch
-    TableArena pred_tables;
+    // fmc_tree_predict: packed + uploaded tables are kept per (model, tree range, hot columns) until the model
+    // or its columns change -- a stream of predict calls on the same model re-uses them
+    struct PredEntry {
+        int id = -1, tb = 0, te = 0, c0 = 0, c1 = 0;
+        uint64_t version = 0, last_use = 0;
+        TableArena arena;
+        TablePlacement pl;
+        int table = 0;
+        bool multi_window = false;
+    };
+    static constexpr int kPredEntries = 12;
+    PredEntry pred[kPredEntries];
+    uint64_t forest_version[FMC_N_MODELS] = {0};
+    uint64_t pred_clock = 0;
 };
 
 extern "C" const char *fmc_last_error(void) { return g_err.c_str(); }
@@ -218,7 +230,8 @@ extern "C" int fmc_create(int device, fmc_ctx **out) {
 extern "C" void fmc_destroy(fmc_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    c->sim_tables.release(); c->pred_tables.release();
+    c->sim_tables.release();
+    for (auto &e : c->pred) e.arena.release();
     cudaFree(c->d_matchups); cudaFree(c->d_next);
     delete c;
 }
@@ -238,6 +251,7 @@ extern "C" int fmc_load_forest(fmc_ctx *c, int32_t id, const fmc_forest_desc *d)
     const int32_t keep0 = c->forest[id].active[0], keep1 = c->forest[id].active[1];
     const bool had = c->forest[id].loaded;
     c->forest[id].assign(*d);
+    c->forest_version[id]++;
     if (!had) { c->forest[id].active[0] = -1; c->forest[id].active[1] = -1; }
     else { c->forest[id].active[0] = keep0; c->forest[id].active[1] = keep1; }
     c->tables_dirty = true;
@@ -249,6 +263,7 @@ extern "C" int fmc_set_scaler(fmc_ctx *c, int32_t id, int32_t n, const int32_t *
     HostForest &f = c->forest[id];
     f.n_scaled = n;
     for (int i = 0; i < n; ++i) { f.scaler_cols[i] = cols[i]; f.scaler_mean[i] = mean[i]; f.scaler_scale[i] = scale[i]; }
+    c->forest_version[id]++;
     c->tables_dirty = true;
     return FMC_OK;
 }
@@ -257,6 +272,7 @@ extern "C" int fmc_set_active_columns(fmc_ctx *c, int32_t id, int32_t col0, int3
     if (!c || id < 0 || id >= FMC_N_MODELS) return fail(FMC_ERR_INVALID, "fmc_set_active_columns: bad argument");
     c->forest[id].active[0] = col0;
     c->forest[id].active[1] = col1;
+    c->forest_version[id]++;
     c->tables_dirty = true;
     return FMC_OK;
 }
@@ -480,21 +496,34 @@ extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, 
     CK(cudaSetDevice(c->device));
     HostForest &f = c->forest[id];
     prescale(f);
-    PackSpec s;
-    preset_predict(s);
-    s.active[0] = f.active[0]; s.active[1] = f.active[1];
-    if (id == FMC_PLAY_MODEL) { s.active[0] = coach_col; s.active[1] = -1; }
-    s.tree_begin = tree_begin; s.tree_end = tree_end;
-    PackedForest pf;
-    const std::string err = pack_forest(f, s, pf);
-    if (!err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(id) + ": " + err);
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaStreamSynchronize(st));   // a previous launch may still read the scratch tables
-    TableArena &A = c->pred_tables;
-    A.clear();
-    TablePlacement pl;
-    const int table = A.place(pf, pl);
-    CK(A.upload(st, true));
+    const int c0 = id == FMC_PLAY_MODEL ? coach_col : f.active[0], c1 = id == FMC_PLAY_MODEL ? -1 : f.active[1];
+    fmc_ctx::PredEntry *E = nullptr, *lru = &c->pred[0];
+    for (auto &e : c->pred) {
+        if (e.id == id && e.tb == tree_begin && e.te == tree_end && e.c0 == c0 && e.c1 == c1 && e.version == c->forest_version[id]) { E = &e; break; }
+        if (e.last_use < lru->last_use) lru = &e;
+    }
+    if (!E) {
+        PackSpec s;
+        preset_predict(s);
+        s.active[0] = c0; s.active[1] = c1;
+        s.tree_begin = tree_begin; s.tree_end = tree_end;
+        PackedForest pf;
+        const std::string err = pack_forest(f, s, pf);
+        if (!err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(id) + ": " + err);
+        CK(cudaDeviceSynchronize());     // a launch in flight may still read the entry that is being replaced
+        E = lru;
+        E->id = -1;
+        E->arena.clear();
+        E->table = E->arena.place(pf, E->pl);
+        CK(E->arena.upload(st, true));
+        E->multi_window = pf.table_bytes() > kWindowBytes;
+        E->id = id; E->tb = tree_begin; E->te = tree_end; E->c0 = c0; E->c1 = c1; E->version = c->forest_version[id];
+    }
+    E->last_use = ++c->pred_clock;
+    TableArena &A = E->arena;
+    const TablePlacement &pl = E->pl;
+    const int table = E->table;
     PredictArgs a;
     std::memset(&a, 0, sizeof(a));
     a.rows = rows_dev; a.out = out_dev; a.n = n;
@@ -503,7 +532,7 @@ extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, 
     a.stream = A.d_stream; a.consts = A.d_consts;
     for (int k = 0; k < 8; ++k) { a.stream_off[k] = pl.stream_off[k]; a.consts_off[k] = pl.consts_off[k]; a.n_groups[k] = pl.n_groups[k]; }
     a.n_outputs = f.n_outputs; a.n_num = f.n_num;
-    a.multi_window = pf.table_bytes() > kWindowBytes ? 1 : 0;
+    a.multi_window = E->multi_window ? 1 : 0;
     a.zero_is_missing = (f.kind == FMC_KIND_XGB && f.zero_is_missing) ? 1 : 0;
     for (int k = 0; k < 8; ++k) a.base[k] = f.base[k];
     a.n_scaled = f.n_scaled;

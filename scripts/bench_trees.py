@@ -73,6 +73,6 @@ print(json.dumps({
     "algorithmic_bytes_per_state": algo, "algorithmic_gbs": algo * n_done / msec * 1e3 / 1e9,
     "models": [name for _, name in models], "batch": batch,
     "note": "fmc_tree_predict on resident float64 [n][17] rows, general rows (nothing folded but the one-hots); "
-            "the host re-packs + uploads the forest tables on every call (inside the timed region)",
+            "packed tables are cached per model in the context (packed + uploaded once, before the timed region)",
     "checksum": float(sum(o.sum().item() for o in outs.values())),
 }))
