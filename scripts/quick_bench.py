@@ -24,4 +24,5 @@ for _ in range(3):
     e0.record(); step(); e1.record(); torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1))
 c = cnt.cpu().numpy()
+print(f"rounds/CTA {c[15]/148:.0f} requests {c[16]:.4g} visits/request {c[17]/max(c[16],1):.0f} us/round {best*1e3/(c[15]/148):.1f}")
 print(f"{os.environ.get('FMC_LIB_PATH','default')}: {games} games {best:.1f} ms -> {games/best*1e3:.3e} games/s {c[1]/best*1e3:.3e} plays/s  checksum {int(hist.to(torch.int64).mul(torch.arange(128*128*2, device='cuda').view(1,2,128,128)).sum())}")
