@@ -347,7 +347,10 @@ def run_ours(args):
 
     # ---- end-to-end through the C-ABI host-buffer call --------------------------------------------------
     e2e_plays, e2e_t = 0, 0.0
+    e2e_steps_s = []
     h2d = d2h = 0
+    sampler2 = ClockSampler(local)
+    sampler2.start()
     table_bytes = sum(int(eng.ctx.packed_slots(i).sum()) for i in range(n_m)) * 8
     for i in range(args.e2e_steps + 1):
         if world > 1:
@@ -370,9 +373,11 @@ def run_ours(args):
             dist.all_reduce(pp)
         e2e_t += float(tt[0])
         e2e_plays += int(pp[0])
+        e2e_steps_s.append(float(tt[0]))
         h2d = table_bytes + 200 + 8
         d2h = G * 4 + int(np.prod(r["hist"].shape)) * 4 + native.N_COUNTERS * 8
     e2e_value = e2e_plays / e2e_t if e2e_t > 0 else None
+    e2e_clocks = sampler2.stop()
 
     if rank == 0:
         # achievable gather rates on this GPU (8-byte dependent gathers, fmc_gather_probe): the denominators the
@@ -395,9 +400,11 @@ def run_ours(args):
             "games_per_sec": games_step * args.steps / (total_ms / 1e3),
             "plays_per_game": plays_step / games_step,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "step_seconds": e2e_steps_s, "clocks": e2e_clocks,
                     "how": "fmc_simulate_host through ctypes: forest specialisation + table upload, kernel, "
                            "per-game scores + histogram + counters copied to host; host wall clock, max over ranks"},
             "gpu_launches": args.steps,
+            "step_ms": step_ms,
             "clocks": clocks,
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
