@@ -45,9 +45,10 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--games", type=int, default=10_000_000, help="games per GPU per step (matchup workload)")
-    ap.add_argument("--workload", default="matchup", choices=["matchup", "slate"],
+    ap.add_argument("--workload", default="matchup", choices=["matchup", "slate", "season"],
                     help="matchup = BASELINE configs[1] (default, the headline); slate = configs[3]: 60 matchups x "
-                         "--slate-games games each, sharded over the GPUs by contiguous game-id ranges (strong scaling)")
+                         "--slate-games games each, sharded over the GPUs by contiguous game-id ranges (strong scaling); "
+                         "season = configs[4]: 12 weekly slates of 60 matchups from seeded shuffles of the 136 teams")
     ap.add_argument("--slate-games", type=int, default=1_000_000, help="games per matchup of the slate workload")
     ap.add_argument("--stage2", default="synthetic", choices=["synthetic", "standin"])
     ap.add_argument("--cpu-games", type=int, default=0, help="games of the bounded CPU sample (0 = auto)")
@@ -64,7 +65,35 @@ def slate_pairs():
     return [(teams[2 * i], teams[2 * i + 1]) for i in range(60)], sp
 
 
+def season_pairs():
+    """12 weeks x 60 matchups, week w = default_rng(2025 + w) shuffle of the 136 teams,
+    paired (2i, 2i+1)."""
+    import numpy as np
+    from fast_monte_carlo_b200 import priors
+    sp = priors.load_sp_flex(priors.packaged_priors_path())
+    teams = list(sp.drop_duplicates(subset=["RATING", "OFFENSE", "DEFENSE"])["team"])
+    pairs = []
+    for week in range(1, 13):
+        order = np.random.default_rng(2025 + week).permutation(len(teams))
+        pairs += [(teams[order[2 * i]], teams[order[2 * i + 1]]) for i in range(60)]
+    return pairs, sp
+
+
 def workload(args, n_gpus):
+    if args.workload == "season":
+        return {
+            "workload": "configs[4]: season slate, 12 weeks x 60 matchups (seeded shuffles of the 136 teams of "
+                        f"PregameSPPlus2025_1) x {args.slate_games:,} simulated games each, contiguous game-id shards "
+                        f"over {n_gpus} GPU(s), Philox seed {SEED}",
+            "total_games_per_step": 720 * args.slate_games,
+            "play_call": "pass_prob_v1 heuristic (reference behaviour when play_model.json is absent)",
+            "stage2": ("synthetic booster of the trained shape (1086 trees, depth<=7)" if args.stage2 == "synthetic"
+                       else "fixed stand-in probabilities"),
+            "players": "Unknown (no usage tables shipped)",
+            "parallelism": f"every matchup's games sharded over {n_gpus} GPU(s); one NCCL all-reduce of the "
+                           "[720][2][128][128] histograms per step",
+            "l2": "flushed between timed steps (256 MiB write); node tables: 720 matchups x ~0.6 MB",
+        }
     if args.workload == "slate":
         return {
             "workload": "configs[3]: full-slate run, 60 matchups (first 120 teams of PregameSPPlus2025_1 paired) x "
@@ -273,12 +302,12 @@ def run_ours(args):
     from fast_monte_carlo_b200.engine import Engine, MatchupSpec
     ms = load_models(args.stage2)
     eng = Engine(ms, device=local, stage2="booster" if args.stage2 == "synthetic" else "standin")
-    if args.workload == "slate":
+    if args.workload in ("slate", "season"):
         from fast_monte_carlo_b200 import api
-        pairs, sp_df = slate_pairs()
+        pairs, sp_df = slate_pairs() if args.workload == "slate" else season_pairs()
         spec = api.slate_specs(pairs, args.slate_games, sp_df, rank, world)
         G = sum(m.game_end - m.game_begin for m in spec)          # this rank's games per step
-        total_games = 60 * args.slate_games
+        total_games = len(pairs) * args.slate_games
     else:
         G = args.games
         g0, g1 = rank * G, (rank + 1) * G
@@ -395,7 +424,7 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.workload == "slate" else "weak", "vs_baseline": None, "dtype": "f64",
+            "scaling": "weak" if args.workload == "matchup" else "strong", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload(args, n_gpus),
             "games_per_sec": games_step * args.steps / (total_ms / 1e3),
             "plays_per_game": plays_step / games_step,

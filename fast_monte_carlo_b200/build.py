@@ -17,6 +17,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     # float64 game state must round like CPython evaluates the reference's expressions: no FMA contraction
     "-fmad=false",
+    "-Xcompiler", "-pthread",      # the forest packer of fmc_set_matchups runs on all host threads
 ]
 
 

@@ -1,10 +1,12 @@
 // C ABI of libfmc_b200.so (include/fmc.h): context, forest specialisation/upload, the tree-predict
 // kernel launch and the persistent simulation kernel launch.  No CPU fallback anywhere: every
 // compute entry point launches a kernel or fails.
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "fmc_sim.cuh"
@@ -314,6 +316,44 @@ static int build_tables(fmc_ctx *c) {
     TableArena &A = c->sim_tables;
     A.clear();
     c->packed_slots.assign((size_t)n * FMC_N_MODELS * 2, 0);
+    // ---- specialise + pack every (matchup, orientation, family) forest; the jobs are independent, a slate
+    // of hundreds of matchups is packed by all host threads
+    struct Job { int matchup, off, fam; PackedForest pf; std::string err; };
+    std::vector<Job> jobs;
+    for (int i = 0; i < n; ++i)
+        for (int off = 0; off < 2; ++off)
+            for (int fam = 0; fam < kNumFam; ++fam)
+                if (family_needed(c, fam)) { jobs.emplace_back(); jobs.back().matchup = i; jobs.back().off = off; jobs.back().fam = fam; }
+    auto run_job = [&](Job &j) {
+        const fmc_matchup &mu = c->matchups[j.matchup];
+        const int off = j.off, de = off ^ 1, fam = j.fam;
+        const HostForest &f = c->forest[fam];
+        PackSpec s;
+        preset_sim(s);
+        s.active[0] = f.active[0]; s.active[1] = f.active[1];
+        if (fam == FMC_PLAY_MODEL) { s.active[0] = mu.coach_col[off]; s.active[1] = -1; }
+        s.fold_value[6] = 3.0; s.fold_value[7] = 3.0;    // timeouts are never spent (FMC:911-912)
+        s.fold_value[8] = mu.sp[off][0]; s.fold_value[9] = mu.sp[off][1];
+        s.fold_value[10] = mu.sp[de][2]; s.fold_value[11] = mu.sp[de][0];
+        s.n_scaled = f.n_scaled;
+        for (int k = 0; k < f.n_scaled; ++k) { s.scaler_cols[k] = f.scaler_cols[k]; s.scaler_mean[k] = f.scaler_mean[k]; s.scaler_scale[k] = f.scaler_scale[k]; }
+        j.err = pack_forest(f, s, j.pf);
+    };
+    {
+        unsigned nt = std::thread::hardware_concurrency();
+        if (nt == 0) nt = 1;
+        if (nt > 32) nt = 32;
+        if (jobs.size() < 24) nt = 1;
+        if (nt <= 1) {
+            for (Job &j : jobs) run_job(j);
+        } else {
+            std::atomic<size_t> next{0};
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nt; ++t)
+                pool.emplace_back([&]() { for (size_t k; (k = next.fetch_add(1)) < jobs.size();) run_job(jobs[k]); });
+            for (auto &th : pool) th.join();
+        }
+    }
     for (int i = 0; i < n; ++i) {
         const fmc_matchup &mu = c->matchups[i];
         MatchupDev &M = md[i];
@@ -326,38 +366,28 @@ static int build_tables(fmc_ctx *c) {
             M.ymul[off] = 1.0 + 0.10 * std::tanh((O - D) / 30.0);  // yardage_multiplier FMC:435-437
             M.mz[off] = (O - D) / 40.0;                          // mismatch_z FMC:440-442
             M.tanh35[off] = std::tanh((O - D) / 35.0);           // FMC:448, 456
-            for (int fam = 0; fam < kNumFam; ++fam) {
-                if (!family_needed(c, fam)) continue;
-                const HostForest &f = c->forest[fam];
-                PackSpec s;
-                preset_sim(s);
-                s.active[0] = f.active[0]; s.active[1] = f.active[1];
-                if (fam == FMC_PLAY_MODEL) { s.active[0] = mu.coach_col[off]; s.active[1] = -1; }
-                s.fold_value[6] = 3.0; s.fold_value[7] = 3.0;    // timeouts are never spent (FMC:911-912)
-                s.fold_value[8] = mu.sp[off][0]; s.fold_value[9] = mu.sp[off][1];
-                s.fold_value[10] = mu.sp[de][2]; s.fold_value[11] = mu.sp[de][0];
-                s.n_scaled = f.n_scaled;
-                for (int j = 0; j < f.n_scaled; ++j) { s.scaler_cols[j] = f.scaler_cols[j]; s.scaler_mean[j] = f.scaler_mean[j]; s.scaler_scale[j] = f.scaler_scale[j]; }
-                PackedForest pf;
-                const std::string err = pack_forest(f, s, pf);
-                if (!err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(fam) + ": " + err);
-                if (pf.n_outputs > 5) return fail(FMC_ERR_CAPACITY, "more than 5 outputs in a simulation model");
-                TableRef &T = M.tbl[fam][off];
-                TablePlacement pl;
-                const int table = A.place(pf, pl);
-                for (int k = 0; k < pf.n_outputs; ++k) {
-                    if (pl.n_groups[k] > 0xFFFFu) return fail(FMC_ERR_CAPACITY, "too many tree groups in one output");
-                    T.stream_off[k] = pl.stream_off[k]; T.consts_off[k] = pl.consts_off[k]; T.n_groups[k] = (uint16_t)pl.n_groups[k];
-                }
-                T.n_outputs = (uint8_t)pf.n_outputs;
-                T.max_depth = (uint8_t)pf.max_depth;
-                T.multi_window = pf.table_bytes() > kWindowBytes ? 1 : 0;
-                for (int k = 0; k < 5 && k < f.n_outputs; ++k) T.base[k] = (float)f.base[k];
-                for (int k = 0; k < 3 && k < f.n_outputs; ++k) T.base64[k] = f.base[k];
-                placed.push_back({i, fam, off, table});
-                c->packed_slots[((size_t)i * FMC_N_MODELS + fam) * 2 + off] = (int32_t)pf.slots.size();
-            }
         }
+    }
+    for (Job &j : jobs) {
+        if (!j.err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(j.fam) + ": " + j.err);
+        PackedForest &pf = j.pf;
+        const HostForest &f = c->forest[j.fam];
+        if (pf.n_outputs > 5) return fail(FMC_ERR_CAPACITY, "more than 5 outputs in a simulation model");
+        TableRef &T = md[j.matchup].tbl[j.fam][j.off];
+        TablePlacement pl;
+        const int table = A.place(pf, pl);
+        for (int k = 0; k < pf.n_outputs; ++k) {
+            if (pl.n_groups[k] > 0xFFFFu) return fail(FMC_ERR_CAPACITY, "too many tree groups in one output");
+            T.stream_off[k] = pl.stream_off[k]; T.consts_off[k] = pl.consts_off[k]; T.n_groups[k] = (uint16_t)pl.n_groups[k];
+        }
+        T.n_outputs = (uint8_t)pf.n_outputs;
+        T.max_depth = (uint8_t)pf.max_depth;
+        T.multi_window = pf.table_bytes() > kWindowBytes ? 1 : 0;
+        for (int k = 0; k < 5 && k < f.n_outputs; ++k) T.base[k] = (float)f.base[k];
+        for (int k = 0; k < 3 && k < f.n_outputs; ++k) T.base64[k] = f.base[k];
+        placed.push_back({j.matchup, j.fam, j.off, table});
+        c->packed_slots[((size_t)j.matchup * FMC_N_MODELS + j.fam) * 2 + j.off] = (int32_t)pf.slots.size();
+        PackedForest().slots.swap(pf.slots);     // release as we go
     }
     CK(cudaSetDevice(c->device));
     CK(A.upload(nullptr, true));
