@@ -217,3 +217,45 @@ def test_visit_counter_and_gather_probe(engine):
     l1 = engine.ctx.gather_probe(64 << 10, 500)
     l2 = engine.ctx.gather_probe(8 << 20, 200)
     assert l1 > l2 > 100.0          # GB/s
+
+
+def test_adversarial_injected_streams(oracle, models_s2):
+    """Draw streams that force the rare branches: every uniform at 0 / just below 1, huge normals (sacks that
+    push yardsToGoal past 100, negative field position, long fourth-down sequences, down >= 5 chains,
+    touchback punts, missed field goals), and per-slot mixtures -- bit-exact against the oracle."""
+    from oracle import c_oracle as co
+    n = 512
+    rng = np.random.default_rng(123)
+    base = oracle.make_stream(n, 5)
+    normal = list(co.NORMAL_SLOTS)
+    uniform = [s for s in range(base.shape[2]) if s not in normal]
+    streams = []
+    for u, z in ((0.0, -4.0), (1.0 - 2.0 ** -40, 4.0), (0.5, 0.0), (1e-12, 3.0), (0.999, -3.0)):
+        s = base.copy()
+        s[:, :, uniform] = u
+        s[:, :, normal] = z
+        streams.append(s)
+    for _ in range(3):                      # per-game, per-slot extremes mixed with ordinary draws
+        s = base.copy()
+        mask = rng.random(s.shape) < 0.35
+        ext = np.where(rng.random(s.shape) < 0.5, 0.0, 1.0 - 2.0 ** -33)
+        zext = np.where(rng.random(s.shape) < 0.5, -5.0, 5.0)
+        s[:, :, uniform] = np.where(mask[:, :, uniform], ext[:, :, uniform], s[:, :, uniform])
+        s[:, :, normal] = np.where(mask[:, :, normal], zext[:, :, normal], s[:, :, normal])
+        streams.append(s)
+    for variant in (dict(stage2="booster"), dict(stage2="booster", policy="play_model", sampler="quantile_interp")):
+        e = _engine_variant(models_s2, **variant)
+        try:
+            e.set_matchups([MatchupSpec("Kansas State", "Iowa State", KSU, ISU, n, 0, n, 0)])
+            cfg = oracle.make_config(models_s2, KSU, ISU, policy=variant.get("policy", "heuristic"),
+                                     coach_cols=(e.coach_col("Kansas State"), e.coach_col("Iowa State")),
+                                     sampler=variant.get("sampler", "normal"), stage2="booster")
+            for k, s in enumerate(streams):
+                got = e.simulate_host(0, stream=s, want_trace=True, want_iters=True)
+                ref = oracle.simulate(cfg, n, stream=s, trace=True)
+                assert np.array_equal(got["scores"], ref["scores"]), k
+                assert np.array_equal(got["iters"], ref["iters"]) and _trace_equal(got["trace"], ref["trace"]), k
+                for c in ("plays", "iters", "pass", "comp", "inc", "int", "sack", "run", "td", "fga", "fg", "punt", "go"):
+                    assert got["counters"][c] == ref["counters"][c], (k, c)
+        finally:
+            e.close()
