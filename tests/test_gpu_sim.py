@@ -45,6 +45,24 @@ def test_reference_golden_trajectories(engine):
             assert r["counters"]["plays"] == int(t["plays"][g])
 
 
+def test_reference_golden_adversarial_trajectories(engine):
+    """The reference's OWN states under adversarial draws (tests/golden/ref_trajectories_adversarial.npz)."""
+    from streams import adversarial_stream
+    t = np.load(os.path.join(GOLDEN, "ref_trajectories_adversarial.npz"))
+    meta = json.loads(str(t["meta"]))
+    stream = adversarial_stream(len(meta), int(t["stream_seed"]))
+    for g, m in enumerate(meta):
+        spA, spB = (m["sp_second"], m["sp_first"]) if g & 1 else (m["sp_first"], m["sp_second"])
+        engine.set_matchups([MatchupSpec("A", "B", tuple(spA), tuple(spB), 1, g, g + 1, 0)])
+        r = engine.simulate_host(0, stream=stream[g:g + 1], want_trace=True, want_iters=True)
+        k = int(t["iters"][g])
+        assert r["iters"][0] == k, (g, m["pattern"])
+        assert np.array_equal(r["trace"][0, :k], t["traces"][g, :k]), (g, m["pattern"])
+        f = g & 1
+        assert (r["scores"][0, f], r["scores"][0, f ^ 1]) == tuple(t["scores"][g])
+        assert r["counters"]["plays"] == int(t["plays"][g])
+
+
 @pytest.mark.parametrize("spa,spb", [(KSU, ISU), ((0.0, 28.0, 27.5), (31.7, 41.9, 10.1))])
 def test_injected_stream_bit_exact_16384(engine, oracle, models_s2, spa, spb):
     """BASELINE config 2's check: 16,384 games, [games, 360, 16] float64 draws from default_rng(7)."""

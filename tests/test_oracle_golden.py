@@ -96,6 +96,27 @@ def test_reference_trajectories_bit_exact(models, oracle):
         assert r["counters"]["plays"] == int(t["plays"][g])
 
 
+def test_reference_trajectories_adversarial_streams(models, oracle):
+    """The reference's own simulate_game under ADVERSARIAL draws (tests/streams.py): uniforms pinned at 0 / just
+    below 1, +-4 sigma normals, mixtures -- the rare branches (touchback punts, missed field goals, sacks past
+    the 100-yard line, down >= 5 chains, 112-112 shoot-outs), bit for bit."""
+    from streams import adversarial_stream
+    t = np.load(os.path.join(GOLDEN, "ref_trajectories_adversarial.npz"))
+    meta = json.loads(str(t["meta"]))
+    stream = adversarial_stream(len(meta), int(t["stream_seed"]))
+    assert int(t["scores"].max()) >= 112 and int(t["scores"].min()) == 0
+    for g, m in enumerate(meta):
+        spA, spB = (m["sp_second"], m["sp_first"]) if g & 1 else (m["sp_first"], m["sp_second"])
+        cfg = oracle.make_config(models, spA, spB)
+        r = oracle.simulate(cfg, 1, game0=g, stream=stream[g:g + 1], trace=True, threads=1)
+        n = int(t["iters"][g])
+        assert r["iters"][0] == n, (g, m["pattern"])
+        assert np.array_equal(r["trace"][0, :n], t["traces"][g, :n]), (g, m["pattern"])
+        first = g & 1
+        assert (r["scores"][0, first], r["scores"][0, first ^ 1]) == tuple(t["scores"][g])
+        assert r["counters"]["plays"] == int(t["plays"][g])
+
+
 def test_oracle_threads_and_determinism(models, oracle):
     cfg = oracle.make_config(models, (15.6, 35.7, 20.0), (11.0, 31.5, 20.6))
     a = oracle.simulate(cfg, 64, seed=5, threads=1)
