@@ -16,7 +16,9 @@ namespace fmc {
 // iteration << 2 | block), key = seed.  One call yields the four 32-bit words of one block of the
 // 16-slot draw record.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+// (not inlined: the draw sites are many and divergent, one shared copy keeps the state machine's
+// instruction footprint -- its real bottleneck, `stall_no_inst` 33 % -- small; +2.5 %)
+__device__ __noinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
@@ -167,6 +169,7 @@ __device__ __forceinline__ void accumulate_group(const uint2 (&n)[kIlp], bool ha
 #pragma unroll
     for (int i = 0; i < kIlp; ++i) {
         const uint32_t c = (counts >> (8 * i)) & 0xFFu;
+#pragma unroll 1
         for (uint32_t j = 0; j < c; ++j) {
             const uint2 v = __ldg(cp);
             ++cp;
