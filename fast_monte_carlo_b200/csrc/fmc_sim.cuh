@@ -140,6 +140,9 @@ __device__ __forceinline__ double softclip(double x, double lo, double hi) {
     return (m > lo) ? m : lo;
 }
 
+// TEST = true: the launch has an injected draw stream and/or a trace buffer (parity tests); the production
+// instantiation carries neither branch.
+template <bool TEST>
 struct Draws {
     const SimKernelArgs &a;
     const double *rec;        // injected record base for this game (or nullptr)
@@ -147,8 +150,8 @@ struct Draws {
     uint32_t have;            // bit b: block b cached
     uint4 w[4];
     __device__ Draws(const SimKernelArgs &a_, const MatchupDev &M, int matchup, const Lane &L) : a(a_) {
-        rec = a.stream ? a.stream + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_N_SLOTS
-                       : nullptr;
+        rec = (TEST && a.stream) ? a.stream + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_N_SLOTS
+                                 : nullptr;
         ctr = make_uint4((uint32_t)L.game, (uint32_t)(L.game >> 32), (uint32_t)matchup, (uint32_t)L.iter << 2);
         have = 0;
     }
@@ -164,8 +167,8 @@ struct Draws {
         const int j = slot & 3;
         return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
     }
-    __device__ __forceinline__ double u(int slot) { return rec ? rec[slot] : u01(word(slot)); }
-    __device__ __forceinline__ double z(int slot) { return rec ? rec[slot] : ppnd16(u01(word(slot))); }
+    __device__ __forceinline__ double u(int slot) { return (TEST && rec) ? rec[slot] : u01(word(slot)); }
+    __device__ __forceinline__ double z(int slot) { return (TEST && rec) ? rec[slot] : ppnd16(u01(word(slot))); }
 };
 
 // ---- state transitions -------------------------------------------------------------------------
@@ -244,7 +247,8 @@ __device__ __forceinline__ double go_for_it_prob(double ytg, double dist, int sd
 }
 
 // yardage samplers FMC:817-852 / sim_helpers.py:32-38
-__device__ __forceinline__ double sample_yards(const SimKernelArgs &a, Draws &D, const double q[3], double sig_floor,
+template <bool TEST>
+__device__ __forceinline__ double sample_yards(const SimKernelArgs &a, Draws<TEST> &D, const double q[3], double sig_floor,
                                                double lo, double hi) {
     if (a.sampler == 0) {
         const double sigma = pymax(sig_floor, (q[2] - q[0]) / 2.56);
@@ -310,6 +314,7 @@ __device__ __forceinline__ int stage2_outcome(const double raw[3], double u2) {
 
 // Advance one lane until it posts a request (returns key = family * 2 + offense) or has nothing
 // left to do (returns -1).  `res` points at this lane's result record of the previous round.
+template <bool TEST>
 __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, SimShared &sh, const double *res) {
     const MatchupDev &M = sh.M;
     const int matchup = sh.cur_matchup;
@@ -342,14 +347,14 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
                 L.stage = ST_NEED_GAME;
                 continue;
             }
-            if (a.trace && L.iter < FMC_MAX_ITERS) {
+            if (TEST && a.trace && L.iter < FMC_MAX_ITERS) {
                 const int first = (int)(L.game & 1ULL);
                 double *t = a.trace + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_TRACE_COLS;
                 t[0] = (L.offense == first) ? 1.0 : 0.0; t[1] = (double)L.down; t[2] = (double)L.sec;
                 t[3] = (double)L.score[first]; t[4] = (double)L.score[first ^ 1]; t[5] = L.dist; t[6] = L.ytg;
                 t[7] = (double)L.going;
             }
-            Draws D(a, M, matchup, L);
+            Draws<TEST> D(a, M, matchup, L);
             L.iter += 1;
             const int team = L.offense;
             const int sd = L.score[team] - L.score[team ^ 1];
@@ -398,7 +403,7 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
         // ---- resuming a parked play: the iteration counter already points past this iteration
         Lane Lv = L;
         Lv.iter = L.iter - 1;
-        Draws D(a, M, matchup, Lv);
+        Draws<TEST> D(a, M, matchup, Lv);
         const int team = L.offense;
         const int sd = L.score[team] - L.score[team ^ 1];
         const double mz = M.mz[team];
@@ -570,6 +575,7 @@ __device__ __forceinline__ double eval_output(int fam, const TableRef &T, int ou
     return walk_output<false, false>(F, fcol, lane, (double)T.base[out], levels);
 }
 
+template <bool TEST>
 __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const SimKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SimShared &sh = *reinterpret_cast<SimShared *>(smem_raw);
@@ -625,7 +631,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
         for (;;) {
             // ---- A: advance to the next request (a held-back lane re-posts the one it has)
             Lane L = unpack_lane(P);
-            const int key = held >= 0 ? held : advance_lane(L, a, sh, results + (size_t)pos * 3);
+            const int key = held >= 0 ? held : advance_lane<TEST>(L, a, sh, results + (size_t)pos * 3);
             __syncwarp();
             // ---- B: compaction
             unsigned int rank = 0;
