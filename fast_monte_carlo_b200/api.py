@@ -162,3 +162,57 @@ def merge_histograms(hist, counters=None):
         if counters is not None:
             dist.all_reduce(counters, op=dist.ReduceOp.SUM)
     return hist, counters
+
+
+def simulate_slate(pairs: Sequence[Tuple[str, str]], n: int = 1000, *, sp_path: Optional[str] = None,
+                   year: int = 2025, week: int = 1, seed: Optional[int] = None,
+                   engine: Optional[Engine] = None, markets: Optional[Dict[Tuple[str, str], Dict[str, float]]] = None):
+    """A whole slate in one launch (BASELINE configs 3-4): every (teamA, teamB) of `pairs` is simulated for
+    `n` PAIRS of games (2n games, A receives / B receives alternately, exactly like `simulate_matchup`).
+
+    Under torch.distributed (one process per GPU) every rank plays its contiguous game-id slice of every
+    matchup and the integer histograms are merged with ONE all-reduce; the result does not depend on the
+    number of ranks.  No per-game table is materialised: everything `edge_finder.py` derives from
+    `scores_*` -- `summary` (FMC:1681-1687), moneyline (edge_finder.py:249-281) and, for pairs listed in
+    `markets` ({(A, B): {"spread": s, "total": t}}), spread / total odds (edge_finder.py:283-336) -- comes
+    from the joint score histogram.  Returns {(A, B): {"hist", "summary", "moneyline", "markets", "games"}},
+    plus the key "_counters" with the event counters of the whole slate.
+    """
+    import torch
+    import torch.distributed as dist
+    eng = engine if engine is not None else get_engine()
+    sp_df = load_sp_flex(sp_path if sp_path is not None else packaged_priors_path())
+    for a, b in pairs:                                    # same errors as the reference for unknown teams
+        build_team_context_from_sp_flex(a, year, week, sp_df)
+        build_team_context_from_sp_flex(b, year, week, sp_df)
+    rank, world = 0, 1
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(), dist.get_world_size()
+    specs = slate_specs(pairs, 2 * int(n), sp_df, rank, world)
+    eng.set_matchups(specs)
+    dev = torch.device("cuda", eng.ctx.device)
+    hist = torch.zeros((len(specs), 2, outputs.HIST_BINS, outputs.HIST_BINS), dtype=torch.int32, device=dev)
+    counters = torch.zeros(len(native_counter_names()), dtype=torch.int64, device=dev)
+    padded = torch.zeros(32, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream(dev)
+    eng.ctx.simulate_device(seed=_fresh_seed() if seed is None else int(seed), hist=hist.data_ptr(),
+                            counters=padded.data_ptr(), cuda_stream=st.cuda_stream)
+    hist64 = hist.to(torch.int64)
+    counters.copy_(padded[:counters.numel()])
+    merge_histograms(hist64, counters)
+    h = hist64.cpu().numpy()
+    c = counters.cpu().numpy()
+    out: Dict[object, object] = {"_counters": {k: int(c[i]) for i, k in enumerate(native_counter_names())}}
+    for m, (a, b) in enumerate(pairs):
+        entry = {"hist": h[m], "games": int(h[m].sum()), "summary": outputs.summary_from_hist(h[m], a, b),
+                 "moneyline": outputs.moneyline_from_hist(h[m], a, b), "markets": None}
+        mk = (markets or {}).get((a, b))
+        if mk:
+            entry["markets"] = outputs.game_market_odds_from_hist(h[m], a, b, spread=mk.get("spread"), total=mk.get("total"))
+        out[(a, b)] = entry
+    return out
+
+
+def native_counter_names():
+    from .native import COUNTER_NAMES
+    return COUNTER_NAMES

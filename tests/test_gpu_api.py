@@ -46,3 +46,29 @@ def test_unknown_team_raises(engine):
     with pytest.raises(ValueError, match="not found in provided SP\\+ table"):
         api.simulate_upcoming_matchup("Nowhere Tech", "Iowa State", sp_path=priors.packaged_priors_path(), n=1,
                                       engine=engine)
+
+
+def test_simulate_slate_matches_per_matchup_runs(engine):
+    """One launch for a slate == the matchups simulated one by one (same seed => same games, since the Philox
+    counter carries the matchup index only through the per-matchup game ids... and the matchup id)."""
+    pairs = [("Kansas State", "Iowa State"), ("UTSA", "Ohio State"), ("Texas", "Michigan")]
+    res = api.simulate_slate(pairs, n=400, seed=7, engine=engine,
+                             markets={("Kansas State", "Iowa State"): {"spread": -3.5, "total": 55.5}})
+    assert res["_counters"]["games"] == 3 * 800
+    sp = priors.load_sp_flex(priors.packaged_priors_path())
+    from fast_monte_carlo_b200.engine import MatchupSpec
+    for m, (a, b) in enumerate(pairs):
+        e = res[(a, b)]
+        assert e["games"] == 800 and e["hist"].shape == (2, 128, 128)
+        assert int(e["hist"][0].sum()) == 400 and int(e["hist"][1].sum()) == 400
+        assert set(e["summary"].index) == {a, b}
+        assert 0.0 <= e["moneyline"]["team"]["p_win"] <= 1.0
+    assert res[("Kansas State", "Iowa State")]["markets"]["spread"]["samples"] == 400
+    assert res[("UTSA", "Ohio State")]["markets"] is None
+    # the slate's first matchup is the same stream of games as a single-matchup launch (matchup index 0)
+    engine.set_matchups([MatchupSpec("Kansas State", "Iowa State", priors.lookup_sp_flex("Kansas State", sp),
+                                     priors.lookup_sp_flex("Iowa State", sp), 800, 0, 800, 0)])
+    single = engine.simulate_host(7)
+    assert np.array_equal(single["hist"][0].astype(np.int64), res[("Kansas State", "Iowa State")]["hist"])
+    with pytest.raises(ValueError):
+        api.simulate_slate([("Nowhere Tech", "Iowa State")], n=1, engine=engine)
