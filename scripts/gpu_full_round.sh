@@ -1,4 +1,6 @@
 #!/bin/bash
+# one gpurun call: GPU tests, bench.py (both arms), tree microbench, ncu launch list of the bench command,
+# ncu --set full capture of sim_kernel
 set -x
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q > gpurun_out/gputests.log 2>&1
@@ -9,6 +11,7 @@ python bench.py --impl reference --steps 1 --warmup 1 > gpurun_out/bench_ref.jso
 cat gpurun_out/bench_ref.json
 python scripts/bench_trees.py 67108864 > gpurun_out/trees.json 2> gpurun_out/trees.err
 cat gpurun_out/trees.json; tail -3 gpurun_out/trees.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --games 500000 --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launch.log 2>&1
+# launch list of the bench command itself (every kernel once, gpu__time_duration only)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_launch.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:sim_kernel -c 1 -o gpurun_out/prof_sim_latest python scripts/quick_bench.py 500000 > gpurun_out/ncu.log 2>&1
 tail -2 gpurun_out/ncu.log
