@@ -166,6 +166,14 @@ struct TableArena {
     }
 };
 
+#ifdef FMC_DEBUG_CHECKS
+static void debug_set_range(const TableArena &A) {
+    const unsigned long long lo = (unsigned long long)(uintptr_t)A.d_nodes, hi = lo + A.h_nodes.size() * 8;
+    cudaMemcpyToSymbol(g_dbg_lo, &lo, 8);
+    cudaMemcpyToSymbol(g_dbg_hi, &hi, 8);
+}
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------------------------
@@ -458,6 +466,9 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
     a.scores = g->scores_dev; a.hist = g->hist_dev; a.counters = (unsigned long long *)g->counters_dev;
     a.stream = g->stream_dev; a.trace = g->trace_dev; a.iters = g->iters_dev;
     const int grid = c->prop.multiProcessorCount * kSimCtasPerSm;
+#ifdef FMC_DEBUG_CHECKS
+    debug_set_range(c->sim_tables);
+#endif
     if (a.stream || a.trace) sim_kernel<true><<<grid, kSimThreads, sim_smem_bytes(), st>>>(a);   // parity-test instantiation
     else sim_kernel<false><<<grid, kSimThreads, sim_smem_bytes(), st>>>(a);
     CK(cudaGetLastError());
@@ -569,6 +580,9 @@ extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, 
     for (int k = 0; k < 8; ++k) a.base[k] = f.base[k];
     a.n_scaled = f.n_scaled;
     for (int j = 0; j < f.n_scaled; ++j) { a.scaler_cols[j] = f.scaler_cols[j]; a.scaler_mean[j] = f.scaler_mean[j]; a.scaler_scale[j] = f.scaler_scale[j]; }
+#ifdef FMC_DEBUG_CHECKS
+    debug_set_range(A);
+#endif
     long long blocks = (n + kPredThreads - 1) / kPredThreads;
     const long long cap = (long long)c->prop.multiProcessorCount * 8;
     if (blocks > cap) blocks = cap;
@@ -601,6 +615,18 @@ extern "C" int fmc_tree_predict_host(fmc_ctx *c, int32_t id, const double *rows_
     return FMC_OK;
 }
 
+// Diagnostics: number of out-of-range gathers / feature offsets seen by a library built with
+// -DFMC_DEBUG_CHECKS (always 0 for the production build), counted since the last call.
+extern "C" int64_t fmc_debug_errors(void) {
+#ifdef FMC_DEBUG_CHECKS
+    unsigned long long v = 0, z = 0;
+    if (cudaMemcpyFromSymbol(&v, g_dbg_errors, 8) != cudaSuccess) return -1;
+    cudaMemcpyToSymbol(g_dbg_errors, &z, 8);
+    return (int64_t)v;
+#else
+    return 0;
+#endif
+}
 extern "C" int fmc_sync(fmc_ctx *c) {
     if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(c->device));

@@ -139,14 +139,30 @@ __device__ __forceinline__ uint2 ldg_slot(uint32_t lo, uint32_t hi) {
     return v;
 }
 
+#ifdef FMC_DEBUG_CHECKS
+// Diagnostics build (compute-sanitizer is not available everywhere): every gather address is checked against
+// the node arena of the launch and every feature offset against the widest row layout; violations are counted
+// (fmc_debug_errors) and the offending load is skipped.
+__device__ unsigned long long g_dbg_lo = 0, g_dbg_hi = 0, g_dbg_errors = 0;
+#endif
+
 template <bool SKL>
 __device__ __forceinline__ void walk_step(uint2 &n, uint32_t fcol, uint32_t win_lo, uint32_t win_hi) {
+#ifdef FMC_DEBUG_CHECKS
+    if ((n.y >> kFeatShift) >= (uint32_t)(kPredRows * kFeatBytes) || ((n.y >> kFeatShift) & 127u)) { atomicAdd(&g_dbg_errors, 1ULL); return; }
+#endif
     const float fv = lds_f32(fcol + (n.y >> kFeatShift));
     uint32_t a = (n.y & kChildMask) | win_lo;
     if (SKL)   // right iff !(fv <= thr)
         asm("{\n\t.reg .pred p;\n\tsetp.gtu.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}" : "+r"(a) : "f"(fv), "f"(__uint_as_float(n.x)));
     else       // right iff !(fv < thr)
         asm("{\n\t.reg .pred p;\n\tsetp.geu.f32 p, %1, %2;\n\t@p add.u32 %0, %0, 8;\n\t}" : "+r"(a) : "f"(fv), "f"(__uint_as_float(n.x)));
+#ifdef FMC_DEBUG_CHECKS
+    {
+        const unsigned long long ad = ((unsigned long long)win_hi << 32) | a;
+        if (ad < g_dbg_lo || ad + 8 > g_dbg_hi || (ad & 7)) { atomicAdd(&g_dbg_errors, 1ULL); return; }
+    }
+#endif
     n = ldg_slot(a, win_hi);
 }
 

@@ -101,6 +101,8 @@ def load_library():
                                         C.c_int32, C.c_int32]
     L.fmc_packed_slots.argtypes = [C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]
     L.fmc_sync.argtypes = [C.c_void_p]
+    L.fmc_debug_errors.restype = C.c_int64
+    L.fmc_debug_errors.argtypes = []
     L.fmc_gather_probe.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(C.c_double)]
     L.fmc_pack_forest_host.restype = C.c_int64
     L.fmc_pack_forest_host.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
@@ -114,7 +116,7 @@ EXPORTED_SYMBOLS = (
     "fmc_last_error", "fmc_abi_version", "fmc_create", "fmc_destroy", "fmc_device_info", "fmc_load_forest",
     "fmc_set_scaler", "fmc_set_active_columns", "fmc_set_params", "fmc_set_matchups", "fmc_simulate",
     "fmc_simulate_host", "fmc_tree_predict", "fmc_tree_predict_host", "fmc_packed_slots", "fmc_sync",
-    "fmc_gather_probe",
+    "fmc_gather_probe", "fmc_debug_errors",
     "fmc_pack_forest_host",
 )
 

@@ -172,6 +172,10 @@ int fmc_packed_slots(fmc_ctx *ctx, int32_t m, int32_t *out);
 
 int fmc_sync(fmc_ctx *ctx);
 
+/* Diagnostics: out-of-range node gathers / feature offsets counted (and skipped) by a library built with
+ * -DFMC_DEBUG_CHECKS since the last call; always 0 for the production build. */
+int64_t fmc_debug_errors(void);
+
 /* Measurement helper for the roofline: achievable rate of dependent 8-byte read-only
  * gathers through a random cyclic table of `table_bytes` (L1-resident when small, L2-resident at a
  * few MiB), 8 chains per lane, one 1024-lane CTA per SM -- a tree walk with nothing around it.
