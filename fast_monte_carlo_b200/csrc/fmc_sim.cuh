@@ -623,6 +623,9 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
             uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.M);
             for (int i = tid; i < (int)(sizeof(MatchupDev) / 4); i += kSimThreads) dst[i] = src[i];
         }
+        // the last round of the previous matchup leaves its counts in one of the two buffers (the loop ends
+        // before it would clear them): start every matchup from empty lists
+        if (tid < kNumKeys) { sh.cnt[0][tid] = 0; sh.cnt[1][tid] = 0; sh.aged[tid] = 0; }
         __syncthreads();
         set_stage(P, ST_NEED_GAME);
         int pos = 0;
