@@ -254,8 +254,11 @@ def run_reference(args):
     if rank != 0:
         return
     ms = load_models(args.stage2)
-    _, dt0, threads = cpu_run(ms, 2000, args.stage2)
-    per_step = int(max(4000, min(400_000, 20.0 / (dt0 / 2000))))       # ~20 s per step
+    if args.cpu_games > 0:
+        per_step = args.cpu_games
+    else:
+        _, dt0, threads = cpu_run(ms, 2000, args.stage2)
+        per_step = int(max(4000, min(400_000, 20.0 / (dt0 / 2000))))       # ~20 s per step
     for w in range(args.warmup):
         cpu_run(ms, max(2000, per_step // 10), args.stage2)
     plays = 0

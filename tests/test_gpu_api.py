@@ -72,3 +72,26 @@ def test_simulate_slate_matches_per_matchup_runs(engine):
     assert np.array_equal(single["hist"][0].astype(np.int64), res[("Kansas State", "Iowa State")]["hist"])
     with pytest.raises(ValueError):
         api.simulate_slate([("Nowhere Tech", "Iowa State")], n=1, engine=engine)
+
+
+def test_bench_json_line_contract(tmp_path):
+    """`python bench.py` (small size) prints ONE JSON line with every key of the driver's contract."""
+    import json, subprocess, sys
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--games", "200000", "--steps", "2", "--warmup", "3",
+                        "--cpu-games", "300", "--e2e-steps", "1"], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["gpu_launches"] == 2 and d["scaling"] == "weak"
+    assert d["value"] > 1e7 and d["e2e"]["value"] > 1e6 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
+    assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
+    assert "workload" in d["config"] and "model" not in d["config"]
