@@ -225,6 +225,7 @@ __device__ __forceinline__ double walk_output(const ForestView &F, uint32_t fcol
     float acc32 = (float)base;
     levels = 0;
     if (F.n_groups == 0) return SKL ? acc64 : (double)acc32;
+    asm volatile("" : "+r"(fcol));      // opaque: keep the column address in a register instead of re-deriving it per loop
     const uint4 *sp = F.stream;
     const uint2 *cp = F.consts;
     // Two groups (2 x kIlp trees) in flight per lane: both are walked together for the depth they share
