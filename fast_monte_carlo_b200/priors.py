@@ -103,14 +103,17 @@ class TeamContext:
         return (self.sp_rating, self.sp_offense, self.sp_defense)
 
 
-def build_team_context_from_sp_flex(team: str, year: int, week: int, sp_df: pd.DataFrame) -> TeamContext:
-    """FMC:1646-1659.  Without usage tables every passer / rusher / target is "Unknown" with share
-    1.0 and nothing is tracked (FMC:246-249) -- the only configuration the shipped reference can reach."""
+def build_team_context_from_sp_flex(team: str, year: int, week: int, sp_df: pd.DataFrame, *,
+                                    focus: Optional[dict] = None, usage_dir: str = ".") -> TeamContext:
+    """FMC:1646-1659.  Usage comes from the focus sheet (`usage.build_focus_usage_tables`), else from
+    `usage_*_share.csv` under `usage_dir`, else every passer / rusher / target is "Unknown" with share
+    1.0 and nothing is tracked (FMC:228-249) -- the only configuration the shipped reference can reach."""
+    from .usage import usage_for_team
     rating, off, de = lookup_sp_flex(team, sp_df)
+    qb, ru, tg, tp, tr, trec = usage_for_team(team, year, focus, usage_dir)
     return TeamContext(name=team, year=year, week=week, sp_rating=rating, sp_offense=off, sp_defense=de,
-                       qb_share=_unknown_share("passer_name"), rush_share=_unknown_share("rusher_name"),
-                       target_share=_unknown_share("receiver_name"),
-                       track_pass=set(), track_rush=set(), track_rec=set())
+                       qb_share=qb, rush_share=ru, target_share=tg,
+                       track_pass=tp, track_rush=tr, track_rec=trec)
 
 
 def csv_base_from(team_a: str, team_b: str, week: int, ext: str = ".csv") -> str:

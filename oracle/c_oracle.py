@@ -40,6 +40,41 @@ class FoConfig(C.Structure):
     ]
 
 
+MAX_USAGE = 8
+PLAYER_FIELDS = 6
+ROLE_INDEX = {"pass": 0, "rush": 1, "rec": 2}
+
+
+class FoUsage(C.Structure):
+    _fields_ = [("n", C.c_int), ("share", C.c_double * MAX_USAGE), ("slot", C.c_int * MAX_USAGE),
+                ("col", (C.c_int * MAX_USAGE) * 7)]
+
+
+class FoTeamUsage(C.Structure):
+    _fields_ = [("role", FoUsage * 3)]
+
+
+def make_usage(team_usages):
+    """Two fast_monte_carlo_b200.usage.TeamUsage-like objects (role[r].share/.slot/.col) -> FoTeamUsage[2]."""
+    arr = (FoTeamUsage * 2)()
+    for t, tu in enumerate(team_usages):
+        for rname, ri in ROLE_INDEX.items():
+            ru = tu.role[rname]
+            u = arr[t].role[ri]
+            u.n = len(ru.names)
+            for e in range(MAX_USAGE):
+                u.slot[e] = -1
+                for m in range(7):
+                    u.col[m][e] = -1
+            for e in range(u.n):
+                u.share[e] = float(ru.share[e])
+                u.slot[e] = int(ru.slot[e])
+                for name, mid in MODEL_IDS.items():
+                    if name in ru.col:
+                        u.col[mid][e] = int(ru.col[name][e])
+    return arr
+
+
 def build(force: bool = False) -> str:
     src = os.path.join(HERE, "fmc_oracle.c")
     if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
@@ -133,8 +168,9 @@ def make_config(ms, spA, spB, *, policy="heuristic", coach_cols=(-1, -1), play_t
 
 
 def simulate(cfg: FoConfig, n: int, *, game0: int = 0, matchup: int = 0, stream: np.ndarray | None = None,
-             seed: int = 0, trace: bool = False, threads: int = 0):
-    """Returns dict(scores[n,2] (team A, team B), iters[n], trace[n,360,8]|None, counters{...})."""
+             seed: int = 0, trace: bool = False, threads: int = 0, usage=None, n_slots: int = 0):
+    """Returns dict(scores[n,2] (team A, team B), iters[n], trace[n,360,8]|None, counters{...});
+    with `usage` (make_usage) also players[n,2,n_slots,6] = yds, att|tgt, comp|rec, td, INT, sacks."""
     L = lib()
     scores = np.zeros((n, 2), dtype=np.int32)
     iters = np.zeros(n, dtype=np.int32)
@@ -143,12 +179,19 @@ def simulate(cfg: FoConfig, n: int, *, game0: int = 0, matchup: int = 0, stream:
     if stream is not None:
         stream = np.ascontiguousarray(stream, dtype=np.float64)
         assert stream.shape == (n, MAX_ITERS, N_SLOTS), stream.shape
-    rc = L.fo_simulate(C.byref(cfg), C.c_long(n), C.c_long(game0), int(matchup), 0 if stream is not None else 1,
-                       _p(stream, C.c_double) if stream is not None else None, C.c_uint64(seed),
-                       _p(scores, C.c_int), _p(iters, C.c_int), _p(tr, C.c_double) if trace else None,
-                       _p(counters, C.c_long), int(threads))
+    tail = (C.c_long(n), C.c_long(game0), int(matchup), 0 if stream is not None else 1,
+            _p(stream, C.c_double) if stream is not None else None, C.c_uint64(seed),
+            _p(scores, C.c_int), _p(iters, C.c_int), _p(tr, C.c_double) if trace else None,
+            _p(counters, C.c_long), int(threads))
+    players = None
+    if usage is None:
+        rc = L.fo_simulate(C.byref(cfg), *tail)
+    else:
+        players = np.zeros((n, 2, max(n_slots, 1), PLAYER_FIELDS), dtype=np.float64)
+        rc = L.fo_simulate_players(C.byref(cfg), usage, int(max(n_slots, 1)), _p(players, C.c_double), *tail)
+        players = players[:, :, :n_slots, :]
     assert rc == 0, rc
-    return dict(scores=scores, iters=iters, trace=tr,
+    return dict(scores=scores, iters=iters, trace=tr, players=players,
                 counters={k: int(counters[i]) for i, k in enumerate(COUNTER_NAMES)})
 
 

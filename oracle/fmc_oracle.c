@@ -20,6 +20,8 @@
  *   one play          simulate_play                   FMC:1026-1257
  *   fourth down       go_for_it_prob, handle_fourth   FMC:1336-1421
  *   one game          simulate_game                   FMC:1428-1464
+ *   players           sample_qb/rusher/target FMC:625-635, focus tracking + per-player box FMC:1058-1075,
+ *                     1105-1148, 1163-1192, 1203-1249 (fo_simulate_players; usage tables are inputs)
  *
  * Pinning: tests/test_oracle_golden.py replays tests/golden/ref_trajectories.npz, which was
  * produced by the UNMODIFIED reference module run in the build container
@@ -87,6 +89,19 @@ typedef struct {
     int stage2_mode;             /* 0 = stand-in probabilities, 1 = booster FO_PASS_STAGE2 */
     double standin[3];           /* raw [incomplete, intercepted, sack] as float32-exact doubles */
 } FoConfig;
+
+/* Usage tables of one team (TeamContext.qb_share / rush_share / target_share, FMC:262-264) reduced to what
+ * the engine reads: the shares Generator.choice gets (FMC:627, 631, 635), whether a name is in the team's
+ * focus track set (FMC:1062-1063, 1204) and which one-hot column the name lights in every model. */
+#define FO_MAX_USAGE 8
+#define FO_PLAYER_FIELDS 6   /* yds, att|tgt, comp|rec, td, INT, sacks */
+typedef struct {
+    int n;
+    double share[FO_MAX_USAGE];
+    int slot[FO_MAX_USAGE];               /* output slot of a tracked name, -1 = not tracked */
+    int col[FO_N_MODELS][FO_MAX_USAGE];   /* hot column of the name in model m (-1 = not a category) */
+} FoUsage;
+typedef struct { FoUsage role[3]; } FoTeamUsage;   /* 0 passer, 1 rusher, 2 target */
 
 static void *dup_mem(const void *p, size_t n) {
     void *q = malloc(n ? n : 1);
@@ -305,6 +320,12 @@ typedef struct {
     double bias[2], ymul[2], mz[2], tanh35[2];
     long plays, iters;
     long n_pass, n_comp, n_inc, n_int, n_sack, n_run, n_td, n_fga, n_fg, n_punt, n_go;
+    /* players mode (fo_simulate_players) */
+    const FoTeamUsage *usage;     /* [2] or NULL */
+    double cdf[2][3][FO_MAX_USAGE];
+    int n_slots;
+    double *box;                  /* this game's [2][n_slots][FO_PLAYER_FIELDS] or NULL */
+    int cur[3];                   /* usage entries sampled for the current play: passer, rusher, target */
 } FoGame;
 
 /* FMC:97 */
@@ -432,6 +453,32 @@ static void fill_row(FoRow *r, const FoGame *G, const FoState *s, int sd, int mo
     r->num[16] = ((s->sec % 1800) <= 120) ? 1.0 : 0.0;
     r->active[0] = c->active[model][0];
     r->active[1] = c->active[model][1];
+    if (G->usage) {      /* passer_name / target_name / rusher_name of the row (FMC:1079-1081, 1216) */
+        const FoTeamUsage *u = &G->usage[off];
+        if (model == FO_RUN_YARDS) {
+            r->active[0] = u->role[1].col[model][G->cur[1]];
+            r->active[1] = -1;
+        } else {
+            r->active[0] = u->role[0].col[model][G->cur[0]];
+            r->active[1] = u->role[2].col[model][G->cur[2]];
+        }
+    }
+}
+
+/* Generator.choice(n, p=shares): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, 'right') */
+static int sample_usage(const FoGame *G, int team, int role, double u) {
+    const int n = G->usage[team].role[role].n;
+    int idx = 0;
+    for (int i = 0; i < n; ++i) idx += (G->cdf[team][role][i] <= u);
+    return idx < n ? idx : n - 1;
+}
+
+/* pstats[team][role][name][field] += v for a tracked name (FMC:1073-1075, 1108-1148, 1163-1192, 1207-1249) */
+static void credit(FoGame *G, int team, int role, int field, double v) {
+    if (!G->box) return;
+    const int slot = G->usage[team].role[role].slot[G->cur[role]];
+    if (slot < 0) return;
+    G->box[((size_t)team * G->n_slots + slot) * FO_PLAYER_FIELDS + field] += v;
 }
 
 /* three quantiles of one family (FMC:780-812) */
@@ -536,8 +583,15 @@ static void simulate_play(FoGame *G, FoState *s, FoRng *rng) {
 
     if (is_pass) {
         G->n_pass++;
-        (void)draw(rng, S_U_P1, 0);            /* sample_qb: single "Unknown" passer (FMC:246-249) */
-        (void)draw(rng, S_U_WR, 0);            /* sample_target */
+        {
+            const double u_qb = draw(rng, S_U_P1, 0);      /* sample_qb  FMC:625-627 */
+            const double u_wr = draw(rng, S_U_WR, 0);      /* sample_target FMC:633-635 */
+            if (G->usage) {
+                G->cur[0] = sample_usage(G, team, 0, u_qb);
+                G->cur[2] = sample_usage(G, team, 2, u_wr);
+                credit(G, team, 2, 1, 1.0);                /* tgt += 1 (FMC:1074-1075) */
+            }
+        }
         FoRow r;
         fill_row(&r, G, s, sd, FO_PASS_STAGE1);
         double m1[1];
@@ -557,13 +611,22 @@ static void simulate_play(FoGame *G, FoState *s, FoRng *rng) {
             if (ytg0 <= 12 && s->down <= 3 &&
                 draw(rng, S_U_FIN, 0) < rz_finish_prob_pass(ytg0, G->tanh35[team], s->down))
                 yards = ytg0;
+            if (G->usage) credit(G, team, 0, 1, 1.0);       /* att (FMC:1108-1109) */
             if (yards + 1e-9 >= s->ytg) {
                 G->n_td++;
+                if (G->usage) {                              /* FMC:1120-1127 */
+                    credit(G, team, 0, 2, 1.0); credit(G, team, 0, 0, s->ytg); credit(G, team, 0, 3, 1.0);
+                    credit(G, team, 2, 2, 1.0); credit(G, team, 2, 0, s->ytg); credit(G, team, 2, 3, 1.0);
+                }
                 s->score[team] += 7;
                 s->going = 0;
                 tick_clock(s, 20);
                 change_possession(s, 1, 75.0);
             } else {
+                if (G->usage) {                              /* FMC:1140-1145 */
+                    credit(G, team, 0, 2, 1.0); credit(G, team, 0, 0, yards);
+                    credit(G, team, 2, 2, 1.0); credit(G, team, 2, 0, yards);
+                }
                 s->going = 0;
                 advance_down(s, yards);
                 tick_clock(s, 26);
@@ -597,11 +660,13 @@ static void simulate_play(FoGame *G, FoState *s, FoRng *rng) {
         if (outcome > 2) outcome = 2;
         if (outcome == 0) {                          /* incomplete FMC:1160-1168 */
             G->n_inc++;
+            if (G->usage) credit(G, team, 0, 1, 1.0);       /* att (FMC:1163-1164) */
             s->down += 1;
             s->going = 0;
             tick_clock(s, 10);
         } else if (outcome == 2) {                   /* sack FMC:1170-1184 */
             G->n_sack++;
+            if (G->usage) credit(G, team, 0, 5, 1.0);       /* sacks (FMC:1173-1174) */
             double q[3];
             quants(G, s, sd, FO_SACK_YARDS, q);
             double loss = -sample_yards(G, rng, q, 0.25, -20.0, 0.0);
@@ -614,6 +679,7 @@ static void simulate_play(FoGame *G, FoState *s, FoRng *rng) {
             tick_clock(s, 24);
         } else {                                     /* intercepted FMC:1186-1199 */
             G->n_int++;
+            if (G->usage) { credit(G, team, 0, 1, 1.0); credit(G, team, 0, 4, 1.0); }   /* att, INT (FMC:1190-1192) */
             double ret = softclip(6 + 5 * draw(rng, S_Z_INT, 1), 0, s->ytg);
             double spot = 100.0 - (s->ytg - ret);
             s->going = 0;
@@ -624,7 +690,13 @@ static void simulate_play(FoGame *G, FoState *s, FoRng *rng) {
     }
     /* run FMC:1201-1257 */
     G->n_run++;
-    (void)draw(rng, S_U_P1, 0);                      /* sample_rusher */
+    {
+        const double u_rb = draw(rng, S_U_P1, 0);    /* sample_rusher FMC:629-631 */
+        if (G->usage) {
+            G->cur[1] = sample_usage(G, team, 1, u_rb);
+            credit(G, team, 1, 1, 1.0);              /* att (FMC:1206-1208) */
+        }
+    }
     double q[3];
     quants(G, s, sd, FO_RUN_YARDS, q);
     double yards = sample_yards(G, rng, q, 0.35, -4.0, s->ytg) * G->ymul[team];
@@ -638,11 +710,13 @@ static void simulate_play(FoGame *G, FoState *s, FoRng *rng) {
     }
     if (yards + 1e-9 >= ytg0) {
         G->n_td++;
+        if (G->usage) { credit(G, team, 1, 0, s->ytg); credit(G, team, 1, 3, 1.0); }   /* FMC:1232-1234 */
         s->score[team] += 7;
         tick_clock(s, 28);
         change_possession(s, 1, 75.0);
         s->going = 0;
     } else {
+        if (G->usage) credit(G, team, 1, 0, yards);   /* FMC:1246-1247 */
         advance_down(s, yards);
         tick_clock(s, 28);
         s->going = 0;
@@ -691,8 +765,9 @@ static void simulate_game(FoGame *G, FoRng *rng, int first, int score_out[2], in
  *   scores[n][2] = points of team 0 / team 1;  iters[n];  trace[n][360][8] or NULL.
  *   counters[16]: plays, iters, pass, comp, inc, int, sack, run, td, fga, fg, punt, go (summed).
  */
-int fo_simulate(const FoConfig *cfg, long n, long game0, int matchup, int rng_mode, const double *stream,
-                uint64_t seed, int *scores, int *iters, double *trace, long *counters, int n_threads) {
+static int simulate_range(const FoConfig *cfg, const FoTeamUsage *usage, int n_slots, double *players,
+                          long n, long game0, int matchup, int rng_mode, const double *stream,
+                          uint64_t seed, int *scores, int *iters, double *trace, long *counters, int n_threads) {
     for (int m = FO_PASS_STAGE1; m <= FO_SACK_YARDS; ++m) {
         if (m == FO_PASS_STAGE2 && cfg->stage2_mode == 0) continue;
         if (!g_forest[m].loaded) return -2;
@@ -707,6 +782,17 @@ int fo_simulate(const FoConfig *cfg, long n, long game0, int matchup, int rng_mo
     {
         FoGame G;
         game_constants(&G, cfg);
+        if (usage) {
+            G.usage = usage;
+            G.n_slots = n_slots;
+            for (int t = 0; t < 2; ++t)
+                for (int r = 0; r < 3; ++r) {
+                    const FoUsage *u = &usage[t].role[r];
+                    double acc = 0.0;
+                    for (int i = 0; i < u->n; ++i) { acc += u->share[i]; G.cdf[t][r][i] = acc; }   /* np.cumsum */
+                    for (int i = 0; i < u->n; ++i) G.cdf[t][r][i] /= acc;                           /* cdf /= cdf[-1] */
+                }
+        }
 #pragma omp for schedule(dynamic, 16)
         for (long i = 0; i < n; ++i) {
             long g = game0 + i;
@@ -718,6 +804,8 @@ int fo_simulate(const FoConfig *cfg, long n, long game0, int matchup, int rng_mo
             rng.ctr_game[0] = (uint32_t)((uint64_t)g); rng.ctr_game[1] = (uint32_t)((uint64_t)g >> 32);
             rng.ctr_game[2] = (uint32_t)matchup;
             int it = 0;
+            G.box = (usage && players) ? players + (size_t)i * 2 * n_slots * FO_PLAYER_FIELDS : NULL;
+            G.cur[0] = G.cur[1] = G.cur[2] = 0;
             simulate_game(&G, &rng, (int)(g & 1), scores + 2 * i, &it,
                           trace ? trace + (size_t)i * FO_MAX_ITERS * FO_TRACE_COLS : NULL);
             if (iters) iters[i] = it;
@@ -731,6 +819,32 @@ int fo_simulate(const FoConfig *cfg, long n, long game0, int matchup, int rng_mo
     }
     if (counters) memcpy(counters, tot, sizeof(tot));
     return 0;
+}
+
+int fo_simulate(const FoConfig *cfg, long n, long game0, int matchup, int rng_mode, const double *stream,
+                uint64_t seed, int *scores, int *iters, double *trace, long *counters, int n_threads) {
+    return simulate_range(cfg, NULL, 0, NULL, n, game0, matchup, rng_mode, stream, seed, scores, iters, trace,
+                          counters, n_threads);
+}
+
+/*
+ * Same with usage tables (FMC:625-635) and the per-player box of the focus names (FMC:1259-1299):
+ *   usage[2]   team A / team B;  players[n][2][n_slots][FO_PLAYER_FIELDS] (zeroed by the caller), fields
+ *   yds, att|tgt, comp|rec, td, INT, sacks of the name tracked in that slot.
+ */
+int fo_simulate_players(const FoConfig *cfg, const FoTeamUsage *usage, int n_slots, double *players,
+                        long n, long game0, int matchup, int rng_mode, const double *stream,
+                        uint64_t seed, int *scores, int *iters, double *trace, long *counters, int n_threads) {
+    if (!usage || n_slots < 0) return -3;
+    for (int t = 0; t < 2; ++t)
+        for (int r = 0; r < 3; ++r) {
+            const FoUsage *u = &usage[t].role[r];
+            if (u->n < 1 || u->n > FO_MAX_USAGE) return -3;
+            for (int i = 0; i < u->n; ++i)
+                if (u->slot[i] >= n_slots) return -3;
+        }
+    return simulate_range(cfg, usage, n_slots, players, n, game0, matchup, rng_mode, stream, seed, scores, iters,
+                          trace, counters, n_threads);
 }
 
 int fo_max_threads(void) {

@@ -1,0 +1,109 @@
+"""Per-player path on the CPU: the host usage tables and the C oracle against fixtures produced by the
+UNMODIFIED reference (tests/golden/make_golden_players.py: synthetic focus sheet -> the reference's
+`_build_focus_usage_tables`, `simulate_game` under injected draws, `flatten_player_box_rows`)."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN
+
+from fast_monte_carlo_b200 import priors, usage
+
+
+@pytest.fixture(scope="module")
+def gold():
+    t = np.load(os.path.join(GOLDEN, "ref_players.npz"))
+    return dict(t=t, meta=json.loads(str(t["meta"])), teams=json.loads(str(t["teams"])),
+                cols=json.loads(str(t["player_cols"])), rows=json.loads(str(t["player_rows"])))
+
+
+@pytest.fixture(scope="module")
+def contexts(gold):
+    focus = usage.build_focus_usage_tables(os.path.join(GOLDEN, "players_focus.csv"))
+    sp = priors.load_sp_flex(priors.packaged_priors_path())
+    return {name: priors.build_team_context_from_sp_flex(name, 2025, 1, sp, focus=focus, usage_dir=GOLDEN)
+            for name in gold["teams"]}
+
+
+def test_usage_tables_match_reference(gold, contexts):
+    """Share tables (names, order, float64 bits) and track sets of the reference's own loader."""
+    for name, ref in gold["teams"].items():
+        tc = contexts[name]
+        for key, df, col in (("qb", tc.qb_share, "passer_name"), ("ru", tc.rush_share, "rusher_name"),
+                             ("tg", tc.target_share, "receiver_name")):
+            assert [str(x) for x in df[col]] == ref[key][0], (name, key)
+            assert np.array_equal(np.asarray(df["share"].values, dtype=np.float64), np.asarray(ref[key][1])), (name, key)
+        assert sorted(tc.track_pass) == ref["track_pass"]
+        assert sorted(tc.track_rush) == ref["track_rush"]
+        assert sorted(tc.track_rec) == ref["track_rec"]
+        assert [tc.sp_rating, tc.sp_offense, tc.sp_defense] == ref["sp"]
+
+
+def test_resolve_team_columns(models, contexts):
+    ksu = usage.resolve_team(contexts["Kansas State"], models)
+    assert ksu.role["pass"].names == ["Taylen Green", "Zach Gibson", "__Other__"]
+    assert [s for s in ksu.role["pass"].slot] == [0, 1, -1]                 # `__Other__` is never tracked
+    g = models["pass_stage1"].group("passer_name")
+    assert ksu.role["pass"].col["pass_stage1"] == [g.column_of("Taylen Green"), g.column_of("Zach Gibson"), -1]
+    # the receiver remainder is fed to the models as "Unknown" (FMC:1066); an unseen name lights nothing
+    tg = models["pass_yards"].group("target_name")
+    assert ksu.role["rec"].names[-1] == "__Other__"
+    assert ksu.role["rec"].col["pass_yards"][-1] == tg.column_of("Unknown") >= 0
+    assert ksu.role["rec"].col["pass_yards"][ksu.role["rec"].names.index("Nobody Known")] == -1
+    assert usage.resolve_team(contexts["UTSA"], models).trivial
+    assert [usage.ROLE_LABEL[r] for r, _ in ksu.slots] == ["QB", "QB", "Rusher", "Rusher", "Rusher", "Receiver", "Receiver", "Receiver"]
+
+
+def test_py_round1():
+    x = np.array([1.15, 2.25, 0.05, 7.349999, 12.45, -0.15, 3.0, 1e-9, 104.65])
+    assert usage.py_round1(x).tolist() == [round(float(v), 1) for v in x]
+    rng = np.random.default_rng(0)
+    y = np.round(rng.random(20000) * 60, 2)
+    assert usage.py_round1(y).tolist() == [round(float(v), 1) for v in y]
+
+
+def _frame(rows, cols):
+    df = pd.DataFrame(rows, columns=cols)
+    return df.sort_values(["sim", "team", "role", "player"], kind="stable").reset_index(drop=True)
+
+
+def test_oracle_players_match_reference(models, oracle, gold, contexts):
+    """Trajectories bit for bit, and the reference's players table row for row."""
+    t, meta = gold["t"], gold["meta"]
+    stream = oracle.make_stream(len(meta), int(t["stream_seed"]))
+    frames = []
+    for g, m in enumerate(meta):
+        ta, tb = contexts[m["team_a"]], contexts[m["team_b"]]
+        us = [usage.resolve_team(ta, models), usage.resolve_team(tb, models)]
+        n_slots = max(len(u.slots) for u in us)
+        cfg = oracle.make_config(models, ta.sp, tb.sp)
+        r = oracle.simulate(cfg, 1, game0=g, stream=stream[g:g + 1], trace=True, threads=1,
+                            usage=oracle.make_usage(us), n_slots=n_slots)
+        n = int(t["iters"][g])
+        assert r["iters"][0] == n, g
+        assert np.array_equal(r["trace"][0, :n], t["traces"][g, :n]), g
+        first = g & 1
+        assert (r["scores"][0, first], r["scores"][0, first ^ 1]) == tuple(t["scores"][g])
+        frames.append(usage.player_rows(r["players"], g, (m["team_a"], m["team_b"]), us))
+    got = pd.concat(frames, ignore_index=True)
+    want = _frame(gold["rows"], gold["cols"])
+    got = _frame(got.values.tolist(), gold["cols"])
+    assert len(got) == len(want) > 50
+    for c in gold["cols"]:
+        assert got[c].tolist() == want[c].tolist(), c
+
+
+def test_oracle_trivial_usage_equals_plain_run(models, oracle):
+    """One "Unknown" per role and nothing tracked is the shipped configuration: same games as without usage."""
+    sp = priors.load_sp_flex(priors.packaged_priors_path())
+    ta = priors.build_team_context_from_sp_flex("Kansas State", 2025, 1, sp, usage_dir=GOLDEN)
+    tb = priors.build_team_context_from_sp_flex("Iowa State", 2025, 1, sp, usage_dir=GOLDEN)
+    us = [usage.resolve_team(ta, models), usage.resolve_team(tb, models)]
+    assert us[0].trivial and us[1].trivial
+    cfg = oracle.make_config(models, ta.sp, tb.sp)
+    a = oracle.simulate(cfg, 64, seed=5)
+    b = oracle.simulate(cfg, 64, seed=5, usage=oracle.make_usage(us), n_slots=0)
+    assert np.array_equal(a["scores"], b["scores"]) and np.array_equal(a["iters"], b["iters"])
