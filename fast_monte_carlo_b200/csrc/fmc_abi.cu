@@ -183,6 +183,8 @@ struct fmc_ctx {
     HostForest forest[FMC_N_MODELS];
     fmc_params params;
     std::vector<fmc_matchup> matchups;
+    std::vector<fmc_team_usage> usage;   // [n_matchups][2] or empty (shipped configuration: every name "Unknown")
+    int n_slots = 0;
     bool tables_dirty = true;
     // device-side state of the last set_matchups
     TableArena sim_tables;
@@ -232,8 +234,10 @@ extern "C" int fmc_create(int device, fmc_ctx **out) {
     c->params.stage2_standin[0] = (double)0.78f;
     c->params.stage2_standin[1] = (double)0.05f;
     c->params.stage2_standin[2] = (double)0.17f;
-    CK(cudaFuncSetAttribute(sim_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes()));
-    CK(cudaFuncSetAttribute(sim_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes()));
+    CK(cudaFuncSetAttribute(sim_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(false)));
+    CK(cudaFuncSetAttribute(sim_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(false)));
+    CK(cudaFuncSetAttribute(sim_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(true)));
+    CK(cudaFuncSetAttribute(sim_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(true)));
     *out = c;
     return FMC_OK;
 }
@@ -302,8 +306,46 @@ extern "C" int fmc_set_matchups(fmc_ctx *c, int32_t n, const fmc_matchup *m) {
     for (int i = 0; i < n; ++i)
         if (m[i].game_end < m[i].game_begin) return fail(FMC_ERR_INVALID, "fmc_set_matchups: game_end < game_begin");
     c->matchups.assign(m, m + n);
+    c->usage.clear();          // usage belongs to a matchup list: set it again after fmc_set_matchups
+    c->n_slots = 0;
     c->tables_dirty = true;
     return FMC_OK;
+}
+
+extern "C" int fmc_set_usage(fmc_ctx *c, int32_t n, const fmc_team_usage *teams, int32_t n_slots) {
+    if (!c) return fail(FMC_ERR_INVALID, "fmc_set_usage: ctx is NULL");
+    if (!teams) { c->usage.clear(); c->n_slots = 0; c->tables_dirty = true; return FMC_OK; }
+    if (n != (int)c->matchups.size()) return fail(FMC_ERR_INVALID, "fmc_set_usage: n_matchups differs from the last fmc_set_matchups");
+    if (n_slots < 0 || n_slots > 3 * FMC_MAX_USAGE) return fail(FMC_ERR_INVALID, "fmc_set_usage: bad n_slots");
+    for (int i = 0; i < 2 * n; ++i)
+        for (int r = 0; r < 3; ++r) {
+            const fmc_usage &u = teams[i].role[r];
+            const int cap = r == 0 ? FMC_MAX_PASSERS : FMC_MAX_USAGE;
+            if (u.n < 1 || u.n > cap) return fail(FMC_ERR_CAPACITY, "fmc_set_usage: a usage table must have 1.." + std::to_string(cap) + " entries");
+            double tot = 0.0;
+            for (int e = 0; e < u.n; ++e) {
+                if (!(u.share[e] >= 0.0) || !std::isfinite(u.share[e])) return fail(FMC_ERR_INVALID, "fmc_set_usage: shares must be finite and >= 0");
+                if (u.slot[e] >= n_slots) return fail(FMC_ERR_INVALID, "fmc_set_usage: slot out of range");
+                tot += u.share[e];
+            }
+            if (!(tot > 0.0)) return fail(FMC_ERR_INVALID, "fmc_set_usage: shares sum to zero");
+        }
+    c->usage.assign(teams, teams + 2 * (size_t)n);
+    c->n_slots = n_slots;
+    c->tables_dirty = true;
+    return FMC_OK;
+}
+
+// Dynamic one-hot columns of (family, team on offense): the sampled names of a play are feature rows
+// (fmc_sim.cuh kDynRow0...), every other name column folds to 0.
+static void dyn_columns(const fmc_team_usage &tu, int fam, PackSpec &s) {
+    s.n_dyn = 0;
+    auto add = [&](const fmc_usage &u, int row0) {
+        for (int e = 0; e < u.n; ++e)
+            if (u.col[fam][e] >= 0) { s.dyn_col[s.n_dyn] = u.col[fam][e]; s.dyn_row[s.n_dyn] = (int8_t)(row0 + e); s.n_dyn++; }
+    };
+    if (fam == FMC_RUN_YARDS) add(tu.role[1], kDynRow0);
+    else if (fam != FMC_PLAY_MODEL) { add(tu.role[0], kDynRow0); add(tu.role[2], kDynRow0 + FMC_MAX_PASSERS); }
 }
 
 static bool family_needed(const fmc_ctx *c, int fam) {
@@ -340,6 +382,10 @@ static int build_tables(fmc_ctx *c) {
         PackSpec s;
         preset_sim(s);
         s.active[0] = f.active[0]; s.active[1] = f.active[1];
+        if (!c->usage.empty()) {      // player mode: every name comes from the usage tables
+            s.active[0] = -1; s.active[1] = -1;
+            dyn_columns(c->usage[(size_t)j.matchup * 2 + off], fam, s);
+        }
         if (fam == FMC_PLAY_MODEL) { s.active[0] = mu.coach_col[off]; s.active[1] = -1; }
         s.fold_value[6] = 3.0; s.fold_value[7] = 3.0;    // timeouts are never spent (FMC:911-912)
         s.fold_value[8] = mu.sp[off][0]; s.fold_value[9] = mu.sp[off][1];
@@ -375,6 +421,18 @@ static int build_tables(fmc_ctx *c) {
             M.ymul[off] = 1.0 + 0.10 * std::tanh((O - D) / 30.0);  // yardage_multiplier FMC:435-437
             M.mz[off] = (O - D) / 40.0;                          // mismatch_z FMC:440-442
             M.tanh35[off] = std::tanh((O - D) / 35.0);           // FMC:448, 456
+            if (!c->usage.empty()) {
+                const fmc_team_usage &tu = c->usage[(size_t)i * 2 + off];
+                for (int r = 0; r < 3; ++r) {
+                    const fmc_usage &u = tu.role[r];
+                    UsageDev &U = M.usage[off];
+                    U.n[r] = (int8_t)u.n;
+                    double acc = 0.0;
+                    for (int e = 0; e < u.n; ++e) { acc += u.share[e]; U.cdf[r][e] = acc; }   // np.cumsum
+                    for (int e = 0; e < u.n; ++e) U.cdf[r][e] /= acc;                          // cdf /= cdf[-1]
+                    for (int e = 0; e < FMC_MAX_USAGE; ++e) U.slot[r][e] = (int8_t)(e < u.n ? u.slot[e] : -1);
+                }
+            }
         }
     }
     for (Job &j : jobs) {
@@ -465,19 +523,29 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
     }
     a.scores = g->scores_dev; a.hist = g->hist_dev; a.counters = (unsigned long long *)g->counters_dev;
     a.stream = g->stream_dev; a.trace = g->trace_dev; a.iters = g->iters_dev;
+    const bool players = !c->usage.empty();
+    if (g->players_dev && !players) return fail(FMC_ERR_INVALID, "fmc_simulate: players_dev needs fmc_set_usage");
+    a.players = g->players_dev; a.n_slots = c->n_slots;
+    if (a.players && c->n_slots == 0) a.players = nullptr;
     const int grid = c->prop.multiProcessorCount * kSimCtasPerSm;
 #ifdef FMC_DEBUG_CHECKS
     debug_set_range(c->sim_tables);
 #endif
-    if (a.stream || a.trace) sim_kernel<true><<<grid, kSimThreads, sim_smem_bytes(), st>>>(a);   // parity-test instantiation
-    else sim_kernel<false><<<grid, kSimThreads, sim_smem_bytes(), st>>>(a);
+    const bool test = a.stream || a.trace;      // parity-test instantiation
+    if (players) {
+        if (test) sim_kernel<true, true><<<grid, kSimThreads, sim_smem_bytes(true), st>>>(a);
+        else sim_kernel<false, true><<<grid, kSimThreads, sim_smem_bytes(true), st>>>(a);
+    } else {
+        if (test) sim_kernel<true, false><<<grid, kSimThreads, sim_smem_bytes(false), st>>>(a);
+        else sim_kernel<false, false><<<grid, kSimThreads, sim_smem_bytes(false), st>>>(a);
+    }
     CK(cudaGetLastError());
     return FMC_OK;
 }
 
-extern "C" int fmc_simulate_host(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
-                                 uint64_t *counters_host, const double *stream_host, double *trace_host,
-                                 uint16_t *iters_host) {
+static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
+                              uint64_t *counters_host, const double *stream_host, double *trace_host,
+                              uint16_t *iters_host, fmc_player_rec *players_host) {
     if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
     if (c->matchups.empty()) return fail(FMC_ERR_INVALID, "fmc_set_matchups has not been called");
     CK(cudaSetDevice(c->device));
@@ -492,6 +560,9 @@ extern "C" int fmc_simulate_host(fmc_ctx *c, uint64_t seed, uint32_t *scores_hos
     uint64_t *d_cnt = nullptr;
     double *d_stream = nullptr, *d_trace = nullptr;
     uint16_t *d_iters = nullptr;
+    fmc_player_rec *d_players = nullptr;
+    const size_t players_n = games * 2 * (size_t)c->n_slots;
+    if (players_host && c->usage.empty()) return fail(FMC_ERR_INVALID, "players output needs fmc_set_usage");
     int rc = FMC_OK;
     cudaError_t e = cudaSuccess;
     auto bail = [&](cudaError_t err, const char *what) { rc = fail(FMC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err)); };
@@ -514,10 +585,15 @@ extern "C" int fmc_simulate_host(fmc_ctx *c, uint64_t seed, uint32_t *scores_hos
             if ((e = cudaMemsetAsync(d_trace, 0xFF, b)) != cudaSuccess) { bail(e, "memset trace"); break; }   // NaN fill
         }
         if (iters_host && games) { if ((e = cudaMalloc(&d_iters, games * 2)) != cudaSuccess) { bail(e, "cudaMalloc iters"); break; } }
+        if (players_host && players_n) {
+            if ((e = cudaMalloc(&d_players, players_n * sizeof(fmc_player_rec))) != cudaSuccess) { bail(e, "cudaMalloc players"); break; }
+            if ((e = cudaMemsetAsync(d_players, 0, players_n * sizeof(fmc_player_rec))) != cudaSuccess) { bail(e, "memset players"); break; }
+        }
         fmc_sim_args g;
         std::memset(&g, 0, sizeof(g));
         g.seed = seed; g.n_matchups = (int)nm; g.scores_dev = d_scores; g.hist_dev = d_hist; g.counters_dev = d_cnt;
         g.stream_dev = d_stream; g.trace_dev = d_trace; g.iters_dev = d_iters; g.stream = nullptr;
+        g.players_dev = d_players;
         rc = fmc_simulate(c, &g);
         if (rc) break;
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) { bail(e, "sim_kernel"); break; }
@@ -526,9 +602,23 @@ extern "C" int fmc_simulate_host(fmc_ctx *c, uint64_t seed, uint32_t *scores_hos
         if (counters_host && (e = cudaMemcpy(counters_host, d_cnt, FMC_N_COUNTERS * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H counters"); break; }
         if (trace_host && games && (e = cudaMemcpy(trace_host, d_trace, games * FMC_MAX_ITERS * FMC_TRACE_COLS * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H trace"); break; }
         if (iters_host && games && (e = cudaMemcpy(iters_host, d_iters, games * 2, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H iters"); break; }
+        if (d_players && (e = cudaMemcpy(players_host, d_players, players_n * sizeof(fmc_player_rec), cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H players"); break; }
     } while (0);
     cudaFree(d_scores); cudaFree(d_hist); cudaFree(d_cnt); cudaFree(d_stream); cudaFree(d_trace); cudaFree(d_iters);
+    cudaFree(d_players);
     return rc;
+}
+
+extern "C" int fmc_simulate_host(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
+                                 uint64_t *counters_host, const double *stream_host, double *trace_host,
+                                 uint16_t *iters_host) {
+    return simulate_host_impl(c, seed, scores_host, hist_host, counters_host, stream_host, trace_host, iters_host, nullptr);
+}
+
+extern "C" int fmc_simulate_players_host(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
+                                         uint64_t *counters_host, const double *stream_host, double *trace_host,
+                                         uint16_t *iters_host, fmc_player_rec *players_host) {
+    return simulate_host_impl(c, seed, scores_host, hist_host, counters_host, stream_host, trace_host, iters_host, players_host);
 }
 
 extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, int64_t n, double *out_dev,
@@ -709,11 +799,12 @@ extern "C" int fmc_gather_probe(fmc_ctx *c, int64_t table_bytes, int32_t iters, 
 // performs no evaluation -- tests walk the returned tables themselves.
 //   mode 0 = simulation preset (timeouts + SP+ folded to `fold_value`), 1 = predict preset.
 // Returns the number of node slots, or a negative status; fills up to the given capacities.
-extern "C" int64_t fmc_pack_forest_host(const fmc_forest_desc *d, int32_t mode, int32_t col0, int32_t col1,
-                                        const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
-                                        const double *scaler_mean, const double *scaler_scale, int32_t tree_begin,
-                                        int32_t tree_end, uint64_t *slots_out, int64_t slots_cap, uint64_t *stream_out,
-                                        int64_t stream_cap, uint64_t *consts_out, int64_t consts_cap, int32_t *info_out) {
+static int64_t pack_host_impl(const fmc_forest_desc *d, int32_t mode, int32_t col0, int32_t col1,
+                              const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
+                              const double *scaler_mean, const double *scaler_scale, int32_t tree_begin,
+                              int32_t tree_end, int32_t n_dyn, const int32_t *dyn_cols, const int32_t *dyn_rows,
+                              uint64_t *slots_out, int64_t slots_cap, uint64_t *stream_out,
+                              int64_t stream_cap, uint64_t *consts_out, int64_t consts_cap, int32_t *info_out) {
     if (!d) return fail(FMC_ERR_INVALID, "fmc_pack_forest_host: desc is NULL");
     HostForest f;
     f.assign(*d);
@@ -721,6 +812,9 @@ extern "C" int64_t fmc_pack_forest_host(const fmc_forest_desc *d, int32_t mode, 
     PackSpec s;
     if (mode == 0) preset_sim(s); else preset_predict(s);
     s.active[0] = col0; s.active[1] = col1;
+    if (n_dyn < 0 || n_dyn > (int)(sizeof(s.dyn_col) / sizeof(s.dyn_col[0]))) return fail(FMC_ERR_INVALID, "fmc_pack_forest_host_dyn: bad n_dyn");
+    s.n_dyn = n_dyn;
+    for (int i = 0; i < n_dyn; ++i) { s.dyn_col[i] = dyn_cols[i]; s.dyn_row[i] = (int8_t)dyn_rows[i]; }
     if (fold_value17) for (int k = 0; k < kNumMax; ++k) s.fold_value[k] = fold_value17[k];
     s.n_scaled = n_scaled;
     for (int j = 0; j < n_scaled && j < 16; ++j) { s.scaler_cols[j] = scaler_cols[j]; s.scaler_mean[j] = scaler_mean[j]; s.scaler_scale[j] = scaler_scale[j]; }
@@ -741,4 +835,23 @@ extern "C" int64_t fmc_pack_forest_host(const fmc_forest_desc *d, int32_t mode, 
     if (stream_out && (int64_t)pf.stream.size() <= stream_cap) std::memcpy(stream_out, pf.stream.data(), pf.stream.size() * 8);
     if (consts_out && (int64_t)pf.consts.size() <= consts_cap) std::memcpy(consts_out, pf.consts.data(), pf.consts.size() * 8);
     return (int64_t)pf.slots.size();
+}
+
+extern "C" int64_t fmc_pack_forest_host(const fmc_forest_desc *d, int32_t mode, int32_t col0, int32_t col1,
+                                        const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
+                                        const double *scaler_mean, const double *scaler_scale, int32_t tree_begin,
+                                        int32_t tree_end, uint64_t *slots_out, int64_t slots_cap, uint64_t *stream_out,
+                                        int64_t stream_cap, uint64_t *consts_out, int64_t consts_cap, int32_t *info_out) {
+    return pack_host_impl(d, mode, col0, col1, fold_value17, n_scaled, scaler_cols, scaler_mean, scaler_scale, tree_begin,
+                          tree_end, 0, nullptr, nullptr, slots_out, slots_cap, stream_out, stream_cap, consts_out,
+                          consts_cap, info_out);
+}
+
+extern "C" int64_t fmc_pack_forest_host_dyn(const fmc_forest_desc *d, int32_t mode, int32_t col0, int32_t col1,
+                                            const double *fold_value17, int32_t n_dyn, const int32_t *dyn_cols,
+                                            const int32_t *dyn_rows, uint64_t *slots_out, int64_t slots_cap,
+                                            uint64_t *stream_out, int64_t stream_cap, uint64_t *consts_out,
+                                            int64_t consts_cap, int32_t *info_out) {
+    return pack_host_impl(d, mode, col0, col1, fold_value17, 0, nullptr, nullptr, nullptr, 0, -1, n_dyn, dyn_cols, dyn_rows,
+                          slots_out, slots_cap, stream_out, stream_cap, consts_out, consts_cap, info_out);
 }

@@ -77,6 +77,16 @@ struct PackSpec {
     uint8_t is_flag[kNumMax];       // 0/1 valued numeric
     int ninf_row = 0;               // feature row that always holds -inf
     int tree_begin = 0, tree_end = -1;
+    // player mode: one-hot columns whose 0/1 value is a per-request feature row (the sampled passer /
+    // target / rusher of the play) instead of a pack-time constant
+    int n_dyn = 0;
+    int32_t dyn_col[2 * FMC_MAX_USAGE + FMC_MAX_PASSERS];
+    int8_t dyn_row[2 * FMC_MAX_USAGE + FMC_MAX_PASSERS];
+    int dyn_row_of(int col) const {
+        for (int i = 0; i < n_dyn; ++i)
+            if (dyn_col[i] == col) return dyn_row[i];
+        return -1;
+    }
     // play_model: fold values are standardised first
     int n_scaled = 0;
     int32_t scaler_cols[16];
@@ -204,6 +214,7 @@ struct Builder {
         return v <= f.thr[i];
     }
     int build(int i) {
+        int dyn = -1;      // feature row of a dynamic one-hot column
         for (;;) {
             if (f.left[i] < 0) return leaf(f.value[i]);
             int col = f.feat[i];
@@ -212,12 +223,24 @@ struct Builder {
                 if (!((s.fold_mask >> k) & 1u)) break;
                 i = const_left(i, cst[k]) ? f.left[i] : f.right[i];
             } else {
+                if (s.n_dyn && (dyn = s.dyn_row_of(col)) >= 0) break;
                 float v = (col == s.active[0] || col == s.active[1]) ? 1.0f : 0.0f;
                 i = const_left(i, v) ? f.left[i] : f.right[i];
             }
         }
-        int k = f.feat[i] - f.num_base;
         bool zm = f.kind == FMC_KIND_XGB && f.zero_is_missing;
+        if (dyn >= 0) {
+            // 0/1 column read per request: row holds 1.0 when the sampled name lights this column
+            const bool l0 = const_left(i, 0.0f), l1 = const_left(i, 1.0f);
+            if (l0 == l1) return build(l0 ? f.left[i] : f.right[i]);
+            int absent = build(l0 ? f.left[i] : f.right[i]);
+            int present = build(l1 ? f.left[i] : f.right[i]);
+            if (same_leaf(nodes[absent], nodes[present])) return absent;
+            // `row < 0.5` (xgboost) / `row <= 0.5` (sklearn): 0 goes left, 1 goes right
+            nodes.push_back({false, 0.0, dyn, 0.5f, absent, present});
+            return (int)nodes.size() - 1;
+        }
+        int k = f.feat[i] - f.num_base;
         if (zm && s.is_flag[k]) {
             bool present_left = 1.0f < f.thr[i];
             bool missing_left = f.dl[i] != 0;

@@ -48,11 +48,25 @@ struct TableRef {
     double base64[3];           // ... or sklearn init constants
 };
 
+// Usage tables of one team as the kernel reads them (include/fmc.h fmc_team_usage): role 0 passer, 1 rusher, 2 target.
+struct UsageDev {
+    double cdf[3][FMC_MAX_USAGE];    // cumsum(share) / total, the array Generator.choice searches (FMC:625-635)
+    int8_t n[3];
+    int8_t slot[3][FMC_MAX_USAGE];   // box line of a tracked name, -1 = not tracked
+};
+
 struct MatchupDev {
     double bias[2], ymul[2], mz[2], tanh35[2];
     unsigned long long game_begin, game_end, out_offset;
     TableRef tbl[kNumFam][2];
+    UsageDev usage[2];               // player mode only
 };
+
+// Player mode: the sampled names of a play are 0/1 feature rows behind the numeric rows of a request:
+// pass families: passer entry e -> row kDynRow0 + e, target entry e -> row kDynRow0 + FMC_MAX_PASSERS + e;
+// run yards: rusher entry e -> row kDynRow0 + e.
+constexpr int kDynRow0 = kSimRows;
+constexpr int kDynRows = FMC_MAX_PASSERS + FMC_MAX_USAGE;
 
 struct SimKernelArgs {
     const MatchupDev *matchups;
@@ -74,6 +88,8 @@ struct SimKernelArgs {
     const double *stream;
     double *trace;
     uint16_t *iters;
+    fmc_player_rec *players;           // player mode: [games][2][n_slots] per-game box lines (zeroed by the caller)
+    int n_slots;
 };
 
 enum Stage : int {
@@ -91,6 +107,7 @@ struct Lane {
     int score[2];
     int stage;
     int plays;                 // plays of the current game
+    int p1, wr;                // player mode: usage entries sampled for the current play (passer | rusher, target)
 };
 
 // A game's state between rounds: nine registers instead of sixteen, so that the tree walk (which runs with
@@ -108,7 +125,7 @@ struct PackedLane {
     unsigned long long game;
     double dist, ytg;
     uint32_t a;     // sec:12 | down:10 | period:3 | offense:1 | going:1 | stage:4
-    uint32_t b;     // iter:10 | plays:10
+    uint32_t b;     // iter:10 | plays:10 | p1:4 | wr:4 (player mode)
     uint32_t c;     // score[0]:16 | score[1]:16
 };
 __device__ __forceinline__ PackedLane pack_lane(const Lane &L) {
@@ -116,7 +133,7 @@ __device__ __forceinline__ PackedLane pack_lane(const Lane &L) {
     P.game = L.game; P.dist = L.dist; P.ytg = L.ytg;
     P.a = (uint32_t)L.sec | ((uint32_t)L.down << 12) | ((uint32_t)L.period << 22) | ((uint32_t)L.offense << 25) |
           ((uint32_t)L.going << 26) | ((uint32_t)L.stage << 27);
-    P.b = (uint32_t)L.iter | ((uint32_t)L.plays << 10);
+    P.b = (uint32_t)L.iter | ((uint32_t)L.plays << 10) | ((uint32_t)L.p1 << 20) | ((uint32_t)L.wr << 24);
     P.c = (uint32_t)L.score[0] | ((uint32_t)L.score[1] << 16);
     return P;
 }
@@ -125,7 +142,8 @@ __device__ __forceinline__ Lane unpack_lane(const PackedLane &P) {
     L.game = P.game; L.dist = P.dist; L.ytg = P.ytg;
     L.sec = (int)(P.a & 0xFFFu); L.down = (int)((P.a >> 12) & 0x3FFu); L.period = (int)((P.a >> 22) & 7u);
     L.offense = (int)((P.a >> 25) & 1u); L.going = (int)((P.a >> 26) & 1u); L.stage = (int)(P.a >> 27);
-    L.iter = (int)(P.b & 0x3FFu); L.plays = (int)(P.b >> 10);
+    L.iter = (int)(P.b & 0x3FFu); L.plays = (int)((P.b >> 10) & 0x3FFu);
+    L.p1 = (int)((P.b >> 20) & 0xFu); L.wr = (int)((P.b >> 24) & 0xFu);
     L.score[0] = (int)(P.c & 0xFFFFu); L.score[1] = (int)(P.c >> 16);
     return L;
 }
@@ -284,9 +302,9 @@ constexpr unsigned int kDeferBelow = FMC_DEFER_BELOW;
 // Requests are kept in 32-request chunks, feature-major ([feature][lane]); every key's list starts on
 // a chunk boundary, so at most kSimThreads/32 + kNumKeys chunks are in use.
 constexpr int kSimChunks = kSimThreads / 32 + kNumKeys;
-constexpr int kChunkFloats = kSimRows * 32;
+__host__ __device__ constexpr int chunk_floats(bool players) { return (kSimRows + (players ? kDynRows : 0)) * 32; }
 constexpr size_t kSimSharedBytes = ((sizeof(SimShared) + 15) / 16) * 16;
-constexpr size_t kSimFeatBytes = (size_t)kSimChunks * kChunkFloats * 4;
+__host__ __device__ constexpr size_t sim_feat_bytes(bool players) { return (size_t)kSimChunks * chunk_floats(players) * 4; }
 constexpr size_t kSimResultBytes = (size_t)kSimChunks * 32 * 3 * 8;
 
 // keys in processing order, heaviest family first (LPT-style dynamic scheduling):
@@ -312,9 +330,43 @@ __device__ __forceinline__ int stage2_outcome(const double raw[3], double u2) {
     return o > 2 ? 2 : o;
 }
 
+// ---- player mode ---------------------------------------------------------------------------------
+// Generator.choice(n, p=share): searchsorted(cdf, u, side='right') (FMC:625-635)
+__device__ __forceinline__ int sample_usage(const UsageDev &U, int role, double u) {
+    int idx = 0;
+#pragma unroll
+    for (int i = 0; i < FMC_MAX_USAGE; ++i) idx += (i < U.n[role] && U.cdf[role][i] <= u) ? 1 : 0;
+    return idx < U.n[role] ? idx : U.n[role] - 1;
+}
+// pstats[team][role][name] of a tracked name (FMC:1073-1075, 1108-1148, 1163-1192, 1207-1249): the lane owns its
+// game's box lines, so a plain read-modify-write.  counts: 10-bit fields att|tgt, comp|rec, td, INT, sacks.
+enum : unsigned long long { PC_ATT = 1ULL, PC_COMP = 1ULL << 10, PC_TD = 1ULL << 20, PC_INT = 1ULL << 30, PC_SACK = 1ULL << 40 };
+__device__ __forceinline__ void credit(const SimKernelArgs &a, const MatchupDev &M, const Lane &L, int team, int role,
+                                       int entry, unsigned long long counts, bool has_yds, double yds) {
+    if (!a.players) return;
+    const int slot = M.usage[team].slot[role][entry];
+    if (slot < 0) return;
+    fmc_player_rec *r = a.players + ((size_t)(M.out_offset + (L.game - M.game_begin)) * 2 + (size_t)team) * (size_t)a.n_slots + (size_t)slot;
+    if (has_yds) r->yds += yds;
+    r->counts += counts;
+}
+// a pass call: sample_qb, sample_target, tgt += 1 (FMC:1058-1075); a run call: sample_rusher, att += 1 (FMC:1203-1208)
+template <bool TEST>
+__device__ __forceinline__ void call_pass(Lane &L, const SimKernelArgs &a, const MatchupDev &M, Draws<TEST> &D, int team) {
+    L.p1 = sample_usage(M.usage[team], 0, D.u(S_U_P1));
+    L.wr = sample_usage(M.usage[team], 2, D.u(S_U_WR));
+    credit(a, M, L, team, 2, L.wr, PC_ATT, false, 0.0);
+}
+template <bool TEST>
+__device__ __forceinline__ void call_run(Lane &L, const SimKernelArgs &a, const MatchupDev &M, Draws<TEST> &D, int team) {
+    L.p1 = sample_usage(M.usage[team], 1, D.u(S_U_P1));
+    L.wr = 0;
+    credit(a, M, L, team, 1, L.p1, PC_ATT, false, 0.0);
+}
+
 // Advance one lane until it posts a request (returns key = family * 2 + offense) or has nothing
 // left to do (returns -1).  `res` points at this lane's result record of the previous round.
-template <bool TEST>
+template <bool TEST, bool PLAYERS>
 __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, SimShared &sh, const double *res) {
     const MatchupDev &M = sh.M;
     const int matchup = sh.cur_matchup;
@@ -326,7 +378,7 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
             L.game = g;
             L.offense = (int)(g & 1ULL);
             L.sec = 3600; L.down = 1; L.dist = 10.0; L.ytg = 75.0; L.period = 1; L.going = 0;
-            L.score[0] = 0; L.score[1] = 0; L.iter = 0; L.plays = 0;
+            L.score[0] = 0; L.score[1] = 0; L.iter = 0; L.plays = 0; L.p1 = 0; L.wr = 0;
             L.stage = ST_ITER;
         }
         if (L.stage == ST_ITER) {
@@ -395,8 +447,14 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
             const double s = a0 + a1;
             a0 = a0 / s; a1 = a1 / s;
             const double c0 = a0 / (a0 + a1);
-            if (D.u(S_U_CALL) < c0) { atomicAdd(&sh.stat[FMC_C_RUN], 1ULL); L.stage = ST_WAIT_RQ; return 3 * 2 + team; }
+            if (D.u(S_U_CALL) < c0) {
+                atomicAdd(&sh.stat[FMC_C_RUN], 1ULL);
+                if (PLAYERS) call_run<TEST>(L, a, M, D, team);
+                L.stage = ST_WAIT_RQ;
+                return 3 * 2 + team;
+            }
             atomicAdd(&sh.stat[FMC_C_PASS], 1ULL);
+            if (PLAYERS) call_pass<TEST>(L, a, M, D, team);
             L.stage = ST_WAIT_S1;
             return 0 * 2 + team;
         }
@@ -421,8 +479,14 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
             const double s = a0 + a1;
             a0 = a0 / s; a1 = a1 / s;
             const double c0 = a0 / (a0 + a1);
-            if (D.u(S_U_CALL) < c0) { atomicAdd(&sh.stat[FMC_C_RUN], 1ULL); L.stage = ST_WAIT_RQ; return 3 * 2 + team; }
+            if (D.u(S_U_CALL) < c0) {
+                atomicAdd(&sh.stat[FMC_C_RUN], 1ULL);
+                if (PLAYERS) call_run<TEST>(L, a, M, D, team);
+                L.stage = ST_WAIT_RQ;
+                return 3 * 2 + team;
+            }
             atomicAdd(&sh.stat[FMC_C_PASS], 1ULL);
+            if (PLAYERS) call_pass<TEST>(L, a, M, D, team);
             L.stage = ST_WAIT_S1;
             return 0 * 2 + team;
         }
@@ -451,13 +515,20 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
             const int outcome = stage2_outcome(raw, D.u(S_U_S2));
             if (outcome == 0) {                                   // incomplete FMC:1160-1168
                 atomicAdd(&sh.stat[FMC_C_INC], 1ULL);
+                if (PLAYERS) credit(a, M, L, team, 0, L.p1, PC_ATT, false, 0.0);                    // FMC:1163-1164
                 L.down += 1; L.going = 0;
                 tick_clock(L, 10);
                 L.stage = ST_ITER;
                 continue;
             }
-            if (outcome == 2) { atomicAdd(&sh.stat[FMC_C_SACK], 1ULL); L.stage = ST_WAIT_SQ; return 4 * 2 + team; }
+            if (outcome == 2) {
+                atomicAdd(&sh.stat[FMC_C_SACK], 1ULL);
+                if (PLAYERS) credit(a, M, L, team, 0, L.p1, PC_SACK, false, 0.0);                   // FMC:1173-1174
+                L.stage = ST_WAIT_SQ;
+                return 4 * 2 + team;
+            }
             atomicAdd(&sh.stat[FMC_C_INT], 1ULL);                 // intercepted FMC:1186-1199
+            if (PLAYERS) credit(a, M, L, team, 0, L.p1, PC_ATT | PC_INT, false, 0.0);               // FMC:1190-1192
             const double ret = softclip(6.0 + 5.0 * D.z(S_Z_INT), 0.0, L.ytg);
             const double spot = 100.0 - (L.ytg - ret);
             L.going = 0;
@@ -477,10 +548,18 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
             if (ytg0 <= 12.0 && L.down <= 3 && D.u(S_U_FIN) < rz_finish_prob(ytg0, M.tanh35[team], L.down, true)) yards = ytg0;
             if (yards + 1e-9 >= L.ytg) {
                 atomicAdd(&sh.stat[FMC_C_TD], 1ULL);
+                if (PLAYERS) {                                                                        // FMC:1108-1127
+                    credit(a, M, L, team, 0, L.p1, PC_ATT | PC_COMP | PC_TD, true, L.ytg);
+                    credit(a, M, L, team, 2, L.wr, PC_COMP | PC_TD, true, L.ytg);
+                }
                 L.score[team] += 7; L.going = 0;
                 tick_clock(L, 20);
                 change_possession(L, true, 75.0);
             } else {
+                if (PLAYERS) {                                                                        // FMC:1108-1109, 1140-1145
+                    credit(a, M, L, team, 0, L.p1, PC_ATT | PC_COMP, true, yards);
+                    credit(a, M, L, team, 2, L.wr, PC_COMP, true, yards);
+                }
                 L.going = 0;
                 advance_down(L, yards);
                 tick_clock(L, 26);
@@ -497,11 +576,13 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
             }
             if (yards + 1e-9 >= ytg0) {
                 atomicAdd(&sh.stat[FMC_C_TD], 1ULL);
+                if (PLAYERS) credit(a, M, L, team, 1, L.p1, PC_TD, true, L.ytg);                     // FMC:1232-1234
                 L.score[team] += 7;
                 tick_clock(L, 28);
                 change_possession(L, true, 75.0);
                 L.going = 0;
             } else {
+                if (PLAYERS) credit(a, M, L, team, 1, L.p1, 0ULL, true, yards);                      // FMC:1246-1247
                 advance_down(L, yards);
                 tick_clock(L, 28);
                 L.going = 0;
@@ -521,8 +602,21 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
 // orientation), written feature-major: col[k * 32] is feature row k of this request.  Rows: 0 down
 // 1 distance 2 yardsToGoal 3 is_red_zone 4 score_diff 5 seconds 6 goal_to_go 7 fourth_and_short
 // 8 fg_range 9 half 10 two_minute 11..13 "B" views of 1, 2, 4; row 14 (-inf) is set once per chunk.
+template <bool PLAYERS>
 __device__ __forceinline__ void write_features(float *col, const Lane &L, int fam, const SimKernelArgs &a) {
     const int team = L.offense;
+    if (PLAYERS && fam != 5) {
+        // passer_name / target_name / rusher_name of the row (FMC:1079-1081, 1216) as 0/1 rows per usage entry
+        if (fam == 3) {
+#pragma unroll
+            for (int e = 0; e < FMC_MAX_USAGE; ++e) col[(kDynRow0 + e) * 32] = (e == L.p1) ? 1.f : 0.f;
+        } else {
+#pragma unroll
+            for (int e = 0; e < FMC_MAX_PASSERS; ++e) col[(kDynRow0 + e) * 32] = (e == L.p1) ? 1.f : 0.f;
+#pragma unroll
+            for (int e = 0; e < FMC_MAX_USAGE; ++e) col[(kDynRow0 + FMC_MAX_PASSERS + e) * 32] = (e == L.wr) ? 1.f : 0.f;
+        }
+    }
     const int sd = L.score[team] - L.score[team ^ 1];
     float v[6];
     v[0] = (float)L.down; v[1] = (float)L.dist; v[2] = (float)L.ytg; v[3] = (L.ytg <= 20.0) ? 1.f : 0.f;
@@ -575,9 +669,14 @@ __device__ __forceinline__ double eval_output(int fam, const TableRef &T, int ou
     return walk_output<false, false>(F, fcol, lane, (double)T.base[out], levels);
 }
 
-template <bool TEST>
+// PLAYERS = true: usage tables are set (fmc_set_usage): names are sampled per play, requests carry kDynRows
+// more feature rows, tracked names get per-game box lines.  The shipped configuration (every name "Unknown")
+// runs the PLAYERS = false instantiation, which carries none of it.
+template <bool TEST, bool PLAYERS>
 __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const SimKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kChunkFloats = chunk_floats(PLAYERS);
+    constexpr size_t kSimFeatBytes = sim_feat_bytes(PLAYERS);
     SimShared &sh = *reinterpret_cast<SimShared *>(smem_raw);
     float *feats = reinterpret_cast<float *>(smem_raw + kSimSharedBytes);
     double *results = reinterpret_cast<double *>(smem_raw + kSimSharedBytes + kSimFeatBytes);
@@ -597,7 +696,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     {
         Lane L0;
         L0.game = 0; L0.dist = 0.0; L0.ytg = 0.0; L0.sec = 0; L0.down = 0; L0.offense = 0; L0.period = 0; L0.going = 0;
-        L0.iter = 0; L0.score[0] = 0; L0.score[1] = 0; L0.plays = 0;
+        L0.iter = 0; L0.score[0] = 0; L0.score[1] = 0; L0.plays = 0; L0.p1 = 0; L0.wr = 0;
         L0.stage = ST_IDLE;
         P = pack_lane(L0);
     }
@@ -634,7 +733,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
         for (;;) {
             // ---- A: advance to the next request (a held-back lane re-posts the one it has)
             Lane L = unpack_lane(P);
-            const int key = held >= 0 ? held : advance_lane<TEST>(L, a, sh, results + (size_t)pos * 3);
+            const int key = held >= 0 ? held : advance_lane<TEST, PLAYERS>(L, a, sh, results + (size_t)pos * 3);
             __syncwarp();
             // ---- B: compaction
             unsigned int rank = 0;
@@ -671,7 +770,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
             if (key >= 0) {
                 if (rank < sh.evalc[key]) {
                     pos = (int)(sh.off[key] + rank);
-                    write_features(feats + (size_t)(pos >> 5) * kChunkFloats + (pos & 31), L, key >> 1, a);
+                    write_features<PLAYERS>(feats + (size_t)(pos >> 5) * kChunkFloats + (pos & 31), L, key >> 1, a);
                 } else {
                     held = key;
                 }
@@ -720,6 +819,6 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     if (a.counters && tid < FMC_N_COUNTERS && sh.stat[tid]) atomicAdd(&a.counters[tid], sh.stat[tid]);
 }
 
-inline size_t sim_smem_bytes() { return kSimSharedBytes + kSimFeatBytes + kSimResultBytes; }
+inline size_t sim_smem_bytes(bool players = false) { return kSimSharedBytes + sim_feat_bytes(players) + kSimResultBytes; }
 
 }  // namespace fmc

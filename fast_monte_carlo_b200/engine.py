@@ -36,6 +36,7 @@ class MatchupSpec:
     game_begin: int = 0                  # this rank's slice [game_begin, game_end)
     game_end: int = 0
     out_offset: int = 0
+    usage: Optional[tuple] = None        # (usage.TeamUsage of team A, of team B) or None = every name "Unknown"
 
 
 class Engine:
@@ -82,6 +83,19 @@ class Engine:
             dict(sp=[list(m.sp_a), list(m.sp_b)], coach_col=(self.coach_col(m.team_a), self.coach_col(m.team_b)),
                  game_begin=m.game_begin, game_end=m.game_end, out_offset=m.out_offset)
             for m in self.matchups])
+        # usage tables (FMC:228-249): all matchups or none; a slate mixing both gives the others the trivial table
+        with_usage = [m for m in self.matchups if m.usage is not None and not (m.usage[0].trivial and m.usage[1].trivial)]
+        if with_usage:
+            from . import usage as _usage
+            teams = []
+            for m in self.matchups:
+                if m.usage is None:
+                    raise ValueError("player usage must be given for every matchup of a slate or for none")
+                teams.append(m.usage)
+            self.n_slots = max(len(tu.slots) for pair in teams for tu in pair)
+            self.ctx.set_usage(teams, self.n_slots)
+        else:
+            self.n_slots = 0
 
     def simulate_host(self, seed: int, **kw) -> dict:
         return self.ctx.simulate_host(seed=seed, **kw)

@@ -17,6 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FMC_LIB_PATH") or os.path.join(HERE, "libfmc_b200.so")
 
 N_MODELS = 7
+MODEL_INDEX = {"pass_stage1": 0, "pass_stage2": 1, "pass_yards": 2, "run_yards": 3, "sack_yards": 4,
+               "play_model": 5, "run_fumble": 6}
 HIST_BINS = 128
 N_COUNTERS = 32
 N_SLOTS = 16
@@ -61,8 +63,33 @@ class SimArgs(C.Structure):
         ("seed", C.c_uint64), ("n_matchups", C.c_int32), ("reserved", C.c_int32),
         ("scores_dev", C.c_void_p), ("hist_dev", C.c_void_p), ("counters_dev", C.c_void_p),
         ("stream_dev", C.c_void_p), ("trace_dev", C.c_void_p), ("iters_dev", C.c_void_p),
-        ("stream", C.c_void_p),
+        ("stream", C.c_void_p), ("players_dev", C.c_void_p),
     ]
+
+
+MAX_USAGE = 8
+MAX_PASSERS = 4
+ROLE_INDEX = {"pass": 0, "rush": 1, "rec": 2}
+PLAYER_REC = np.dtype([("yds", "<f8"), ("counts", "<u8")])     # fmc_player_rec
+
+
+class Usage(C.Structure):
+    _fields_ = [("n", C.c_int32), ("reserved", C.c_int32), ("share", C.c_double * MAX_USAGE),
+                ("slot", C.c_int32 * MAX_USAGE), ("col", (C.c_int32 * MAX_USAGE) * N_MODELS)]
+
+
+class TeamUsageC(C.Structure):
+    _fields_ = [("role", Usage * 3)]
+
+
+def unpack_player_box(rec: np.ndarray) -> np.ndarray:
+    """fmc_player_rec[...] -> float64[..., 6] = yds, att|tgt, comp|rec, td, INT, sacks (10-bit count fields)."""
+    out = np.zeros(rec.shape + (6,), dtype=np.float64)
+    out[..., 0] = rec["yds"]
+    c = rec["counts"]
+    for k in range(5):
+        out[..., 1 + k] = ((c >> np.uint64(10 * k)) & np.uint64(0x3FF)).astype(np.float64)
+    return out
 
 
 _lib = None
@@ -95,6 +122,13 @@ def load_library():
     L.fmc_simulate.argtypes = [C.c_void_p, C.POINTER(SimArgs)]
     L.fmc_simulate_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
+    L.fmc_simulate_players_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fmc_set_usage.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    L.fmc_pack_forest_host_dyn.restype = C.c_int64
+    L.fmc_pack_forest_host_dyn.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                           C.c_void_p, C.c_int64, C.c_void_p]
     L.fmc_tree_predict.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_void_p]
     L.fmc_tree_predict_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
@@ -117,7 +151,7 @@ EXPORTED_SYMBOLS = (
     "fmc_set_scaler", "fmc_set_active_columns", "fmc_set_params", "fmc_set_matchups", "fmc_simulate",
     "fmc_simulate_host", "fmc_tree_predict", "fmc_tree_predict_host", "fmc_packed_slots", "fmc_sync",
     "fmc_gather_probe", "fmc_debug_errors",
-    "fmc_pack_forest_host",
+    "fmc_pack_forest_host", "fmc_pack_forest_host_dyn", "fmc_set_usage", "fmc_simulate_players_host",
 )
 
 
@@ -151,7 +185,7 @@ def forest_desc(f) -> tuple:
     return d, arrs
 
 
-def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begin=0, tree_end=-1):
+def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begin=0, tree_end=-1, dyn=None):
     """Host-only: run the specialiser/packer and return (slots u64[], stream u64[], consts u64[], info dict)
     -- the node table, the root stream and the constants side stream of csrc/fmc_pack.hpp.
     Evaluates nothing; used by the CPU tests and for table-size accounting."""
@@ -174,11 +208,19 @@ def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begi
     slots = np.zeros(cap_s, dtype=np.uint64)
     stream = np.zeros(cap_r, dtype=np.uint64)
     consts = np.zeros(cap_c, dtype=np.uint64)
-    n = L.fmc_pack_forest_host(
-        C.byref(d), int(mode), int(cols[0]), int(cols[1]), fv.ctypes.data, ns,
-        None if sc is None else sc.ctypes.data, None if sm is None else sm.ctypes.data,
-        None if ss is None else ss.ctypes.data, int(tree_begin), int(tree_end),
-        slots.ctypes.data, cap_s, stream.ctypes.data, cap_r, consts.ctypes.data, cap_c, info.ctypes.data)
+    if dyn is not None:      # player mode: {model column: feature row} read per request instead of folded
+        dc = np.ascontiguousarray(list(dyn.keys()), np.int32)
+        dr = np.ascontiguousarray(list(dyn.values()), np.int32)
+        n = L.fmc_pack_forest_host_dyn(
+            C.byref(d), int(mode), int(cols[0]), int(cols[1]), fv.ctypes.data, int(dc.shape[0]),
+            dc.ctypes.data if dc.shape[0] else None, dr.ctypes.data if dr.shape[0] else None,
+            slots.ctypes.data, cap_s, stream.ctypes.data, cap_r, consts.ctypes.data, cap_c, info.ctypes.data)
+    else:
+        n = L.fmc_pack_forest_host(
+            C.byref(d), int(mode), int(cols[0]), int(cols[1]), fv.ctypes.data, ns,
+            None if sc is None else sc.ctypes.data, None if sm is None else sm.ctypes.data,
+            None if ss is None else ss.ctypes.data, int(tree_begin), int(tree_end),
+            slots.ctypes.data, cap_s, stream.ctypes.data, cap_r, consts.ctypes.data, cap_c, info.ctypes.data)
     if n < 0:
         _check(int(n))
     if n > cap_s or int(info[5]) > cap_r or int(info[6]) > cap_c:
@@ -207,6 +249,8 @@ class Context:
         self.smem_per_block = int(smem.value)
         self.device_name = name.value.decode()
         self.n_matchups = 0
+        self.n_slots = 0
+        self.has_usage = False
 
     def close(self):
         if getattr(self, "_h", None):
@@ -256,7 +300,37 @@ class Context:
             arr[i].out_offset = int(m.get("out_offset", 0))
         _check(self._L.fmc_set_matchups(self._h, len(ms), arr))
         self.n_matchups = len(ms)
+        self.n_slots = 0
+        self.has_usage = False
         self.total_games = max((int(m.get("out_offset", 0)) + int(m["game_end"]) - int(m["game_begin"])) for m in ms)
+
+    def set_usage(self, teams, n_slots: int) -> None:
+        """teams: [n_matchups][2] objects with .role[r].names/.share/.slot/.col (usage.TeamUsage), or None to
+        return to the shipped configuration (every name "Unknown").  fmc_set_usage."""
+        if teams is None:
+            _check(self._L.fmc_set_usage(self._h, 0, None, 0))
+            self.n_slots, self.has_usage = 0, False
+            return
+        flat = [tu for pair in teams for tu in pair]
+        arr = (TeamUsageC * len(flat))()
+        for i, tu in enumerate(flat):
+            for rname, ri in ROLE_INDEX.items():
+                ru = tu.role[rname]
+                u = arr[i].role[ri]
+                if len(ru.names) > MAX_USAGE:
+                    raise ValueError("usage table too long")
+                u.n = len(ru.names)
+                for e in range(MAX_USAGE):
+                    u.slot[e] = -1
+                    for m in range(N_MODELS):
+                        u.col[m][e] = -1
+                for e in range(u.n):
+                    u.share[e] = float(ru.share[e])
+                    u.slot[e] = int(ru.slot[e])
+                    for name, cols in ru.col.items():
+                        u.col[MODEL_INDEX[name]][e] = int(cols[e])
+        _check(self._L.fmc_set_usage(self._h, len(teams), C.cast(arr, C.c_void_p), int(n_slots)))
+        self.n_slots, self.has_usage = int(n_slots), True
 
     def packed_slots(self, matchup: int = 0) -> np.ndarray:
         out = np.zeros((N_MODELS, 2), dtype=np.int32)
@@ -265,7 +339,7 @@ class Context:
 
     # -- simulation ------------------------------------------------------------------------------
     def simulate_device(self, *, seed: int, scores=0, hist=0, counters=0, stream_in=0, trace=0, iters=0,
-                        cuda_stream=0) -> None:
+                        cuda_stream=0, players=0) -> None:
         """Asynchronous launch on raw device pointers (ints; 0 = not requested)."""
         a = SimArgs()
         a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -273,11 +347,12 @@ class Context:
         a.scores_dev = scores or None; a.hist_dev = hist or None; a.counters_dev = counters or None
         a.stream_dev = stream_in or None; a.trace_dev = trace or None; a.iters_dev = iters or None
         a.stream = cuda_stream or None
+        a.players_dev = players or None      # fmc_player_rec[games][2][n_slots], zeroed by the caller
         _check(self._L.fmc_simulate(self._h, C.byref(a)))
 
     def simulate_host(self, *, seed: int, want_scores=True, want_hist=True, stream: Optional[np.ndarray] = None,
-                      want_trace=False, want_iters=False) -> dict:
-        """End-to-end call with host buffers (fmc_simulate_host)."""
+                      want_trace=False, want_iters=False, want_players=False) -> dict:
+        """End-to-end call with host buffers (fmc_simulate_host / fmc_simulate_players_host)."""
         n = self.total_games
         scores = np.zeros(n, dtype=np.uint32) if want_scores else None
         hist = np.zeros((self.n_matchups, 2, HIST_BINS, HIST_BINS), dtype=np.uint32) if want_hist else None
@@ -289,9 +364,20 @@ class Context:
             if stream.shape != (n, MAX_ITERS, N_SLOTS):
                 raise ValueError(f"stream must be [{n},{MAX_ITERS},{N_SLOTS}]")
         vp = lambda a: None if a is None else a.ctypes.data
-        _check(self._L.fmc_simulate_host(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, vp(scores), vp(hist), vp(counters),
-                                         vp(stream), vp(trace), vp(iters)))
+        players = None
+        if want_players:
+            if not self.has_usage:
+                raise FmcError("want_players needs set_usage")
+            players = np.zeros((n, 2, max(self.n_slots, 1)), dtype=PLAYER_REC)
+            _check(self._L.fmc_simulate_players_host(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, vp(scores), vp(hist),
+                                                     vp(counters), vp(stream), vp(trace), vp(iters),
+                                                     players.ctypes.data if self.n_slots else None))
+        else:
+            _check(self._L.fmc_simulate_host(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, vp(scores), vp(hist), vp(counters),
+                                             vp(stream), vp(trace), vp(iters)))
         out = dict(counters={k: int(counters[i]) for i, k in enumerate(COUNTER_NAMES)})
+        if players is not None:
+            out["players"] = unpack_player_box(players[:, :, :self.n_slots])
         if scores is not None:
             # score word = points A | points B << 16: on a little-endian host the uint16 view IS the [n, 2] table
             out["scores"] = (scores.view(np.uint16).reshape(n, 2).astype(np.int32) if sys.byteorder == "little" else

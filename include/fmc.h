@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FMC_ABI_VERSION 2
+#define FMC_ABI_VERSION 3
 
 typedef enum {
     FMC_OK = 0,
@@ -96,6 +96,31 @@ typedef struct {
     uint64_t out_offset;  /* index of game_begin in the per-game output arrays */
 } fmc_matchup;
 
+/* Usage table of one role of one team: TeamContext.qb_share / rush_share / target_share (FMC:262-264) as
+ * the hot path reads them.  The engine samples an entry per play exactly as Generator.choice(len(df),
+ * p=share) does (FMC:625-635: cdf = cumsum(share) / total, searchsorted(cdf, u, 'right')), feeds the models
+ * the entry's one-hot column (the OneHotEncoder(handle_unknown='ignore') half of the preprocessors applied
+ * to passer_name / target_name / rusher_name, FMC:1079-1081, 1216) and keeps a per-game box line for
+ * entries whose `slot` is >= 0 (names in the team's focus track set, FMC:1062-1063, 1204). */
+#define FMC_MAX_USAGE 8          /* entries per table */
+#define FMC_MAX_PASSERS 4        /* entries of the passer table */
+typedef struct {
+    int32_t n;                   /* 1..FMC_MAX_USAGE (passers: 1..FMC_MAX_PASSERS) */
+    int32_t reserved;
+    double share[FMC_MAX_USAGE]; /* df['share'].values, in table order */
+    int32_t slot[FMC_MAX_USAGE]; /* output slot of a tracked name inside the team's box, -1 = not tracked */
+    int32_t col[FMC_N_MODELS][FMC_MAX_USAGE]; /* one-hot column the name lights in model m, -1 = not a category */
+} fmc_usage;
+typedef struct { fmc_usage role[3]; } fmc_team_usage;   /* 0 passer (sample_qb), 1 rusher, 2 target */
+
+/* Per-game box line of one tracked name: pstats[team][role][name] (FMC:146-166) at the end of the game.
+ * counts: 10-bit fields from bit 0: att|tgt, comp|rec, td, INT, sacks.  yds is the float64 running sum in
+ * play order (the reference rounds it to one decimal only when it writes the row, FMC:1276-1296). */
+typedef struct {
+    double yds;
+    uint64_t counts;
+} fmc_player_rec;
+
 #define FMC_HIST_BINS 128        /* joint (points A, points B) histogram is FMC_HIST_BINS^2 per orientation */
 #define FMC_N_COUNTERS 32
 /* counters[] layout (totals over the call) */
@@ -121,6 +146,7 @@ typedef struct {
     double *trace_dev;        /* optional per-iteration states [games][FMC_MAX_ITERS][FMC_TRACE_COLS] (test mode) */
     uint16_t *iters_dev;      /* optional [games] loop iterations of each game */
     void *stream;             /* cudaStream_t */
+    fmc_player_rec *players_dev; /* optional, only with fmc_set_usage: [games][2 teams A/B][n_slots], ZEROED by the caller */
 } fmc_sim_args;
 
 typedef struct fmc_ctx fmc_ctx;
@@ -147,6 +173,14 @@ int fmc_set_params(fmc_ctx *ctx, const fmc_params *p);
  * every loaded forest on the per-orientation constants and uploads the packed node tables. */
 int fmc_set_matchups(fmc_ctx *ctx, int32_t n, const fmc_matchup *m);
 
+/* Replaces the usage half of build_team_context_from_sp_flex (`_usage_from_focus_or_fallback`, FMC:228-249,
+ * 1646-1659): teams[n_matchups][2] (team A, team B of each matchup of the last fmc_set_matchups), n_slots =
+ * box lines per team in the per-game output.  teams == NULL returns to the shipped configuration (one
+ * "Unknown" per role, nothing tracked; the hot columns of fmc_set_active_columns apply).  With usage set,
+ * fmc_simulate runs the player instantiation of the kernel: the sampled names become extra 0/1 feature rows
+ * of a request, so the node tables stay specialised per orientation only. */
+int fmc_set_usage(fmc_ctx *ctx, int32_t n_matchups, const fmc_team_usage *teams, int32_t n_slots);
+
 /* Replaces simulate_matchup's pool of _run_pair workers (FMC:1467-1521): plays every game of every
  * matchup range to completion on the GPU.  Asynchronous on args->stream. */
 int fmc_simulate(fmc_ctx *ctx, const fmc_sim_args *args);
@@ -156,6 +190,11 @@ int fmc_simulate(fmc_ctx *ctx, const fmc_sim_args *args);
 int fmc_simulate_host(fmc_ctx *ctx, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
                       uint64_t *counters_host, const double *stream_host, double *trace_host,
                       uint16_t *iters_host);
+
+/* fmc_simulate_host plus the per-game player box [games][2][n_slots] (collect_players=True, FMC:1480-1505). */
+int fmc_simulate_players_host(fmc_ctx *ctx, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
+                              uint64_t *counters_host, const double *stream_host, double *trace_host,
+                              uint16_t *iters_host, fmc_player_rec *players_host);
 
 /* Raw margins of one model on n rows of the 17 numerics (play_model: first 12), NUM order of
  * FMC:676-682, float64 row-major [n][17]; out float64 [n][n_outputs].  Trees [tree_begin, tree_end)
@@ -191,6 +230,13 @@ int fmc_gather_probe(fmc_ctx *ctx, int64_t table_bytes, int32_t iters, double *g
  * small are left untouched.  info_out[32] = {rounds, max group depth, n_outputs, trees per group,
  * "-inf" feature row, stream words, side-stream words, constant trees, stream_off[8] (8-byte words),
  * n_groups[8], consts_off[8]}. */
+/* Same with dynamic one-hot columns (player mode): dyn_cols[n_dyn] are model columns whose 0/1 value is read
+ * per request from feature row dyn_rows[i] instead of being folded. */
+int64_t fmc_pack_forest_host_dyn(const fmc_forest_desc *desc, int32_t mode, int32_t col0, int32_t col1,
+                                 const double *fold_value17, int32_t n_dyn, const int32_t *dyn_cols,
+                                 const int32_t *dyn_rows, uint64_t *slots_out, int64_t slots_cap,
+                                 uint64_t *stream_out, int64_t stream_cap, uint64_t *consts_out, int64_t consts_cap,
+                                 int32_t *info_out);
 int64_t fmc_pack_forest_host(const fmc_forest_desc *desc, int32_t mode, int32_t col0, int32_t col1,
                              const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
                              const double *scaler_mean, const double *scaler_scale, int32_t tree_begin,

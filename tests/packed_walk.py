@@ -66,7 +66,8 @@ def walk(slots, stream, consts, meta, rows, skl, base):
     ilp = meta["ilp"]
     out = np.zeros((n, meta["n_outputs"]), dtype=np.float64)
     ar = np.arange(n)
-    assert rows.shape[1] == meta["ninf_row"] + 1 and np.all(np.isneginf(rows[:, meta["ninf_row"]]))
+    # player mode appends 0/1 rows (one per usage entry) behind the -inf row
+    assert rows.shape[1] >= meta["ninf_row"] + 1 and np.all(np.isneginf(rows[:, meta["ninf_row"]]))
 
     def value(w_lo, w_hi):
         if skl:

@@ -1,0 +1,132 @@
+"""Player mode of the CUDA engine (usage tables, dynamic one-hots, per-game player box) through the C-ABI:
+against the fixtures produced by the unmodified reference (tests/golden/ref_players.npz) and against the
+C oracle on injected and Philox draws."""
+import json
+import os
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from conftest import GOLDEN
+from fast_monte_carlo_b200 import priors, usage
+from fast_monte_carlo_b200.engine import Engine, MatchupSpec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def contexts(models_s2):
+    focus = usage.build_focus_usage_tables(os.path.join(GOLDEN, "players_focus.csv"))
+    sp = priors.load_sp_flex(priors.packaged_priors_path())
+    out = {}
+    for name in ("Kansas State", "Iowa State", "UTSA", "Ohio State"):
+        tc = priors.build_team_context_from_sp_flex(name, 2025, 1, sp, focus=focus, usage_dir=GOLDEN)
+        out[name] = (tc, usage.resolve_team(tc, models_s2))
+    return out
+
+
+def _spec(contexts, a, b, n, g0=0, out_offset=0):
+    (ta, ua), (tb, ub) = contexts[a], contexts[b]
+    return MatchupSpec(a, b, ta.sp, tb.sp, n, g0, g0 + n, out_offset, usage=(ua, ub))
+
+
+def _box_equal_philox(got, ref):
+    """Philox runs: counts exact; yards within float tolerance (the state machine is bit-exact, but a normal
+    draw in the AS241 tail goes through `log`, where the device and glibc results may differ in the last
+    bit -- it vanishes in `ytg - yards` yet stays visible in a running sum of yards).  Injected-stream runs
+    compare the float64 bits (test_players_injected_stream_vs_oracle)."""
+    assert np.array_equal(got[..., 1:], ref[..., 1:])
+    assert np.allclose(got[..., 0], ref[..., 0], rtol=1e-12, atol=1e-9)
+
+
+def _frame(rows, cols):
+    df = pd.DataFrame(rows, columns=cols)
+    return df.sort_values(["sim", "team", "role", "player"], kind="stable").reset_index(drop=True)
+
+
+def test_reference_golden_players(engine, contexts):
+    """The reference's OWN trajectories and players table under a synthetic focus sheet."""
+    t = np.load(os.path.join(GOLDEN, "ref_players.npz"))
+    meta = json.loads(str(t["meta"]))
+    cols = json.loads(str(t["player_cols"]))
+    from oracle import c_oracle as co
+    stream = co.make_stream(len(meta), int(t["stream_seed"]))
+    frames = []
+    for g, m in enumerate(meta):
+        spec = _spec(contexts, m["team_a"], m["team_b"], 1, g0=g)
+        engine.set_matchups([spec])
+        r = engine.simulate_host(0, stream=stream[g:g + 1], want_trace=True, want_iters=True, want_players=True)
+        k = int(t["iters"][g])
+        assert r["iters"][0] == k, g
+        assert np.array_equal(r["trace"][0, :k], t["traces"][g, :k]), g
+        f = g & 1
+        assert (r["scores"][0, f], r["scores"][0, f ^ 1]) == tuple(t["scores"][g])
+        frames.append(usage.player_rows(r["players"], g, (m["team_a"], m["team_b"]), spec.usage))
+    got = _frame(pd.concat(frames, ignore_index=True).values.tolist(), cols)
+    want = _frame(json.loads(str(t["player_rows"])), cols)
+    assert len(got) == len(want) > 50
+    for c in cols:
+        assert got[c].tolist() == want[c].tolist(), c
+
+
+@pytest.mark.parametrize("a,b", [("Kansas State", "Iowa State"), ("UTSA", "Iowa State")])
+def test_players_injected_stream_vs_oracle(engine, oracle, models_s2, contexts, a, b):
+    n = 4096
+    stream = oracle.make_stream(n, 31)
+    spec = _spec(contexts, a, b, n)
+    engine.set_matchups([spec])
+    got = engine.simulate_host(0, stream=stream, want_trace=True, want_iters=True, want_players=True)
+    cfg = oracle.make_config(models_s2, spec.sp_a, spec.sp_b)
+    ref = oracle.simulate(cfg, n, stream=stream, trace=True, usage=oracle.make_usage(spec.usage), n_slots=engine.n_slots)
+    assert np.array_equal(got["scores"], ref["scores"])
+    assert np.array_equal(got["iters"], ref["iters"])
+    t0, t1 = got["trace"], ref["trace"]
+    assert bool(((t0 == t1) | (np.isnan(t0) & np.isnan(t1))).all())
+    assert np.array_equal(got["players"], ref["players"])          # float64 yards bit for bit
+    assert got["players"][..., 1].sum() > n                          # something was tracked
+
+
+def test_players_philox_vs_oracle_booster(oracle, models_s2, contexts):
+    """Philox on both sides, stage-2 booster on (its passer / target one-hots become dynamic rows too)."""
+    n = 30000
+    e = Engine(models_s2, device=0, stage2="booster")
+    try:
+        spec = _spec(contexts, "Kansas State", "Iowa State", n)
+        e.set_matchups([spec])
+        got = e.simulate_host(99, want_iters=True, want_players=True)
+        cfg = oracle.make_config(models_s2, spec.sp_a, spec.sp_b, stage2="booster")
+        ref = oracle.simulate(cfg, n, seed=99, usage=oracle.make_usage(spec.usage), n_slots=e.n_slots)
+        assert np.array_equal(got["scores"], ref["scores"])
+        assert np.array_equal(got["iters"], ref["iters"])
+        _box_equal_philox(got["players"], ref["players"])
+        for k in ("plays", "pass", "comp", "inc", "int", "sack", "run", "td"):
+            assert got["counters"][k] == ref["counters"][k], k
+    finally:
+        e.close()
+
+
+def test_trivial_usage_is_the_shipped_configuration(engine, contexts):
+    n = 8192
+    (ta, _), (tb, _) = contexts["UTSA"], contexts["Ohio State"]
+    engine.set_matchups([MatchupSpec("UTSA", "Ohio State", ta.sp, tb.sp, n, 0, n, 0)])
+    plain = engine.simulate_host(5)
+    engine.set_matchups([_spec(contexts, "UTSA", "Ohio State", n)])
+    assert not engine.ctx.has_usage           # both teams trivial: the production kernel runs
+    again = engine.simulate_host(5)
+    assert np.array_equal(plain["scores"], again["scores"])
+
+
+def test_players_slate_two_matchups(engine, oracle, models_s2, contexts):
+    """Two matchups in one launch, different usage tables, game-id slices as a rank would get them."""
+    specs = [_spec(contexts, "Kansas State", "Iowa State", 3000, g0=1000, out_offset=0),
+             _spec(contexts, "Iowa State", "UTSA", 2000, g0=0, out_offset=3000)]
+    engine.set_matchups(specs)
+    got = engine.simulate_host(7, want_players=True)
+    for mi, s in enumerate(specs):
+        cfg = oracle.make_config(models_s2, s.sp_a, s.sp_b)
+        ref = oracle.simulate(cfg, s.games, game0=s.game_begin, matchup=mi, seed=7,
+                              usage=oracle.make_usage(s.usage), n_slots=engine.n_slots)
+        sl = slice(s.out_offset, s.out_offset + s.games)
+        assert np.array_equal(got["scores"][sl], ref["scores"])
+        _box_equal_philox(got["players"][sl], ref["players"])
