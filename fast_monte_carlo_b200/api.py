@@ -12,8 +12,14 @@ error behaviour (ValueError for an unknown team / schema).  `n` counts PAIRS of 
 then B receives); `processes` and `show_progress` are accepted and ignored (the GPU replaces the
 process pool).  Differences, all documented in DESIGN.md: a given `seed` makes the run
 reproducible game by game (counter-based Philox keyed by (seed, game id)) instead of re-seeding
-NumPy before every game; per-player box scores are not simulated
-(SURVEY 8f row 1), so `players_df` is an empty table with the reference's PLAYER_COLS.
+NumPy before every game.
+
+Players: when a team has usage data -- the focus sheet `2025_week1_players.csv`
+(FMC:508-605) or `usage_*_share.csv` (FMC:487-505), looked up in the working directory exactly like
+the reference, or passed with `focus_csv=` / `usage_dir=` -- passer, target and rusher are sampled
+per play on the GPU, feed the models' one-hot columns, and the focus names get per-game box lines:
+`players_df` has the reference's PLAYER_COLS rows (`flatten_player_box_rows`, FMC:1266-1299).  Without
+usage data every name is "Unknown" and `players_df` is empty, as in the shipped reference.
 """
 from __future__ import annotations
 
@@ -25,6 +31,7 @@ import numpy as np
 import pandas as pd
 
 from . import outputs
+from . import usage as _usage
 from .engine import Engine, MatchupSpec
 from .priors import (TeamContext, build_team_context_from_sp_flex, csv_base_from, load_sp_flex,
                      lookup_sp_flex, packaged_priors_path)
@@ -63,19 +70,26 @@ def simulate_matchup(teamA: TeamContext, teamB: TeamContext, n: int = 100, seed:
                      *, engine: Optional[Engine] = None) -> Tuple[pd.DataFrame, Optional[pd.DataFrame]]:
     eng = engine if engine is not None else get_engine()
     games = 2 * int(n)
+    box = None
+    use = (_usage.resolve_team(teamA, eng.models), _usage.resolve_team(teamB, eng.models))
     if games <= 0:
         sims_df = pd.DataFrame(columns=["team", "opp", "pts", "opp_pts"])
     else:
-        eng.set_matchups([MatchupSpec(teamA.name, teamB.name, teamA.sp, teamB.sp, games, 0, games, 0)])
-        res = eng.simulate_host(_fresh_seed() if seed is None else int(seed), want_scores=True, want_hist=True)
+        # the sampled names feed the models whether or not the box is collected (FMC:1058-1081, 1203-1216)
+        eng.set_matchups([MatchupSpec(teamA.name, teamB.name, teamA.sp, teamB.sp, games, 0, games, 0, usage=use)])
+        want_box = bool(collect_players) and eng.n_slots > 0
+        res = eng.simulate_host(_fresh_seed() if seed is None else int(seed), want_scores=True, want_hist=True,
+                                want_players=want_box)
+        box = res.get("players")
         sims_df = outputs.sims_frame(teamA.name, teamB.name, res["scores"])
         sims_df.attrs["counters"] = dict(res["counters"])
         LAST_RUN.clear()
         LAST_RUN.update(hist=res["hist"][0], counters=dict(res["counters"]), teams=(teamA.name, teamB.name),
-                        scores=res["scores"])
+                        scores=res["scores"], player_box=box, usage=use)
     players_df = None
     if collect_players:
-        players_df = pd.DataFrame(columns=PLAYER_COLS)
+        players_df = (_usage.player_rows(box, 0, (teamA.name, teamB.name), use) if box is not None
+                      else pd.DataFrame(columns=PLAYER_COLS))
         if players_csv:
             if players_csv.lower().endswith(".parquet"):
                 players_df.to_parquet(players_csv, index=False)
@@ -88,10 +102,13 @@ def simulate_upcoming_matchup(teamA: str, teamB: str, *, year: int = 2025, week:
                               sp_path: str = "Pregame_SPPlus2025_1.csv", n: int = 1000,
                               show_progress: bool = True, collect_players: bool = True,
                               save_csv: Optional[str] = None, processes: Optional[int] = None,
-                              seed: Optional[int] = None, engine: Optional[Engine] = None):
+                              seed: Optional[int] = None, engine: Optional[Engine] = None,
+                              focus_csv: Optional[str] = None, usage_dir: str = "."):
     sp_df = load_sp_flex(sp_path)
-    A = build_team_context_from_sp_flex(teamA, year, week, sp_df)
-    B = build_team_context_from_sp_flex(teamB, year, week, sp_df)
+    # FMC:605 builds the focus tables at import from `2025_week1_players.csv` in the working directory
+    focus = _usage.build_focus_usage_tables(focus_csv if focus_csv is not None else _usage.FOCUS_PLAYERS_CSV)
+    A = build_team_context_from_sp_flex(teamA, year, week, sp_df, focus=focus, usage_dir=usage_dir)
+    B = build_team_context_from_sp_flex(teamB, year, week, sp_df, focus=focus, usage_dir=usage_dir)
 
     t0 = time.perf_counter()
     sims_df, players_df = simulate_matchup(A, B, n=n, seed=seed, show_progress=show_progress,

@@ -241,3 +241,51 @@ def player_rows(box: np.ndarray, game0: int, team_names: Sequence[str], usage: S
     out = pd.concat(frames, ignore_index=True)
     out = out.sort_values(["sim", "_team_order", "_slot"], kind="stable").drop(columns=["_team_order", "_slot"])
     return out[PLAYER_COLS].reset_index(drop=True)
+
+
+_STAT_FIELD = {  # players_* column -> (role, box field); PLAYER_COLS FMC:1259-1264
+    "pass_att": ("pass", 1), "pass_comp": ("pass", 2), "pass_yds": ("pass", 0), "pass_td": ("pass", 3),
+    "INT": ("pass", 4), "sacks": ("pass", 5),
+    "rush_att": ("rush", 1), "rush_yds": ("rush", 0), "rush_td": ("rush", 3),
+    "tgt": ("rec", 1), "rec": ("rec", 2), "rec_yds": ("rec", 0), "rec_td": ("rec", 3),
+}
+_STAT_ALIASES = {"pass_yards": "pass_yds", "rush_yards": "rush_yds", "rec_yards": "rec_yds"}   # edge_finder.py:12-17
+
+
+def player_prop_odds_from_box(box: np.ndarray, team_names: Sequence[str], usage: Sequence[TeamUsage],
+                              team: str, player: str, stat: str, line: float) -> Dict[str, object]:
+    """`edge_finder.player_prop_odds` (edge_finder.py:168-231) straight from the per-game box, without
+    materialising `players_*`: over/under/push rates of one player's stat against `line`, fair American
+    odds, mean / median / p75 / p90 and the better side at -110.  Like the players table, only games in
+    which the name was sampled at least once count as samples."""
+    from .outputs import prob_to_american
+    col = _STAT_ALIASES.get(stat, stat)
+    if col not in _STAT_FIELD:
+        raise ValueError(f"Stat '{stat}' (mapped to '{col}') not present in the player box.")
+    role, fld = _STAT_FIELD[col]
+    t = [i for i, nm in enumerate(team_names) if nm.lower() == team.lower()]
+    hit = [s for s, (r, nm) in enumerate(usage[t[0]].slots) if r == role and nm.lower() == player.lower()] if t else []
+    if not hit:
+        raise ValueError(f"No rows found for {player} on {team}.")
+    rec = box[:, t[0], hit[0], :]
+    seen = (rec[:, 1] > 0) | (rec[:, 5] > 0)
+    vals = rec[seen, fld]
+    if fld == 0:
+        vals = py_round1(vals)
+    if vals.size == 0:
+        raise ValueError(f"No rows found for {player} on {team}.")
+    p_over = float(np.mean(vals > line))
+    p_under = float(np.mean(vals < line))
+    p_push = float(np.mean(np.isclose(vals, line, atol=1e-9)))
+    ev = lambda p: p * (100.0 * (100.0 / 110.0)) - (1.0 - p) * 100.0      # EV per $100 at -110
+    implied = 110.0 / 210.0
+    side, best_ev, edge = (("Over", ev(p_over), p_over - implied) if ev(p_over) >= ev(1.0 - p_over)
+                           else ("Under", ev(1.0 - p_over), (1.0 - p_over) - implied))
+    return {
+        "team": team, "player": player, "role": ROLE_LABEL[role], "stat": col, "line": float(line),
+        "samples": int(vals.size), "p_over": round(p_over, 4), "p_under": round(p_under, 4),
+        "push_rate": round(p_push, 4), "american_over": prob_to_american(p_over),
+        "american_under": prob_to_american(p_under), "mean": float(np.mean(vals)), "median": float(np.median(vals)),
+        "p75": float(np.percentile(vals, 75)), "p90": float(np.percentile(vals, 90)),
+        "best_side": side, "edge": round(edge * 100, 2), "ev_per_$100": round(best_ev, 2),
+    }

@@ -95,3 +95,38 @@ def test_bench_json_line_contract(tmp_path):
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] > 0 and "sample" in cb
     assert set(("sm_mhz", "sm_max_mhz", "reasons")) <= set(d["clocks"])
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_simulate_upcoming_matchup_players(engine, oracle, models_s2, tmp_path, monkeypatch):
+    """collect_players=True with a focus sheet: players_df / players_<base>.csv carry the reference's rows, and
+    they equal the oracle's on the same Philox seed."""
+    from conftest import GOLDEN
+    from fast_monte_carlo_b200 import usage
+    monkeypatch.chdir(tmp_path)
+    base = api.csv_base_from("Kansas State", "Iowa State", 1)
+    sheet = os.path.join(GOLDEN, "players_focus.csv")
+    sims_df, players_df, summary, A, B, meta = api.simulate_upcoming_matchup(
+        "Kansas State", "Iowa State", sp_path=priors.packaged_priors_path(), n=400, show_progress=False,
+        collect_players=True, save_csv=base, seed=21, engine=engine, focus_csv=sheet)
+    assert list(players_df.columns) == api.PLAYER_COLS and len(sims_df) == 800
+    assert set(players_df["role"]) == {"QB", "Rusher", "Receiver"} and "__Other__" not in set(players_df["player"])
+    assert set(players_df["start"]) == {"A", "B"} and players_df["sim"].max() <= 799
+    us = (usage.resolve_team(A, models_s2), usage.resolve_team(B, models_s2))
+    ref = oracle.simulate(oracle.make_config(models_s2, A.sp, B.sp), 800, seed=21, usage=oracle.make_usage(us),
+                          n_slots=max(len(u.slots) for u in us))
+    want = usage.player_rows(ref["players"], 0, ("Kansas State", "Iowa State"), us)
+    assert len(want) == len(players_df)
+    for c in api.PLAYER_COLS:
+        if c.endswith("_yds"):
+            assert np.allclose(players_df[c].to_numpy(float), want[c].to_numpy(float), atol=1e-6), c
+        else:
+            assert players_df[c].tolist() == want[c].tolist(), c
+    on_disk = pd.read_csv(tmp_path / f"players_{base}")
+    assert len(on_disk) == len(players_df) and list(on_disk.columns) == api.PLAYER_COLS
+    odds = usage.player_prop_odds_from_box(api.LAST_RUN["player_box"], ("Kansas State", "Iowa State"), us,
+                                           "Kansas State", "Taylen Green", "pass_yards", 150.5)
+    assert odds["samples"] > 700 and 0.0 < odds["p_over"] < 1.0
+    # without the sheet the same call is the shipped configuration: nobody is tracked
+    _, empty, *_ = api.simulate_upcoming_matchup("Kansas State", "Iowa State", sp_path=priors.packaged_priors_path(),
+                                                 n=50, show_progress=False, seed=21, engine=engine)
+    assert len(empty) == 0 and list(empty.columns) == api.PLAYER_COLS

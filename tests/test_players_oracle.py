@@ -107,3 +107,51 @@ def test_oracle_trivial_usage_equals_plain_run(models, oracle):
     a = oracle.simulate(cfg, 64, seed=5)
     b = oracle.simulate(cfg, 64, seed=5, usage=oracle.make_usage(us), n_slots=0)
     assert np.array_equal(a["scores"], b["scores"]) and np.array_equal(a["iters"], b["iters"])
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/edge_finder.py"), reason="reference not mounted")
+def test_unmodified_edge_finder_reads_our_players_file(models, oracle, contexts, tmp_path, monkeypatch):
+    """`players_<base>.csv` written from the per-game box is what edge_finder.player_prop_odds /
+    scan_props_for_matchup expect (edge_finder.py:131-231, 340-390), and the box adapter returns the same odds."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("edge_finder_ref", "/root/reference/edge_finder.py")
+    ef = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ef)
+    monkeypatch.chdir(tmp_path)                      # edge_finder drops a scratch `testings.csv` into the cwd
+    ta, tb = contexts["Kansas State"], contexts["Iowa State"]
+    us = [usage.resolve_team(ta, models), usage.resolve_team(tb, models)]
+    n = 600
+    r = oracle.simulate(oracle.make_config(models, ta.sp, tb.sp), n, seed=3, usage=oracle.make_usage(us),
+                        n_slots=max(len(u.slots) for u in us))
+    names = ("Kansas State", "Iowa State")
+    df = usage.player_rows(r["players"], 0, names, us)
+    assert list(df.columns) == gold_cols() and len(df) > 5 * n
+    base = priors.csv_base_from("Kansas State", "Iowa State", 1)
+    stem = base[:-4]
+    from fast_monte_carlo_b200 import outputs
+    outputs.sims_frame(*names, r["scores"]).to_csv(tmp_path / f"scores_{base}", index=False)
+    df.to_csv(tmp_path / f"players_{base}", index=False)
+    for team, player, stat, line in (("Kansas State", "Taylen Green", "pass_yards", 180.5),
+                                     ("Kansas State", "Blake Watson", "rush_yards", 35.5),
+                                     ("Iowa State", "Carson Hansen", "rec_yards", 40.5),
+                                     ("Iowa State", "Levi Williams", "pass_td", 1.5),
+                                     ("kansas state", "benjamin brahmer", "rec", 3.0)):
+        want = ef.player_prop_odds(stem, team, player, stat, line, directory=str(tmp_path))
+        got = usage.player_prop_odds_from_box(r["players"], names, us, team, player, stat, line)
+        assert set(want) == set(got)
+        for k, v in want.items():
+            if isinstance(v, float):
+                assert abs(got[k] - v) < 1e-9, (player, k, got[k], v)
+            else:
+                assert got[k] == v, (player, k)
+    sheet = os.path.join(GOLDEN, "players_focus.csv")
+    props = ef.scan_props_for_matchup(stem, "Kansas State", "Iowa State", prop_sheet_path=sheet, directory=str(tmp_path),
+                                      min_abs_edge_pct=0.0)
+    assert len(props) >= 10 and {"Taylen Green", "Bo Nix"} <= set(props["player"])
+    with pytest.raises(ValueError):
+        usage.player_prop_odds_from_box(r["players"], names, us, "Kansas State", "Nobody Here", "rush_yards", 10.5)
+
+
+def gold_cols():
+    from fast_monte_carlo_b200.api import PLAYER_COLS
+    return PLAYER_COLS
