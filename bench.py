@@ -51,6 +51,9 @@ def parse():
                          "season = configs[4]: 12 weekly slates of 60 matchups from seeded shuffles of the 136 teams")
     ap.add_argument("--slate-games", type=int, default=1_000_000, help="games per matchup of the slate workload")
     ap.add_argument("--stage2", default="synthetic", choices=["synthetic", "standin"])
+    ap.add_argument("--players", action="store_true",
+                    help="matchup workload in player mode: usage tables from the synthetic focus sheet "
+                         "(fast_monte_carlo_b200/data/players_focus_synthetic.csv), per-game player box written")
     ap.add_argument("--cpu-games", type=int, default=0, help="games of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -116,7 +119,9 @@ def workload(args, n_gpus):
         "play_call": "pass_prob_v1 heuristic (reference behaviour when play_model.json is absent)",
         "stage2": ("synthetic booster of the trained shape (1086 trees, depth<=7)" if args.stage2 == "synthetic"
                    else "fixed stand-in probabilities"),
-        "players": "Unknown (no usage tables shipped)",
+        "players": ("synthetic focus sheet: 3 passers / 4 rushers / 4 targets per team sampled per play, one-hot "
+                    "columns fed from the sampled names, 8 box lines per team per game written"
+                    if getattr(args, "players", False) else "Unknown (no usage tables shipped)"),
         "parallelism": f"games sharded over {n_gpus} GPU(s); one NCCL all-reduce of the histograms per step",
         "l2": "flushed between timed steps (256 MiB write); node tables are meant to be cache-resident",
     }
@@ -227,13 +232,29 @@ def load_models(stage2: str):
     return ms
 
 
-def cpu_run(ms, games: int, stage2: str, game0: int = 0):
+def synthetic_usage(ms):
+    """Usage tables of the --players workload (both teams of the matchup)."""
+    from fast_monte_carlo_b200 import priors, usage
+    sheet = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fast_monte_carlo_b200", "data",
+                         "players_focus_synthetic.csv")
+    focus = usage.build_focus_usage_tables(sheet)
+    sp_df = priors.load_sp_flex(priors.packaged_priors_path())
+    return tuple(usage.resolve_team(priors.build_team_context_from_sp_flex(t, 2025, 1, sp_df, focus=focus,
+                                                                           usage_dir=os.path.dirname(sheet)), ms)
+                 for t in (KSU[0], ISU[0]))
+
+
+def cpu_run(ms, games: int, stage2: str, game0: int = 0, players: bool = False):
     from oracle import c_oracle as co
     co.load_models(ms)
     cfg = co.make_config(ms, KSU[1], ISU[1], stage2="booster" if stage2 == "synthetic" else "standin")
     threads = co.lib().fo_max_threads()
+    kw = {}
+    if players:
+        use = synthetic_usage(ms)
+        kw = dict(usage=co.make_usage(use), n_slots=max(len(u.slots) for u in use))
     t = time.perf_counter()
-    r = co.simulate(cfg, games, game0=game0, seed=SEED, threads=threads)
+    r = co.simulate(cfg, games, game0=game0, seed=SEED, threads=threads, **kw)
     dt = time.perf_counter() - t
     return r, dt, threads
 
@@ -241,9 +262,9 @@ def cpu_run(ms, games: int, stage2: str, game0: int = 0):
 def cpu_baseline(ms, args):
     games = args.cpu_games
     if games <= 0:
-        _, dt, _ = cpu_run(ms, 2000, args.stage2)
+        _, dt, _ = cpu_run(ms, 2000, args.stage2, players=args.players)
         games = int(max(4000, min(400_000, 15.0 / (dt / 2000))))     # ~15 s of CPU work
-    r, dt, threads = cpu_run(ms, games, args.stage2)
+    r, dt, threads = cpu_run(ms, games, args.stage2, players=args.players)
     return {"value": r["counters"]["plays"] / dt, "unit": UNIT, "games_per_sec": games / dt, "cores": threads,
             "host_cpus": os.cpu_count(), "kind": "port",
             "sample": f"{games} games of the same matchup/seed through oracle/fmc_oracle.c (OpenMP, {threads} threads), {dt:.1f} s"}
@@ -257,14 +278,14 @@ def run_reference(args):
     if args.cpu_games > 0:
         per_step = args.cpu_games
     else:
-        _, dt0, threads = cpu_run(ms, 2000, args.stage2)
+        _, dt0, threads = cpu_run(ms, 2000, args.stage2, players=args.players)
         per_step = int(max(4000, min(400_000, 20.0 / (dt0 / 2000))))       # ~20 s per step
     for w in range(args.warmup):
-        cpu_run(ms, max(2000, per_step // 10), args.stage2)
+        cpu_run(ms, max(2000, per_step // 10), args.stage2, players=args.players)
     plays = 0
     t_tot = 0.0
     for s in range(args.steps):
-        r, dt, threads = cpu_run(ms, per_step, args.stage2, game0=s * per_step)
+        r, dt, threads = cpu_run(ms, per_step, args.stage2, game0=s * per_step, players=args.players)
         plays += r["counters"]["plays"]
         t_tot += dt
     value = plays / t_tot
@@ -314,7 +335,8 @@ def run_ours(args):
     else:
         G = args.games
         g0, g1 = rank * G, (rank + 1) * G
-        spec = [MatchupSpec(KSU[0], ISU[0], KSU[1], ISU[1], G * world, g0, g1, 0)]
+        use = synthetic_usage(ms) if args.players else None
+        spec = [MatchupSpec(KSU[0], ISU[0], KSU[1], ISU[1], G * world, g0, g1, 0, usage=use)]
         total_games = G * world
     n_m = len(spec)
     eng.set_matchups(spec)
@@ -327,12 +349,17 @@ def run_ours(args):
     counters = torch.zeros(native.N_COUNTERS, dtype=torch.int64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    box = None
+    if args.workload == "matchup" and args.players and eng.n_slots:
+        box = torch.zeros((G, 2, eng.n_slots, 2), dtype=torch.int64, device=dev)      # fmc_player_rec = 16 bytes
 
     def step():
         hist.zero_()
         counters.zero_()
+        if box is not None:
+            box.zero_()
         eng.ctx.simulate_device(seed=SEED, scores=scores.data_ptr(), hist=hist.data_ptr(), counters=counters.data_ptr(),
-                                cuda_stream=stream.cuda_stream)
+                                cuda_stream=stream.cuda_stream, players=box.data_ptr() if box is not None else 0)
         if world > 1:
             hist64.copy_(hist)
             dist.all_reduce(hist64)
@@ -389,7 +416,7 @@ def run_ours(args):
             dist.barrier()
         t0 = time.perf_counter()
         eng.set_matchups(spec)                                   # forces re-specialisation + H2D of the tables
-        r = eng.simulate_host(SEED, want_scores=True, want_hist=True)
+        r = eng.simulate_host(SEED, want_scores=True, want_hist=True, want_players=box is not None)
         h = torch.from_numpy(r["hist"].astype(np.int64))
         if world > 1:
             hd = h.to(dev)
@@ -407,7 +434,7 @@ def run_ours(args):
         e2e_plays += int(pp[0])
         e2e_steps_s.append(float(tt[0]))
         h2d = table_bytes + 200 + 8
-        d2h = G * 4 + int(np.prod(r["hist"].shape)) * 4 + native.N_COUNTERS * 8
+        d2h = G * 4 + int(np.prod(r["hist"].shape)) * 4 + native.N_COUNTERS * 8 + (box.numel() * 8 if box is not None else 0)
     e2e_value = e2e_plays / e2e_t if e2e_t > 0 else None
     e2e_clocks = sampler2.stop()
 

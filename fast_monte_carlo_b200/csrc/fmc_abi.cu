@@ -184,6 +184,8 @@ struct fmc_ctx {
     fmc_params params;
     std::vector<fmc_matchup> matchups;
     std::vector<fmc_team_usage> usage;   // [n_matchups][2] or empty (shipped configuration: every name "Unknown")
+    struct NameRows { int8_t row[3][FMC_MAX_USAGE]; };
+    std::vector<NameRows> name_rows;     // per team: the 0/1 feature row of every usage entry (-1: no model knows the name)
     int n_slots = 0;
     bool tables_dirty = true;
     // device-side state of the last set_matchups
@@ -307,6 +309,7 @@ extern "C" int fmc_set_matchups(fmc_ctx *c, int32_t n, const fmc_matchup *m) {
         if (m[i].game_end < m[i].game_begin) return fail(FMC_ERR_INVALID, "fmc_set_matchups: game_end < game_begin");
     c->matchups.assign(m, m + n);
     c->usage.clear();          // usage belongs to a matchup list: set it again after fmc_set_matchups
+    c->name_rows.clear();
     c->n_slots = 0;
     c->tables_dirty = true;
     return FMC_OK;
@@ -314,23 +317,34 @@ extern "C" int fmc_set_matchups(fmc_ctx *c, int32_t n, const fmc_matchup *m) {
 
 extern "C" int fmc_set_usage(fmc_ctx *c, int32_t n, const fmc_team_usage *teams, int32_t n_slots) {
     if (!c) return fail(FMC_ERR_INVALID, "fmc_set_usage: ctx is NULL");
-    if (!teams) { c->usage.clear(); c->n_slots = 0; c->tables_dirty = true; return FMC_OK; }
+    if (!teams) { c->usage.clear(); c->name_rows.clear(); c->n_slots = 0; c->tables_dirty = true; return FMC_OK; }
     if (n != (int)c->matchups.size()) return fail(FMC_ERR_INVALID, "fmc_set_usage: n_matchups differs from the last fmc_set_matchups");
     if (n_slots < 0 || n_slots > 3 * FMC_MAX_USAGE) return fail(FMC_ERR_INVALID, "fmc_set_usage: bad n_slots");
+    std::vector<fmc_ctx::NameRows> rows(2 * (size_t)n);
     for (int i = 0; i < 2 * n; ++i)
         for (int r = 0; r < 3; ++r) {
             const fmc_usage &u = teams[i].role[r];
-            const int cap = r == 0 ? FMC_MAX_PASSERS : FMC_MAX_USAGE;
-            if (u.n < 1 || u.n > cap) return fail(FMC_ERR_CAPACITY, "fmc_set_usage: a usage table must have 1.." + std::to_string(cap) + " entries");
+            if (u.n < 1 || u.n > FMC_MAX_USAGE) return fail(FMC_ERR_CAPACITY, "fmc_set_usage: a usage table must have 1.." + std::to_string(FMC_MAX_USAGE) + " entries");
             double tot = 0.0;
+            int next_row = 0;
+            const int cap = r == 0 ? FMC_MAX_PASSER_ROWS : FMC_MAX_NAME_ROWS;
+            for (int e = 0; e < FMC_MAX_USAGE; ++e) rows[i].row[r][e] = -1;
             for (int e = 0; e < u.n; ++e) {
                 if (!(u.share[e] >= 0.0) || !std::isfinite(u.share[e])) return fail(FMC_ERR_INVALID, "fmc_set_usage: shares must be finite and >= 0");
                 if (u.slot[e] >= n_slots) return fail(FMC_ERR_INVALID, "fmc_set_usage: slot out of range");
                 tot += u.share[e];
+                bool known = false;      // some model has a one-hot column for this name
+                for (int m = 0; m < FMC_N_MODELS; ++m) known = known || u.col[m][e] >= 0;
+                if (known) {
+                    if (next_row >= cap)
+                        return fail(FMC_ERR_CAPACITY, "fmc_set_usage: more than " + std::to_string(cap) + " names of one role that the models have columns for");
+                    rows[i].row[r][e] = (int8_t)next_row++;
+                }
             }
             if (!(tot > 0.0)) return fail(FMC_ERR_INVALID, "fmc_set_usage: shares sum to zero");
         }
     c->usage.assign(teams, teams + 2 * (size_t)n);
+    c->name_rows.swap(rows);
     c->n_slots = n_slots;
     c->tables_dirty = true;
     return FMC_OK;
@@ -338,14 +352,15 @@ extern "C" int fmc_set_usage(fmc_ctx *c, int32_t n, const fmc_team_usage *teams,
 
 // Dynamic one-hot columns of (family, team on offense): the sampled names of a play are feature rows
 // (fmc_sim.cuh kDynRow0...), every other name column folds to 0.
-static void dyn_columns(const fmc_team_usage &tu, int fam, PackSpec &s) {
+static void dyn_columns(const fmc_team_usage &tu, const fmc_ctx::NameRows &nr, int fam, PackSpec &s) {
     s.n_dyn = 0;
-    auto add = [&](const fmc_usage &u, int row0) {
+    auto add = [&](int role, int row0) {
+        const fmc_usage &u = tu.role[role];
         for (int e = 0; e < u.n; ++e)
-            if (u.col[fam][e] >= 0) { s.dyn_col[s.n_dyn] = u.col[fam][e]; s.dyn_row[s.n_dyn] = (int8_t)(row0 + e); s.n_dyn++; }
+            if (u.col[fam][e] >= 0) { s.dyn_col[s.n_dyn] = u.col[fam][e]; s.dyn_row[s.n_dyn] = (int8_t)(row0 + nr.row[role][e]); s.n_dyn++; }
     };
-    if (fam == FMC_RUN_YARDS) add(tu.role[1], kDynRow0);
-    else if (fam != FMC_PLAY_MODEL) { add(tu.role[0], kDynRow0); add(tu.role[2], kDynRow0 + FMC_MAX_PASSERS); }
+    if (fam == FMC_RUN_YARDS) add(1, kDynRow0);
+    else if (fam != FMC_PLAY_MODEL) { add(0, kDynRow0); add(2, kDynRow0 + FMC_MAX_PASSER_ROWS); }
 }
 
 static bool family_needed(const fmc_ctx *c, int fam) {
@@ -384,7 +399,7 @@ static int build_tables(fmc_ctx *c) {
         s.active[0] = f.active[0]; s.active[1] = f.active[1];
         if (!c->usage.empty()) {      // player mode: every name comes from the usage tables
             s.active[0] = -1; s.active[1] = -1;
-            dyn_columns(c->usage[(size_t)j.matchup * 2 + off], fam, s);
+            dyn_columns(c->usage[(size_t)j.matchup * 2 + off], c->name_rows[(size_t)j.matchup * 2 + off], fam, s);
         }
         if (fam == FMC_PLAY_MODEL) { s.active[0] = mu.coach_col[off]; s.active[1] = -1; }
         s.fold_value[6] = 3.0; s.fold_value[7] = 3.0;    // timeouts are never spent (FMC:911-912)
@@ -430,7 +445,10 @@ static int build_tables(fmc_ctx *c) {
                     double acc = 0.0;
                     for (int e = 0; e < u.n; ++e) { acc += u.share[e]; U.cdf[r][e] = acc; }   // np.cumsum
                     for (int e = 0; e < u.n; ++e) U.cdf[r][e] /= acc;                          // cdf /= cdf[-1]
-                    for (int e = 0; e < FMC_MAX_USAGE; ++e) U.slot[r][e] = (int8_t)(e < u.n ? u.slot[e] : -1);
+                    for (int e = 0; e < FMC_MAX_USAGE; ++e) {
+                        U.slot[r][e] = (int8_t)(e < u.n ? u.slot[e] : -1);
+                        U.row[r][e] = c->name_rows[(size_t)i * 2 + off].row[r][e];
+                    }
                 }
             }
         }

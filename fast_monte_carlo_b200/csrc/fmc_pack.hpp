@@ -80,8 +80,8 @@ struct PackSpec {
     // player mode: one-hot columns whose 0/1 value is a per-request feature row (the sampled passer /
     // target / rusher of the play) instead of a pack-time constant
     int n_dyn = 0;
-    int32_t dyn_col[2 * FMC_MAX_USAGE + FMC_MAX_PASSERS];
-    int8_t dyn_row[2 * FMC_MAX_USAGE + FMC_MAX_PASSERS];
+    int32_t dyn_col[FMC_MAX_PASSER_ROWS + FMC_MAX_NAME_ROWS];
+    int8_t dyn_row[FMC_MAX_PASSER_ROWS + FMC_MAX_NAME_ROWS];
     int dyn_row_of(int col) const {
         for (int i = 0; i < n_dyn; ++i)
             if (dyn_col[i] == col) return dyn_row[i];

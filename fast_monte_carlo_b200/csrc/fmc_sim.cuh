@@ -53,6 +53,7 @@ struct UsageDev {
     double cdf[3][FMC_MAX_USAGE];    // cumsum(share) / total, the array Generator.choice searches (FMC:625-635)
     int8_t n[3];
     int8_t slot[3][FMC_MAX_USAGE];   // box line of a tracked name, -1 = not tracked
+    int8_t row[3][FMC_MAX_USAGE];    // 0/1 feature row of a name some model has a column for, -1 = lights nothing
 };
 
 struct MatchupDev {
@@ -63,10 +64,11 @@ struct MatchupDev {
 };
 
 // Player mode: the sampled names of a play are 0/1 feature rows behind the numeric rows of a request:
-// pass families: passer entry e -> row kDynRow0 + e, target entry e -> row kDynRow0 + FMC_MAX_PASSERS + e;
-// run yards: rusher entry e -> row kDynRow0 + e.
+// pass families: passer with name row r -> feature row kDynRow0 + r, target -> kDynRow0 + FMC_MAX_PASSER_ROWS + r;
+// run yards: rusher -> kDynRow0 + r.  Only names that some model has a one-hot column for get a name row
+// (UsageDev::row); every other name lights nothing (OneHotEncoder(handle_unknown='ignore')).
 constexpr int kDynRow0 = kSimRows;
-constexpr int kDynRows = FMC_MAX_PASSERS + FMC_MAX_USAGE;
+constexpr int kDynRows = FMC_MAX_PASSER_ROWS + FMC_MAX_NAME_ROWS;
 
 struct SimKernelArgs {
     const MatchupDev *matchups;
@@ -125,7 +127,7 @@ struct PackedLane {
     unsigned long long game;
     double dist, ytg;
     uint32_t a;     // sec:12 | down:10 | period:3 | offense:1 | going:1 | stage:4
-    uint32_t b;     // iter:10 | plays:10 | p1:4 | wr:4 (player mode)
+    uint32_t b;     // iter:10 | plays:10 | p1:5 | wr:5 (player mode)
     uint32_t c;     // score[0]:16 | score[1]:16
 };
 __device__ __forceinline__ PackedLane pack_lane(const Lane &L) {
@@ -133,7 +135,7 @@ __device__ __forceinline__ PackedLane pack_lane(const Lane &L) {
     P.game = L.game; P.dist = L.dist; P.ytg = L.ytg;
     P.a = (uint32_t)L.sec | ((uint32_t)L.down << 12) | ((uint32_t)L.period << 22) | ((uint32_t)L.offense << 25) |
           ((uint32_t)L.going << 26) | ((uint32_t)L.stage << 27);
-    P.b = (uint32_t)L.iter | ((uint32_t)L.plays << 10) | ((uint32_t)L.p1 << 20) | ((uint32_t)L.wr << 24);
+    P.b = (uint32_t)L.iter | ((uint32_t)L.plays << 10) | ((uint32_t)L.p1 << 20) | ((uint32_t)L.wr << 25);
     P.c = (uint32_t)L.score[0] | ((uint32_t)L.score[1] << 16);
     return P;
 }
@@ -143,7 +145,7 @@ __device__ __forceinline__ Lane unpack_lane(const PackedLane &P) {
     L.sec = (int)(P.a & 0xFFFu); L.down = (int)((P.a >> 12) & 0x3FFu); L.period = (int)((P.a >> 22) & 7u);
     L.offense = (int)((P.a >> 25) & 1u); L.going = (int)((P.a >> 26) & 1u); L.stage = (int)(P.a >> 27);
     L.iter = (int)(P.b & 0x3FFu); L.plays = (int)((P.b >> 10) & 0x3FFu);
-    L.p1 = (int)((P.b >> 20) & 0xFu); L.wr = (int)((P.b >> 24) & 0xFu);
+    L.p1 = (int)((P.b >> 20) & 0x1Fu); L.wr = (int)((P.b >> 25) & 0x1Fu);
     L.score[0] = (int)(P.c & 0xFFFFu); L.score[1] = (int)(P.c >> 16);
     return L;
 }
@@ -333,10 +335,10 @@ __device__ __forceinline__ int stage2_outcome(const double raw[3], double u2) {
 // ---- player mode ---------------------------------------------------------------------------------
 // Generator.choice(n, p=share): searchsorted(cdf, u, side='right') (FMC:625-635)
 __device__ __forceinline__ int sample_usage(const UsageDev &U, int role, double u) {
+    const int n = U.n[role];
     int idx = 0;
-#pragma unroll
-    for (int i = 0; i < FMC_MAX_USAGE; ++i) idx += (i < U.n[role] && U.cdf[role][i] <= u) ? 1 : 0;
-    return idx < U.n[role] ? idx : U.n[role] - 1;
+    for (int i = 0; i < n; ++i) idx += (U.cdf[role][i] <= u) ? 1 : 0;
+    return idx < n ? idx : n - 1;
 }
 // pstats[team][role][name] of a tracked name (FMC:1073-1075, 1108-1148, 1163-1192, 1207-1249): the lane owns its
 // game's box lines, so a plain read-modify-write.  counts: 10-bit fields att|tgt, comp|rec, td, INT, sacks.
@@ -603,18 +605,21 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
 // 1 distance 2 yardsToGoal 3 is_red_zone 4 score_diff 5 seconds 6 goal_to_go 7 fourth_and_short
 // 8 fg_range 9 half 10 two_minute 11..13 "B" views of 1, 2, 4; row 14 (-inf) is set once per chunk.
 template <bool PLAYERS>
-__device__ __forceinline__ void write_features(float *col, const Lane &L, int fam, const SimKernelArgs &a) {
+__device__ __forceinline__ void write_features(float *col, const Lane &L, int fam, const SimKernelArgs &a, const MatchupDev &M) {
     const int team = L.offense;
     if (PLAYERS && fam != 5) {
-        // passer_name / target_name / rusher_name of the row (FMC:1079-1081, 1216) as 0/1 rows per usage entry
+        // passer_name / target_name / rusher_name of the row (FMC:1079-1081, 1216) as 0/1 name rows
+        const UsageDev &U = M.usage[team];
         if (fam == 3) {
+            const int r1 = U.row[1][L.p1];
 #pragma unroll
-            for (int e = 0; e < FMC_MAX_USAGE; ++e) col[(kDynRow0 + e) * 32] = (e == L.p1) ? 1.f : 0.f;
+            for (int e = 0; e < FMC_MAX_NAME_ROWS; ++e) col[(kDynRow0 + e) * 32] = (e == r1) ? 1.f : 0.f;
         } else {
+            const int r1 = U.row[0][L.p1], r2 = U.row[2][L.wr];
 #pragma unroll
-            for (int e = 0; e < FMC_MAX_PASSERS; ++e) col[(kDynRow0 + e) * 32] = (e == L.p1) ? 1.f : 0.f;
+            for (int e = 0; e < FMC_MAX_PASSER_ROWS; ++e) col[(kDynRow0 + e) * 32] = (e == r1) ? 1.f : 0.f;
 #pragma unroll
-            for (int e = 0; e < FMC_MAX_USAGE; ++e) col[(kDynRow0 + FMC_MAX_PASSERS + e) * 32] = (e == L.wr) ? 1.f : 0.f;
+            for (int e = 0; e < FMC_MAX_NAME_ROWS; ++e) col[(kDynRow0 + FMC_MAX_PASSER_ROWS + e) * 32] = (e == r2) ? 1.f : 0.f;
         }
     }
     const int sd = L.score[team] - L.score[team ^ 1];
@@ -770,7 +775,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
             if (key >= 0) {
                 if (rank < sh.evalc[key]) {
                     pos = (int)(sh.off[key] + rank);
-                    write_features<PLAYERS>(feats + (size_t)(pos >> 5) * kChunkFloats + (pos & 31), L, key >> 1, a);
+                    write_features<PLAYERS>(feats + (size_t)(pos >> 5) * kChunkFloats + (pos & 31), L, key >> 1, a, sh.M);
                 } else {
                     held = key;
                 }

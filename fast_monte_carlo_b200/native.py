@@ -67,8 +67,7 @@ class SimArgs(C.Structure):
     ]
 
 
-MAX_USAGE = 8
-MAX_PASSERS = 4
+MAX_USAGE = 32
 ROLE_INDEX = {"pass": 0, "rush": 1, "rec": 2}
 PLAYER_REC = np.dtype([("yds", "<f8"), ("counts", "<u8")])     # fmc_player_rec
 
@@ -80,6 +79,28 @@ class Usage(C.Structure):
 
 class TeamUsageC(C.Structure):
     _fields_ = [("role", Usage * 3)]
+
+
+class PlayerBox:
+    """The per-game player box as the kernel wrote it (fmc_player_rec[games][2][n_slots]), unpacked on demand:
+    a 10 M-game run holds a gigabyte of records, and a prop question reads one slot of it."""
+
+    def __init__(self, rec: np.ndarray):
+        self.rec = rec
+        self.shape = rec.shape + (6,)
+
+    def slot(self, team: int, slot: int) -> np.ndarray:
+        """float64[games, 6] = yds, att|tgt, comp|rec, td, INT, sacks of one box line."""
+        return unpack_player_box(self.rec[:, team, slot])
+
+    def dense(self) -> np.ndarray:
+        """float64[games, 2, n_slots, 6] (tests; small runs)."""
+        return unpack_player_box(self.rec)
+
+
+def box_slot(box, team: int, slot: int) -> np.ndarray:
+    """[games, 6] of one box line from a PlayerBox or from a dense float64[games, 2, n_slots, 6] array."""
+    return box.slot(team, slot) if isinstance(box, PlayerBox) else np.asarray(box)[:, team, slot, :]
 
 
 def unpack_player_box(rec: np.ndarray) -> np.ndarray:
@@ -377,7 +398,7 @@ class Context:
                                              vp(stream), vp(trace), vp(iters)))
         out = dict(counters={k: int(counters[i]) for i, k in enumerate(COUNTER_NAMES)})
         if players is not None:
-            out["players"] = unpack_player_box(players[:, :, :self.n_slots])
+            out["players"] = PlayerBox(players[:, :, :self.n_slots])
         if scores is not None:
             # score word = points A | points B << 16: on a little-endian host the uint16 view IS the [n, 2] table
             out["scores"] = (scores.view(np.uint16).reshape(n, 2).astype(np.int32) if sys.byteorder == "little" else

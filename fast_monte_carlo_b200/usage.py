@@ -34,8 +34,8 @@ ROLE_NAME_COL = {"pass": "passer_name", "rush": "rusher_name", "rec": "receiver_
 ROLE_LABEL = {"pass": "QB", "rush": "Rusher", "rec": "Receiver"}      # FMC:1275, 1284, 1293
 _FOCUS_STAT = {"pass": "pass_yards", "rush": "rush_yards", "rec": "rec_yards"}
 _FILES = {"pass": "usage_qb_share.csv", "rush": "usage_rush_share.csv", "rec": "usage_target_share.csv"}
-MAX_USAGE = 8        # entries per table the kernels hold (include/fmc.h FMC_MAX_USAGE)
-MAX_PASSERS = 4
+MAX_USAGE = 32       # entries per table the kernels hold (include/fmc.h FMC_MAX_USAGE)
+MAX_NAME_ROWS = {"pass": 4, "rush": 8, "rec": 8}   # names per role that some model has a one-hot column for
 # which name group of which model a role feeds (model name -> group name); FMC:1079-1081, 1216
 _ROLE_GROUP = {"pass": "passer_name", "rush": "rusher_name", "rec": "target_name"}
 _PLAYER_MODELS = ("pass_stage1", "pass_stage2", "pass_yards", "run_yards", "sack_yards")
@@ -151,6 +151,19 @@ class RoleUsage:
     col: Dict[str, List[int]]         # model name -> hot column per entry (-1: not a category)
 
 
+def name_rows(ru: "RoleUsage") -> List[int]:
+    """0/1 feature row of every usage entry, -1 for names no model has a column for (the same numbering
+    fmc_set_usage derives, csrc/fmc_abi.cu)."""
+    out, nxt = [], 0
+    for e in range(len(ru.names)):
+        if any(ru.col[m][e] >= 0 for m in ru.col):
+            out.append(nxt)
+            nxt += 1
+        else:
+            out.append(-1)
+    return out
+
+
 @dataclass
 class TeamUsage:
     role: Dict[str, RoleUsage]
@@ -176,9 +189,8 @@ def resolve_team(tc, models: art.ModelSet) -> TeamUsage:
         df = tables[r] if tables[r] is not None else _unknown(ROLE_NAME_COL[r])
         names = [str(x) for x in df[ROLE_NAME_COL[r]].tolist()]
         share = np.asarray(df["share"].values, dtype=np.float64)
-        cap = MAX_PASSERS if r == "pass" else MAX_USAGE
-        if not (1 <= len(names) <= cap):
-            raise ValueError(f"{tc.name}: {len(names)} {r} usage entries; the kernels hold 1..{cap}")
+        if not (1 <= len(names) <= MAX_USAGE):
+            raise ValueError(f"{tc.name}: {len(names)} {r} usage entries; the kernels hold 1..{MAX_USAGE}")
         if not np.all(np.isfinite(share)) or np.any(share < 0) or not share.sum() > 0:
             raise ValueError(f"{tc.name}: {r} shares must be finite, non-negative and not all zero")
         track = tracks[r] or set()
@@ -196,24 +208,29 @@ def resolve_team(tc, models: art.ModelSet) -> TeamUsage:
             hot = [c for c in col[m] if c >= 0]
             if len(hot) != len(set(hot)):
                 raise ValueError(f"{tc.name}: two {r} usage entries map to the same {m} column")
+        known = sum(1 for e in range(len(names)) if any(col[m][e] >= 0 for m in col))
+        if known > MAX_NAME_ROWS[r]:
+            raise ValueError(f"{tc.name}: {known} {r} names that the models have one-hot columns for; "
+                             f"the kernels hold {MAX_NAME_ROWS[r]} (names unknown to every model are not limited)")
         out.role[r] = RoleUsage(names=names, share=share, slot=slot, col=col)
     return out
 
 
-def player_rows(box: np.ndarray, game0: int, team_names: Sequence[str], usage: Sequence[TeamUsage]) -> pd.DataFrame:
+def player_rows(box, game0: int, team_names: Sequence[str], usage: Sequence[TeamUsage]) -> pd.DataFrame:
     """Per-game box `[games][2][n_slots][6]` (yds, att|tgt, comp|rec, td, INT, sacks) -> the reference's
     players table (`flatten_player_box_rows`, PLAYER_COLS, FMC:1259-1299): one row per game, team and
     tracked name that was sampled at least once in that game; `sim` = game id, `start` = "A"/"B".
     Row order: game, receiving team first, then QB / Rusher / Receiver in usage-table order (the reference
     orders names by first appearance inside a game)."""
     from .api import PLAYER_COLS
+    from .native import box_slot
     n = box.shape[0]
     frames = []
     gid = np.arange(game0, game0 + n, dtype=np.int64)
     first = (gid & 1).astype(np.int64)                     # team that received the opening kickoff
     for t in (0, 1):
         for s, (role, name) in enumerate(usage[t].slots):
-            rec = box[:, t, s, :]
+            rec = box_slot(box, t, s)
             seen = (rec[:, 1] > 0) | (rec[:, 5] > 0)        # _ensure_player ran: a pass call, a target, a carry
             if not seen.any():
                 continue
@@ -252,7 +269,7 @@ _STAT_FIELD = {  # players_* column -> (role, box field); PLAYER_COLS FMC:1259-1
 _STAT_ALIASES = {"pass_yards": "pass_yds", "rush_yards": "rush_yds", "rec_yards": "rec_yds"}   # edge_finder.py:12-17
 
 
-def player_prop_odds_from_box(box: np.ndarray, team_names: Sequence[str], usage: Sequence[TeamUsage],
+def player_prop_odds_from_box(box, team_names: Sequence[str], usage: Sequence[TeamUsage],
                               team: str, player: str, stat: str, line: float) -> Dict[str, object]:
     """`edge_finder.player_prop_odds` (edge_finder.py:168-231) straight from the per-game box, without
     materialising `players_*`: over/under/push rates of one player's stat against `line`, fair American
@@ -267,7 +284,8 @@ def player_prop_odds_from_box(box: np.ndarray, team_names: Sequence[str], usage:
     hit = [s for s, (r, nm) in enumerate(usage[t[0]].slots) if r == role and nm.lower() == player.lower()] if t else []
     if not hit:
         raise ValueError(f"No rows found for {player} on {team}.")
-    rec = box[:, t[0], hit[0], :]
+    from .native import box_slot
+    rec = box_slot(box, t[0], hit[0])
     seen = (rec[:, 1] > 0) | (rec[:, 5] > 0)
     vals = rec[seen, fld]
     if fld == 0:

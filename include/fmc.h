@@ -102,10 +102,11 @@ typedef struct {
  * the entry's one-hot column (the OneHotEncoder(handle_unknown='ignore') half of the preprocessors applied
  * to passer_name / target_name / rusher_name, FMC:1079-1081, 1216) and keeps a per-game box line for
  * entries whose `slot` is >= 0 (names in the team's focus track set, FMC:1062-1063, 1204). */
-#define FMC_MAX_USAGE 8          /* entries per table */
-#define FMC_MAX_PASSERS 4        /* entries of the passer table */
+#define FMC_MAX_USAGE 32         /* entries per table */
+#define FMC_MAX_PASSER_ROWS 4    /* passers per team that some model has a one-hot column for */
+#define FMC_MAX_NAME_ROWS 8      /* same for targets and for rushers; names no model knows are not limited */
 typedef struct {
-    int32_t n;                   /* 1..FMC_MAX_USAGE (passers: 1..FMC_MAX_PASSERS) */
+    int32_t n;                   /* 1..FMC_MAX_USAGE */
     int32_t reserved;
     double share[FMC_MAX_USAGE]; /* df['share'].values, in table order */
     int32_t slot[FMC_MAX_USAGE]; /* output slot of a tracked name inside the team's box, -1 = not tracked */

@@ -40,7 +40,7 @@ class FoConfig(C.Structure):
     ]
 
 
-MAX_USAGE = 8
+MAX_USAGE = 32
 PLAYER_FIELDS = 6
 ROLE_INDEX = {"pass": 0, "rush": 1, "rec": 2}
 

@@ -93,7 +93,7 @@ typedef struct {
 /* Usage tables of one team (TeamContext.qb_share / rush_share / target_share, FMC:262-264) reduced to what
  * the engine reads: the shares Generator.choice gets (FMC:627, 631, 635), whether a name is in the team's
  * focus track set (FMC:1062-1063, 1204) and which one-hot column the name lights in every model. */
-#define FO_MAX_USAGE 8
+#define FO_MAX_USAGE 32
 #define FO_PLAYER_FIELDS 6   /* yds, att|tgt, comp|rec, td, INT, sacks */
 typedef struct {
     int n;

@@ -11,6 +11,7 @@ focus rows.  Then it drives the reference's own `simulate_game` with injected dr
 (oracle/ref_harness.py) and stores
 
   players_focus.csv        the synthetic sheet
+  usage_*_share.csv        synthetic fallback usage files (committed; written once by hand)
   ref_players.npz          per team the reference's share tables + track sets
                            (`_build_focus_usage_tables` / `_usage_from_focus_or_fallback`), per game the
                            per-iteration states, final scores and `flatten_player_box_rows` (FMC:1266-1299)
@@ -48,7 +49,9 @@ Iowa State,Avery Morrow,WR,,rec_yards,12.5
 Iowa State,Zed Unknown,WR,0.25,rec_yards,30.5
 """
 
-PAIRS = [("Kansas State", "Iowa State"), ("UTSA", "Iowa State")]
+# Ohio State has no focus rows: its usage comes from the fallback files usage_{qb,rush,target}_share.csv in this
+# directory (FMC:243-245, 487-505): 21 rushers (one with a negative share), 12 targets, nothing tracked
+PAIRS = [("Kansas State", "Iowa State"), ("UTSA", "Iowa State"), ("Ohio State", "Kansas State")]
 PLAYER_COLS = ["sim", "start", "team", "opp", "player", "role", "pass_att", "pass_comp", "pass_yds", "pass_td", "INT",
                "sacks", "rush_att", "rush_yds", "rush_td", "rec", "tgt", "rec_yds", "rec_td"]
 
@@ -62,6 +65,7 @@ def main():
     mod._FOCUS_USAGE = mod._build_focus_usage_tables(sheet_path)      # FMC:605 does this at import from the cwd
     assert mod.OTHER_SENTINEL == "__Other__"
 
+    os.chdir(HERE)      # `_load_usage_table` reads the fallback files relative to the working directory
     teams = {}
     for name in sorted({t for p in PAIRS for t in p}):
         tc = rh.team_context(mod, name)

@@ -12,7 +12,7 @@ from fast_monte_carlo_b200 import native, priors, usage
 from oracle import tree_oracle as to
 from test_pack import _rows
 
-DYN_ROW0, MAX_PASSERS, MAX_USAGE = 15, 4, 8
+DYN_ROW0, MAX_PASSERS, MAX_USAGE = 15, 4, 8      # kDynRow0, FMC_MAX_PASSER_ROWS, FMC_MAX_NAME_ROWS
 
 
 @pytest.fixture(scope="module")
@@ -20,14 +20,15 @@ def teams(models_s2):
     focus = usage.build_focus_usage_tables(os.path.join(GOLDEN, "players_focus.csv"))
     sp = priors.load_sp_flex(priors.packaged_priors_path())
     out = {}
-    for name in ("Kansas State", "Iowa State", "UTSA"):
+    for name in ("Kansas State", "Iowa State", "UTSA", "Ohio State"):
         tc = priors.build_team_context_from_sp_flex(name, 2025, 1, sp, focus=focus, usage_dir=GOLDEN)
         out[name] = (tc, usage.resolve_team(tc, models_s2))
     return out
 
 
 @pytest.mark.parametrize("name", ["pass_stage1", "pass_stage2", "pass_yards", "run_yards", "sack_yards"])
-@pytest.mark.parametrize("off,de", [("Kansas State", "Iowa State"), ("Iowa State", "UTSA"), ("UTSA", "Kansas State")])
+@pytest.mark.parametrize("off,de", [("Kansas State", "Iowa State"), ("Iowa State", "UTSA"), ("UTSA", "Kansas State"),
+                                    ("Ohio State", "Kansas State")])
 def test_dynamic_one_hot_rows(models_s2, native_lib, teams, name, off, de):
     f = models_s2[name]
     skl = f.kind == 1
@@ -46,21 +47,24 @@ def test_dynamic_one_hot_rows(models_s2, native_lib, teams, name, off, de):
         ru = tu.role["rush"]
         e0 = rng.integers(0, len(ru.names), n)
         cols = np.stack([np.asarray(ru.col[name])[e0], np.full(n, -1)], axis=1)
-        hot = [(e0, DYN_ROW0)]
-        dyn.update({c: DYN_ROW0 + e for e, c in enumerate(ru.col[name]) if c >= 0})
+        nr = np.asarray(usage.name_rows(ru))
+        hot = [(nr[e0], DYN_ROW0)]
+        dyn.update({c: DYN_ROW0 + nr[e] for e, c in enumerate(ru.col[name]) if c >= 0})
     else:
         qb, wr = tu.role["pass"], tu.role["rec"]
         e0 = rng.integers(0, len(qb.names), n)
         e1 = rng.integers(0, len(wr.names), n)
         cols = np.stack([np.asarray(qb.col[name])[e0], np.asarray(wr.col[name])[e1]], axis=1)
-        hot = [(e0, DYN_ROW0), (e1, DYN_ROW0 + MAX_PASSERS)]
-        dyn.update({c: DYN_ROW0 + e for e, c in enumerate(qb.col[name]) if c >= 0})
-        dyn.update({c: DYN_ROW0 + MAX_PASSERS + e for e, c in enumerate(wr.col[name]) if c >= 0})
+        nq, nw = np.asarray(usage.name_rows(qb)), np.asarray(usage.name_rows(wr))
+        hot = [(nq[e0], DYN_ROW0), (nw[e1], DYN_ROW0 + MAX_PASSERS)]
+        dyn.update({c: DYN_ROW0 + nq[e] for e, c in enumerate(qb.col[name]) if c >= 0})
+        dyn.update({c: DYN_ROW0 + MAX_PASSERS + nw[e] for e, c in enumerate(wr.col[name]) if c >= 0})
     slots, stream, consts, meta = native.pack_forest_host(f, mode=0, cols=(-1, -1), fold_values=fv, dyn=dyn)
     rows = np.zeros((n, DYN_ROW0 + MAX_PASSERS + MAX_USAGE), dtype=np.float32)
     rows[:, :DYN_ROW0] = pw.sim_rows(num, zm, None)
-    for e, r0 in hot:
-        rows[np.arange(n), r0 + e] = 1.0
+    for r, r0 in hot:            # a name without a name row lights nothing
+        k = np.nonzero(r >= 0)[0]
+        rows[k, r0 + r[k]] = 1.0
     got = pw.walk(slots, stream, consts, meta, rows, skl, f.base_margin)
     ref = to.raw_margin(f, num, cols)
     assert np.array_equal(got, ref)
