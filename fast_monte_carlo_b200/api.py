@@ -181,6 +181,36 @@ def merge_histograms(hist, counters=None):
     return hist, counters
 
 
+def gather_player_box(local_rec, total_games: int):
+    """The exchange step of the player path across ranks: every rank holds the per-game box of its contiguous
+    game-id slice (`shard_range`), fmc_player_rec[games_local][2][n_slots]; one all-gather over the default
+    torch.distributed group (NCCL for a CUDA tensor, gloo for a CPU tensor / NumPy array) returns the whole run's
+    box in game order on every rank.  `local_rec` may be a NumPy structured array (native.PLAYER_REC), a
+    native.PlayerBox or an int64 torch tensor [games_local, 2, n_slots, 2].  No-op without a process group.
+    Memory: 32 bytes x n_slots x total_games on every rank -- meant for one matchup, not for a slate."""
+    import torch
+    import torch.distributed as dist
+    from .native import PLAYER_REC, PlayerBox
+    if isinstance(local_rec, PlayerBox):
+        local_rec = local_rec.rec
+    as_numpy = isinstance(local_rec, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(local_rec).view(np.int64).reshape(local_rec.shape + (2,))) if as_numpy else local_rec
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return PlayerBox(local_rec) if as_numpy else t
+    rank, world = dist.get_rank(), dist.get_world_size()
+    sizes = [shard_range(int(total_games), r, world) for r in range(world)]
+    assert t.shape[0] == sizes[rank][1] - sizes[rank][0], "local box does not match this rank's game slice"
+    longest = max(b - a for a, b in sizes)
+    pad = torch.zeros((longest,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad)
+    whole = torch.cat([parts[r][:sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
+    if as_numpy:
+        return PlayerBox(whole.cpu().numpy().view(PLAYER_REC).reshape(whole.shape[:-1]))
+    return whole
+
+
 def simulate_slate(pairs: Sequence[Tuple[str, str]], n: int = 1000, *, sp_path: Optional[str] = None,
                    year: int = 2025, week: int = 1, seed: Optional[int] = None,
                    engine: Optional[Engine] = None, markets: Optional[Dict[Tuple[str, str], Dict[str, float]]] = None):

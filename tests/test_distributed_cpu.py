@@ -76,3 +76,58 @@ def test_two_rank_histogram_merge_equals_single_process():
     h2, c2 = results[2]
     assert np.array_equal(h1, h2) and np.array_equal(c1, c2)
     assert h1.sum() == 2 * games and c1[0] == 2 * games
+
+
+def _players_worker(rank, world, port, games, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from conftest import GOLDEN
+    from fast_monte_carlo_b200 import artifacts as art, priors, usage, native
+    from oracle import c_oracle as co
+    ms = art.load_default_models()
+    co.load_models(ms)
+    focus = usage.build_focus_usage_tables(os.path.join(GOLDEN, "players_focus.csv"))
+    sp = priors.load_sp_flex(priors.packaged_priors_path())
+    tcs = [priors.build_team_context_from_sp_flex(t, 2025, 1, sp, focus=focus, usage_dir=GOLDEN)
+           for t in ("Kansas State", "Iowa State")]
+    us = [usage.resolve_team(tc, ms) for tc in tcs]
+    n_slots = max(len(u.slots) for u in us)
+    g0, g1 = api.shard_range(games, rank, world)
+    r = co.simulate(co.make_config(ms, tcs[0].sp, tcs[1].sp), g1 - g0, game0=g0, seed=4, threads=1,
+                    usage=co.make_usage(us), n_slots=n_slots)
+    # pack the oracle's dense box into the kernel's record layout (fmc_player_rec) -- the rank-local product output
+    rec = np.zeros((g1 - g0, 2, n_slots), dtype=native.PLAYER_REC)
+    rec["yds"] = r["players"][..., 0]
+    for k in range(5):
+        rec["counts"] |= r["players"][..., 1 + k].astype(np.uint64) << np.uint64(10 * k)
+    whole = api.gather_player_box(rec, games)
+    assert whole.shape[0] == games
+    odds = usage.player_prop_odds_from_box(whole, ("Kansas State", "Iowa State"), us, "Iowa State", "Levi Williams",
+                                           "pass_yards", 150.5)
+    if rank == 0:
+        q.put((whole.dense(), odds))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_player_box_gather_equals_single_process():
+    """Ranks play contiguous game-id slices; one all-gather of the per-game boxes gives the single-process box
+    (odd game count: the slices differ in length), hence the same prop odds."""
+    games = 301
+    ctx = mp.get_context("spawn")
+    results = {}
+    for world in (1, 2):
+        q = ctx.SimpleQueue()
+        port = _free_port()
+        procs = [ctx.Process(target=_players_worker, args=(r, world, port, games, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        results[world] = q.get()
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+    b1, o1 = results[1]
+    b2, o2 = results[2]
+    assert b1.shape[0] == games and np.array_equal(b1, b2) and o1 == o2 and o1["samples"] > 250
