@@ -132,3 +132,55 @@ def test_players_slate_two_matchups(engine, oracle, models_s2, contexts):
         sl = slice(s.out_offset, s.out_offset + s.games)
         assert np.array_equal(got["scores"][sl], ref["scores"])
         _box_equal_philox(got["players"].dense()[sl], ref["players"])
+
+
+def test_players_full_size_properties(engine, contexts):
+    """4 M games in player mode (device buffers): size-independent invariants of the per-game box.
+    Iowa State's sheet has one passer with share 1 and four receivers that sum to 1 (all tracked, no `__Other__`),
+    so in every game its passer's completions / touchdowns / yards equal the sums over its receivers, and every
+    pass call (attempt or sack) is exactly one target.  A launch over [0, N) equals two launches over the halves."""
+    import torch
+    n = 4_000_000
+    spec = _spec(contexts, "Kansas State", "Iowa State", n)
+    engine.set_matchups([spec])
+    S = engine.n_slots
+    dev = torch.device("cuda", 0)
+    box = torch.zeros((n, 2, S, 2), dtype=torch.int64, device=dev)
+    cnt = torch.zeros(32, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream()
+    engine.ctx.simulate_device(seed=77, counters=cnt.data_ptr(), players=box.data_ptr(), cuda_stream=st.cuda_stream)
+    torch.cuda.synchronize()
+    assert int(cnt[0]) == n
+    yds = box[..., 0].view(torch.float64)
+    c = box[..., 1]
+    f = lambda k: (c >> (10 * k)) & 0x3FF                     # att|tgt, comp|rec, td, INT, sacks
+    isu = contexts["Iowa State"][1]
+    qb = [s for s, (r, _) in enumerate(isu.slots) if r == "pass"]
+    wr = [s for s, (r, _) in enumerate(isu.slots) if r == "rec"]
+    assert len(qb) == 1 and len(wr) == 4
+    q = qb[0]
+    assert torch.equal(f(1)[:, 1, q], f(1)[:, 1, wr].sum(dim=1))            # completions == receptions
+    assert torch.equal(f(2)[:, 1, q], f(2)[:, 1, wr].sum(dim=1))            # passing TDs == receiving TDs
+    assert torch.equal(f(0)[:, 1, q] + f(4)[:, 1, q], f(0)[:, 1, wr].sum(dim=1))   # attempts + sacks == targets
+    assert torch.allclose(yds[:, 1, q], yds[:, 1, wr].sum(dim=1), rtol=0, atol=1e-9)
+    assert bool((f(1) <= f(0)).all())                                       # completions <= attempts, receptions <= targets
+    assert bool((f(3) <= f(0)).all())                                       # interceptions are attempts
+    for t, tu in enumerate(spec.usage):
+        for s_, (r, _) in enumerate(tu.slots):
+            td_cap = f(0)[:, t, s_] if r == "rush" else f(1)[:, t, s_]      # a TD needs a carry / a completion
+            assert bool((f(2)[:, t, s_] <= td_cap).all()), (t, s_)
+    names = [isu.slots[s][1] for s in wr]
+    assert int(f(0)[:, 1, wr[names.index("Avery Morrow")]].sum()) == 0      # share 0 (NaN usage): tracked, never sampled
+    want = np.asarray(isu.role["rec"].share)[[isu.role["rec"].names.index(nm) for nm in names]]
+    got = (f(0)[:, 1, wr].sum(dim=0).double() / f(0)[:, 1, wr].sum()).cpu().numpy()
+    assert np.allclose(got, want / want.sum(), atol=2e-3)                   # targets follow the usage shares
+    # sharding invariance (what a rank gets): two launches over the halves
+    half = n // 2
+    parts = []
+    for g0 in (0, half):
+        engine.set_matchups([_spec(contexts, "Kansas State", "Iowa State", half, g0=g0)])
+        b = torch.zeros((half, 2, S, 2), dtype=torch.int64, device=dev)
+        engine.ctx.simulate_device(seed=77, players=b.data_ptr(), cuda_stream=st.cuda_stream)
+        torch.cuda.synchronize()
+        parts.append(b)
+    assert torch.equal(torch.cat(parts, dim=0), box)
