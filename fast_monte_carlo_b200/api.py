@@ -213,7 +213,8 @@ def gather_player_box(local_rec, total_games: int):
 
 def simulate_slate(pairs: Sequence[Tuple[str, str]], n: int = 1000, *, sp_path: Optional[str] = None,
                    year: int = 2025, week: int = 1, seed: Optional[int] = None,
-                   engine: Optional[Engine] = None, markets: Optional[Dict[Tuple[str, str], Dict[str, float]]] = None):
+                   engine: Optional[Engine] = None, markets: Optional[Dict[Tuple[str, str], Dict[str, float]]] = None,
+                   focus_csv: Optional[str] = None, usage_dir: str = "."):
     """A whole slate in one launch (BASELINE configs 3-4): every (teamA, teamB) of `pairs` is simulated for
     `n` PAIRS of games (2n games, A receives / B receives alternately, exactly like `simulate_matchup`).
 
@@ -224,29 +225,50 @@ def simulate_slate(pairs: Sequence[Tuple[str, str]], n: int = 1000, *, sp_path: 
     `markets` ({(A, B): {"spread": s, "total": t}}), spread / total odds (edge_finder.py:283-336) -- comes
     from the joint score histogram.  Returns {(A, B): {"hist", "summary", "moneyline", "markets", "games"}},
     plus the key "_counters" with the event counters of the whole slate.
+
+    Players: when a team of the slate has usage data (`focus_csv`, default `2025_week1_players.csv` in the working
+    directory, or `usage_*_share.csv` under `usage_dir`; FMC:228-249) the slate runs in player mode and every
+    matchup also returns "player_hist" ([2][n_slots][PH_BINS], merged over ranks with the same all-reduce),
+    "usage" and "props": `edge_finder.scan_props_for_matchup` (edge_finder.py:340-390) for the sheet's lines,
+    computed from the histograms (`usage.player_prop_odds_from_hist`).
     """
     import torch
     import torch.distributed as dist
     eng = engine if engine is not None else get_engine()
     sp_df = load_sp_flex(sp_path if sp_path is not None else packaged_priors_path())
+    sheet = focus_csv if focus_csv is not None else _usage.FOCUS_PLAYERS_CSV
+    focus = _usage.build_focus_usage_tables(sheet)
+    uses = []
     for a, b in pairs:                                    # same errors as the reference for unknown teams
-        build_team_context_from_sp_flex(a, year, week, sp_df)
-        build_team_context_from_sp_flex(b, year, week, sp_df)
+        ta = build_team_context_from_sp_flex(a, year, week, sp_df, focus=focus, usage_dir=usage_dir)
+        tb = build_team_context_from_sp_flex(b, year, week, sp_df, focus=focus, usage_dir=usage_dir)
+        uses.append((_usage.resolve_team(ta, eng.models), _usage.resolve_team(tb, eng.models)))
     rank, world = 0, 1
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(), dist.get_world_size()
     specs = slate_specs(pairs, 2 * int(n), sp_df, rank, world)
+    for sp_, u in zip(specs, uses):
+        sp_.usage = u
     eng.set_matchups(specs)
+    with_players = eng.ctx.has_usage and eng.n_slots > 0
     dev = torch.device("cuda", eng.ctx.device)
     hist = torch.zeros((len(specs), 2, outputs.HIST_BINS, outputs.HIST_BINS), dtype=torch.int32, device=dev)
     counters = torch.zeros(len(native_counter_names()), dtype=torch.int64, device=dev)
     padded = torch.zeros(32, dtype=torch.int64, device=dev)
     st = torch.cuda.current_stream(dev)
+    phist = (torch.zeros((len(specs), 2, eng.n_slots, _usage.PH_BINS), dtype=torch.int32, device=dev)
+             if with_players else None)
     eng.ctx.simulate_device(seed=_fresh_seed() if seed is None else int(seed), hist=hist.data_ptr(),
-                            counters=padded.data_ptr(), cuda_stream=st.cuda_stream)
+                            counters=padded.data_ptr(), cuda_stream=st.cuda_stream,
+                            player_hist=phist.data_ptr() if phist is not None else 0)
     hist64 = hist.to(torch.int64)
     counters.copy_(padded[:counters.numel()])
     merge_histograms(hist64, counters)
+    ph = None
+    if phist is not None:
+        ph64 = phist.to(torch.int64)
+        merge_histograms(ph64)
+        ph = ph64.cpu().numpy()
     h = hist64.cpu().numpy()
     c = counters.cpu().numpy()
     out: Dict[object, object] = {"_counters": {k: int(c[i]) for i, k in enumerate(native_counter_names())}}
@@ -256,6 +278,10 @@ def simulate_slate(pairs: Sequence[Tuple[str, str]], n: int = 1000, *, sp_path: 
         mk = (markets or {}).get((a, b))
         if mk:
             entry["markets"] = outputs.game_market_odds_from_hist(h[m], a, b, spread=mk.get("spread"), total=mk.get("total"))
+        if ph is not None:
+            entry["player_hist"] = ph[m]
+            entry["usage"] = uses[m]
+            entry["props"] = _usage.scan_props_from_hist(ph[m], (a, b), uses[m], sheet)
         out[(a, b)] = entry
     return out
 

@@ -187,6 +187,8 @@ struct fmc_ctx {
     struct NameRows { int8_t row[3][FMC_MAX_USAGE]; };
     std::vector<NameRows> name_rows;     // per team: the 0/1 feature row of every usage entry (-1: no model knows the name)
     int n_slots = 0;
+    fmc_player_rec *d_box_scratch = nullptr;   // running box of every resident lane [grid x threads][2][n_slots]
+    size_t box_scratch_bytes = 0;
     bool tables_dirty = true;
     // device-side state of the last set_matchups
     TableArena sim_tables;
@@ -249,7 +251,7 @@ extern "C" void fmc_destroy(fmc_ctx *c) {
     cudaSetDevice(c->device);
     c->sim_tables.release();
     for (auto &e : c->pred) e.arena.release();
-    cudaFree(c->d_matchups); cudaFree(c->d_next);
+    cudaFree(c->d_matchups); cudaFree(c->d_next); cudaFree(c->d_box_scratch);
     delete c;
 }
 
@@ -542,10 +544,21 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
     a.scores = g->scores_dev; a.hist = g->hist_dev; a.counters = (unsigned long long *)g->counters_dev;
     a.stream = g->stream_dev; a.trace = g->trace_dev; a.iters = g->iters_dev;
     const bool players = !c->usage.empty();
-    if (g->players_dev && !players) return fail(FMC_ERR_INVALID, "fmc_simulate: players_dev needs fmc_set_usage");
-    a.players = g->players_dev; a.n_slots = c->n_slots;
-    if (a.players && c->n_slots == 0) a.players = nullptr;
+    if ((g->players_dev || g->player_hist_dev) && !players)
+        return fail(FMC_ERR_INVALID, "fmc_simulate: players_dev / player_hist_dev need fmc_set_usage");
     const int grid = c->prop.multiProcessorCount * kSimCtasPerSm;
+    a.n_slots = c->n_slots;
+    if (players && c->n_slots > 0) {
+        a.players = g->players_dev; a.player_hist = g->player_hist_dev;
+        const size_t need = (size_t)grid * kSimThreads * 2 * (size_t)c->n_slots * sizeof(fmc_player_rec);
+        if (need > c->box_scratch_bytes) {
+            cudaFree(c->d_box_scratch); c->d_box_scratch = nullptr; c->box_scratch_bytes = 0;
+            CK(cudaMalloc(&c->d_box_scratch, need));
+            c->box_scratch_bytes = need;
+        }
+        CK(cudaMemsetAsync(c->d_box_scratch, 0, need, st));
+        a.box_scratch = c->d_box_scratch;
+    }
 #ifdef FMC_DEBUG_CHECKS
     debug_set_range(c->sim_tables);
 #endif
@@ -563,7 +576,7 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
 
 static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
                               uint64_t *counters_host, const double *stream_host, double *trace_host,
-                              uint16_t *iters_host, fmc_player_rec *players_host) {
+                              uint16_t *iters_host, fmc_player_rec *players_host, uint32_t *player_hist_host) {
     if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
     if (c->matchups.empty()) return fail(FMC_ERR_INVALID, "fmc_set_matchups has not been called");
     CK(cudaSetDevice(c->device));
@@ -580,7 +593,9 @@ static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, 
     uint16_t *d_iters = nullptr;
     fmc_player_rec *d_players = nullptr;
     const size_t players_n = games * 2 * (size_t)c->n_slots;
-    if (players_host && c->usage.empty()) return fail(FMC_ERR_INVALID, "players output needs fmc_set_usage");
+    if ((players_host || player_hist_host) && c->usage.empty()) return fail(FMC_ERR_INVALID, "players output needs fmc_set_usage");
+    uint32_t *d_phist = nullptr;
+    const size_t phist_n = c->matchups.size() * 2 * (size_t)c->n_slots * FMC_PH_BINS;
     int rc = FMC_OK;
     cudaError_t e = cudaSuccess;
     auto bail = [&](cudaError_t err, const char *what) { rc = fail(FMC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err)); };
@@ -605,10 +620,14 @@ static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, 
         if (iters_host && games) { if ((e = cudaMalloc(&d_iters, games * 2)) != cudaSuccess) { bail(e, "cudaMalloc iters"); break; } }
         if (players_host && players_n) {
             if ((e = cudaMalloc(&d_players, players_n * sizeof(fmc_player_rec))) != cudaSuccess) { bail(e, "cudaMalloc players"); break; }
-            if ((e = cudaMemsetAsync(d_players, 0, players_n * sizeof(fmc_player_rec))) != cudaSuccess) { bail(e, "memset players"); break; }
+        }
+        if (player_hist_host && phist_n) {
+            if ((e = cudaMalloc(&d_phist, phist_n * 4)) != cudaSuccess) { bail(e, "cudaMalloc player hist"); break; }
+            if ((e = cudaMemsetAsync(d_phist, 0, phist_n * 4)) != cudaSuccess) { bail(e, "memset player hist"); break; }
         }
         fmc_sim_args g;
         std::memset(&g, 0, sizeof(g));
+        g.player_hist_dev = d_phist;
         g.seed = seed; g.n_matchups = (int)nm; g.scores_dev = d_scores; g.hist_dev = d_hist; g.counters_dev = d_cnt;
         g.stream_dev = d_stream; g.trace_dev = d_trace; g.iters_dev = d_iters; g.stream = nullptr;
         g.players_dev = d_players;
@@ -621,22 +640,24 @@ static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, 
         if (trace_host && games && (e = cudaMemcpy(trace_host, d_trace, games * FMC_MAX_ITERS * FMC_TRACE_COLS * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H trace"); break; }
         if (iters_host && games && (e = cudaMemcpy(iters_host, d_iters, games * 2, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H iters"); break; }
         if (d_players && (e = cudaMemcpy(players_host, d_players, players_n * sizeof(fmc_player_rec), cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H players"); break; }
+        if (d_phist && (e = cudaMemcpy(player_hist_host, d_phist, phist_n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H player hist"); break; }
     } while (0);
     cudaFree(d_scores); cudaFree(d_hist); cudaFree(d_cnt); cudaFree(d_stream); cudaFree(d_trace); cudaFree(d_iters);
-    cudaFree(d_players);
+    cudaFree(d_players); cudaFree(d_phist);
     return rc;
 }
 
 extern "C" int fmc_simulate_host(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
                                  uint64_t *counters_host, const double *stream_host, double *trace_host,
                                  uint16_t *iters_host) {
-    return simulate_host_impl(c, seed, scores_host, hist_host, counters_host, stream_host, trace_host, iters_host, nullptr);
+    return simulate_host_impl(c, seed, scores_host, hist_host, counters_host, stream_host, trace_host, iters_host, nullptr, nullptr);
 }
 
 extern "C" int fmc_simulate_players_host(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
                                          uint64_t *counters_host, const double *stream_host, double *trace_host,
-                                         uint16_t *iters_host, fmc_player_rec *players_host) {
-    return simulate_host_impl(c, seed, scores_host, hist_host, counters_host, stream_host, trace_host, iters_host, players_host);
+                                         uint16_t *iters_host, fmc_player_rec *players_host, uint32_t *player_hist_host) {
+    return simulate_host_impl(c, seed, scores_host, hist_host, counters_host, stream_host, trace_host, iters_host, players_host,
+                              player_hist_host);
 }
 
 extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, int64_t n, double *out_dev,

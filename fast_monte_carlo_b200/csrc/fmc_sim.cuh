@@ -90,7 +90,9 @@ struct SimKernelArgs {
     const double *stream;
     double *trace;
     uint16_t *iters;
-    fmc_player_rec *players;           // player mode: [games][2][n_slots] per-game box lines (zeroed by the caller)
+    fmc_player_rec *players;           // player mode: [games][2][n_slots] per-game box lines (optional output)
+    uint32_t *player_hist;             // player mode: [n_matchups][2][n_slots][FMC_PH_BINS] (optional output)
+    fmc_player_rec *box_scratch;       // player mode: [lanes of the grid][2][n_slots] running box of each lane's game
     int n_slots;
 };
 
@@ -343,14 +345,51 @@ __device__ __forceinline__ int sample_usage(const UsageDev &U, int role, double 
 // pstats[team][role][name] of a tracked name (FMC:1073-1075, 1108-1148, 1163-1192, 1207-1249): the lane owns its
 // game's box lines, so a plain read-modify-write.  counts: 10-bit fields att|tgt, comp|rec, td, INT, sacks.
 enum : unsigned long long { PC_ATT = 1ULL, PC_COMP = 1ULL << 10, PC_TD = 1ULL << 20, PC_INT = 1ULL << 30, PC_SACK = 1ULL << 40 };
+__device__ __forceinline__ fmc_player_rec *lane_box(const SimKernelArgs &a) {
+    return a.box_scratch + (size_t)(blockIdx.x * kSimThreads + threadIdx.x) * 2 * (size_t)a.n_slots;
+}
 __device__ __forceinline__ void credit(const SimKernelArgs &a, const MatchupDev &M, const Lane &L, int team, int role,
                                        int entry, unsigned long long counts, bool has_yds, double yds) {
-    if (!a.players) return;
     const int slot = M.usage[team].slot[role][entry];
     if (slot < 0) return;
-    fmc_player_rec *r = a.players + ((size_t)(M.out_offset + (L.game - M.game_begin)) * 2 + (size_t)team) * (size_t)a.n_slots + (size_t)slot;
+    fmc_player_rec *r = lane_box(a) + team * a.n_slots + slot;
     if (has_yds) r->yds += yds;
     r->counts += counts;
+}
+// Python's round(x, 1) in tenths (FMC:1276, 1286, 1296): the decimal value of x correctly rounded, ties to even.
+// k = floor(RN(10 x)) is the lower neighbour (or, when the product rounds up to an integer, the nearest itself);
+// fma gives the exact sign of x - (2k + 1) / 20, the midpoint between k and k + 1 tenths.
+__device__ __forceinline__ long long round_tenths(double x) {
+    const double k = floor(x * 10.0);
+    const double r = fma(x, 20.0, -(2.0 * k + 1.0));
+    long long q = (long long)k;
+    if (r > 0.0 || (r == 0.0 && (q & 1LL))) q += 1;
+    return q;
+}
+// End of a game: every box line of the lane goes to the per-game output and into the per-player histograms
+// (a line counts only if the name was sampled in this game), then the running box is cleared for the next game.
+// (scalars by value on purpose: a reference to the lane or to the kernel arguments would force them into local memory)
+__device__ __noinline__ void flush_box(fmc_player_rec *box, fmc_player_rec *out, uint32_t *hist, int lines,
+                                       unsigned long long *overflow) {
+    for (int i = 0; i < lines; ++i) {
+        const fmc_player_rec r = box[i];
+        if (out) out[i] = r;
+        if (r.counts == 0ULL && r.yds == 0.0) continue;       // nothing was credited: the line is still clear
+        box[i].yds = 0.0;
+        box[i].counts = 0ULL;
+        // `_ensure_player` ran: a pass call (attempt or sack), a target, a carry
+        const bool seen = ((r.counts & 0x3FFULL) | ((r.counts >> 40) & 0x3FFULL)) != 0ULL;
+        if (!hist || !seen) continue;
+        uint32_t *h = hist + (size_t)i * FMC_PH_BINS;
+        long long b = round_tenths(r.yds) + FMC_PH_YDS_OFFSET;
+        if (b < 0 || b >= FMC_PH_YDS_BINS) { atomicAdd(overflow, 1ULL); b = b < 0 ? 0 : FMC_PH_YDS_BINS - 1; }
+        atomicAdd(h + b, 1u);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const unsigned int c = (unsigned int)((r.counts >> (10 * k)) & 0x3FFULL);
+            atomicAdd(h + FMC_PH_YDS_BINS + k * FMC_PH_CNT_BINS + (c < FMC_PH_CNT_BINS ? c : FMC_PH_CNT_BINS - 1), 1u);
+        }
+    }
 }
 // a pass call: sample_qb, sample_target, tgt += 1 (FMC:1058-1075); a run call: sample_rusher, att += 1 (FMC:1203-1208)
 template <bool TEST>
@@ -394,6 +433,12 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
                     const int hb = L.score[1] < FMC_HIST_BINS ? L.score[1] : FMC_HIST_BINS - 1;
                     if (L.score[0] >= FMC_HIST_BINS || L.score[1] >= FMC_HIST_BINS) atomicAdd(&sh.stat[FMC_C_HIST_OVERFLOW], 1ULL);
                     atomicAdd(&a.hist[(((size_t)matchup * 2 + (size_t)(L.game & 1ULL)) * FMC_HIST_BINS + ha) * FMC_HIST_BINS + hb], 1u);
+                }
+                if (PLAYERS && a.n_slots > 0) {
+                    const int lines = 2 * a.n_slots;
+                    flush_box(lane_box(a), a.players ? a.players + oi * (size_t)lines : nullptr,
+                              a.player_hist ? a.player_hist + (size_t)matchup * (size_t)lines * FMC_PH_BINS : nullptr, lines,
+                              &sh.stat[FMC_C_PH_OVERFLOW]);
                 }
                 atomicAdd(&sh.stat[FMC_C_GAMES], 1ULL);
                 atomicAdd(&sh.stat[FMC_C_PLAYS], (unsigned long long)L.plays);

@@ -25,7 +25,9 @@ N_SLOTS = 16
 MAX_ITERS = 360
 TRACE_COLS = 8
 COUNTER_NAMES = ("games", "plays", "iters", "pass", "comp", "inc", "int", "sack", "run", "td", "fga", "fg",
-                 "punt", "go", "hist_overflow", "rounds", "requests", "visits")
+                 "punt", "go", "hist_overflow", "rounds", "requests", "visits", "ph_overflow")
+PH_YDS_BINS, PH_YDS_OFFSET, PH_CNT_BINS = 8192, 1000, 128
+PH_BINS = PH_YDS_BINS + 5 * PH_CNT_BINS
 
 
 class FmcError(RuntimeError):
@@ -63,7 +65,7 @@ class SimArgs(C.Structure):
         ("seed", C.c_uint64), ("n_matchups", C.c_int32), ("reserved", C.c_int32),
         ("scores_dev", C.c_void_p), ("hist_dev", C.c_void_p), ("counters_dev", C.c_void_p),
         ("stream_dev", C.c_void_p), ("trace_dev", C.c_void_p), ("iters_dev", C.c_void_p),
-        ("stream", C.c_void_p), ("players_dev", C.c_void_p),
+        ("stream", C.c_void_p), ("players_dev", C.c_void_p), ("player_hist_dev", C.c_void_p),
     ]
 
 
@@ -144,7 +146,7 @@ def load_library():
     L.fmc_simulate_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
     L.fmc_simulate_players_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                            C.c_void_p, C.c_void_p, C.c_void_p]
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.fmc_set_usage.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
     L.fmc_pack_forest_host_dyn.restype = C.c_int64
     L.fmc_pack_forest_host_dyn.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
@@ -360,7 +362,7 @@ class Context:
 
     # -- simulation ------------------------------------------------------------------------------
     def simulate_device(self, *, seed: int, scores=0, hist=0, counters=0, stream_in=0, trace=0, iters=0,
-                        cuda_stream=0, players=0) -> None:
+                        cuda_stream=0, players=0, player_hist=0) -> None:
         """Asynchronous launch on raw device pointers (ints; 0 = not requested)."""
         a = SimArgs()
         a.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
@@ -368,11 +370,12 @@ class Context:
         a.scores_dev = scores or None; a.hist_dev = hist or None; a.counters_dev = counters or None
         a.stream_dev = stream_in or None; a.trace_dev = trace or None; a.iters_dev = iters or None
         a.stream = cuda_stream or None
-        a.players_dev = players or None      # fmc_player_rec[games][2][n_slots], zeroed by the caller
+        a.players_dev = players or None      # fmc_player_rec[games][2][n_slots]
+        a.player_hist_dev = player_hist or None   # uint32[n_matchups][2][n_slots][PH_BINS], zeroed by the caller
         _check(self._L.fmc_simulate(self._h, C.byref(a)))
 
     def simulate_host(self, *, seed: int, want_scores=True, want_hist=True, stream: Optional[np.ndarray] = None,
-                      want_trace=False, want_iters=False, want_players=False) -> dict:
+                      want_trace=False, want_iters=False, want_players=False, want_player_hist=False) -> dict:
         """End-to-end call with host buffers (fmc_simulate_host / fmc_simulate_players_host)."""
         n = self.total_games
         scores = np.zeros(n, dtype=np.uint32) if want_scores else None
@@ -385,20 +388,26 @@ class Context:
             if stream.shape != (n, MAX_ITERS, N_SLOTS):
                 raise ValueError(f"stream must be [{n},{MAX_ITERS},{N_SLOTS}]")
         vp = lambda a: None if a is None else a.ctypes.data
-        players = None
-        if want_players:
+        players = phist = None
+        if want_players or want_player_hist:
             if not self.has_usage:
-                raise FmcError("want_players needs set_usage")
-            players = np.zeros((n, 2, max(self.n_slots, 1)), dtype=PLAYER_REC)
+                raise FmcError("want_players / want_player_hist need set_usage")
+            if want_players:
+                players = np.zeros((n, 2, max(self.n_slots, 1)), dtype=PLAYER_REC)
+            if want_player_hist:
+                phist = np.zeros((self.n_matchups, 2, max(self.n_slots, 1), PH_BINS), dtype=np.uint32)
             _check(self._L.fmc_simulate_players_host(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, vp(scores), vp(hist),
                                                      vp(counters), vp(stream), vp(trace), vp(iters),
-                                                     players.ctypes.data if self.n_slots else None))
+                                                     players.ctypes.data if (players is not None and self.n_slots) else None,
+                                                     phist.ctypes.data if (phist is not None and self.n_slots) else None))
         else:
             _check(self._L.fmc_simulate_host(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF, vp(scores), vp(hist), vp(counters),
                                              vp(stream), vp(trace), vp(iters)))
         out = dict(counters={k: int(counters[i]) for i, k in enumerate(COUNTER_NAMES)})
         if players is not None:
             out["players"] = PlayerBox(players[:, :, :self.n_slots])
+        if phist is not None:
+            out["player_hist"] = phist[:, :, :self.n_slots]
         if scores is not None:
             # score word = points A | points B << 16: on a little-endian host the uint16 view IS the [n, 2] table
             out["scores"] = (scores.view(np.uint16).reshape(n, 2).astype(np.int32) if sys.byteorder == "little" else

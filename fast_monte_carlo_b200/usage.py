@@ -307,3 +307,116 @@ def player_prop_odds_from_box(box, team_names: Sequence[str], usage: Sequence[Te
         "p75": float(np.percentile(vals, 75)), "p90": float(np.percentile(vals, 90)),
         "best_side": side, "edge": round(edge * 100, 2), "ev_per_$100": round(best_ev, 2),
     }
+
+
+# ---------------------------------------------------------------------------------------------
+# per-player histograms (include/fmc.h FMC_PH_*): what the kernel accumulates with atomics and ranks merge with
+# one integer all-reduce -- the scalable form of `players_*`
+# ---------------------------------------------------------------------------------------------
+PH_YDS_BINS, PH_YDS_OFFSET, PH_CNT_BINS = 8192, 1000, 128
+PH_BINS = PH_YDS_BINS + 5 * PH_CNT_BINS
+
+
+def player_hist_from_box(box, usage: Sequence[TeamUsage]) -> np.ndarray:
+    """Host restatement of the kernel's histogram step: uint32[2][n_slots][PH_BINS] from a per-game box; a game
+    counts for a line only if the name was sampled in it.  Yards are rounded like Python's round(x, 1)."""
+    from .native import box_slot
+    n_slots = box.shape[2]
+    h = np.zeros((2, n_slots, PH_BINS), dtype=np.uint32)
+    for t in (0, 1):
+        for s in range(len(usage[t].slots)):
+            rec = box_slot(box, t, s)
+            seen = (rec[:, 1] > 0) | (rec[:, 5] > 0)
+            if not seen.any():
+                continue
+            tenths = np.rint(py_round1(rec[seen, 0]) * 10.0).astype(np.int64) + PH_YDS_OFFSET
+            h[t, s, :PH_YDS_BINS] = np.bincount(np.clip(tenths, 0, PH_YDS_BINS - 1), minlength=PH_YDS_BINS)
+            for k in range(5):
+                c = np.minimum(rec[seen, 1 + k].astype(np.int64), PH_CNT_BINS - 1)
+                lo = PH_YDS_BINS + k * PH_CNT_BINS
+                h[t, s, lo:lo + PH_CNT_BINS] = np.bincount(c, minlength=PH_CNT_BINS)
+    return h
+
+
+def _percentile_from_counts(values: np.ndarray, counts: np.ndarray, q: float) -> float:
+    """np.percentile(sample, q) (linear interpolation) of the sample a histogram stands for."""
+    cum = np.cumsum(counts)
+    n = int(cum[-1])
+    pos = (n - 1) * (q / 100.0)
+    lo, hi = int(np.floor(pos)), int(np.ceil(pos))
+    a = float(values[np.searchsorted(cum, lo + 1, side="left")])
+    b = float(values[np.searchsorted(cum, hi + 1, side="left")])
+    t = pos - lo
+    return b - (b - a) * (1.0 - t) if t >= 0.5 else a + (b - a) * t      # numpy's _lerp
+
+
+def player_prop_odds_from_hist(hist2: np.ndarray, team_names: Sequence[str], usage: Sequence[TeamUsage],
+                               team: str, player: str, stat: str, line: float) -> Dict[str, object]:
+    """`edge_finder.player_prop_odds` (edge_finder.py:168-231) from the per-player histograms of one matchup
+    (`[2][n_slots][PH_BINS]`, merged over ranks): same keys and values as from the per-game rows."""
+    from .outputs import prob_to_american
+    col = _STAT_ALIASES.get(stat, stat)
+    if col not in _STAT_FIELD:
+        raise ValueError(f"Stat '{stat}' (mapped to '{col}') not present in the player histograms.")
+    role, fld = _STAT_FIELD[col]
+    t = [i for i, nm in enumerate(team_names) if nm.lower() == team.lower()]
+    hit = [s for s, (r, nm) in enumerate(usage[t[0]].slots) if r == role and nm.lower() == player.lower()] if t else []
+    if not hit:
+        raise ValueError(f"No rows found for {player} on {team}.")
+    rec = np.asarray(hist2[t[0], hit[0]], dtype=np.int64)
+    if fld == 0:
+        counts = rec[:PH_YDS_BINS]
+        values = (np.arange(PH_YDS_BINS, dtype=np.float64) - PH_YDS_OFFSET) / 10.0
+    else:
+        lo = PH_YDS_BINS + (fld - 1) * PH_CNT_BINS
+        counts = rec[lo:lo + PH_CNT_BINS]
+        values = np.arange(PH_CNT_BINS, dtype=np.float64)
+    n = int(counts.sum())
+    if n == 0:
+        raise ValueError(f"No rows found for {player} on {team}.")
+    p_over = float(counts[values > line].sum() / n)
+    p_under = float(counts[values < line].sum() / n)
+    p_push = float(counts[np.isclose(values, line, atol=1e-9)].sum() / n)
+    ev = lambda p: p * (100.0 * (100.0 / 110.0)) - (1.0 - p) * 100.0
+    implied = 110.0 / 210.0
+    side, best_ev, edge = (("Over", ev(p_over), p_over - implied) if ev(p_over) >= ev(1.0 - p_over)
+                           else ("Under", ev(1.0 - p_over), (1.0 - p_over) - implied))
+    nz = counts > 0
+    return {
+        "team": team, "player": player, "role": ROLE_LABEL[role], "stat": col, "line": float(line),
+        "samples": n, "p_over": round(p_over, 4), "p_under": round(p_under, 4),
+        "push_rate": round(p_push, 4), "american_over": prob_to_american(p_over),
+        "american_under": prob_to_american(p_under), "mean": float((values[nz] * counts[nz]).sum() / n),
+        "median": _percentile_from_counts(values, counts, 50.0),
+        "p75": _percentile_from_counts(values, counts, 75.0), "p90": _percentile_from_counts(values, counts, 90.0),
+        "best_side": side, "edge": round(edge * 100, 2), "ev_per_$100": round(best_ev, 2),
+    }
+
+
+def scan_props_from_hist(hist2: np.ndarray, team_names: Sequence[str], usage: Sequence[TeamUsage],
+                         prop_sheet_path: str, min_abs_edge_pct: float = 0.0) -> pd.DataFrame:
+    """`edge_finder.scan_props_for_matchup` (edge_finder.py:340-390): every line of the prop sheet
+    (`team, player, stat, yards`) that belongs to one of the two teams, priced from the histograms; rows the
+    simulation has nothing for are skipped, the rest sorted by |edge| then EV."""
+    cols = ["team", "player", "stat", "line", "best_side", "p_over", "p_under", "edge_pct", "ev_$100", "mean", "median", "samples"]
+    if not os.path.exists(prop_sheet_path):
+        return pd.DataFrame(columns=cols)
+    props = pd.read_csv(prop_sheet_path)
+    low = {t.lower() for t in team_names}
+    keep = props[props["team"].astype(str).str.lower().isin(low)]
+    rows = []
+    for _, r in keep.iterrows():
+        stat = _STAT_ALIASES.get(str(r["stat"]), str(r["stat"]))
+        try:
+            o = player_prop_odds_from_hist(hist2, team_names, usage, str(r["team"]), str(r["player"]), stat, float(r["yards"]))
+        except Exception:
+            continue
+        rows.append({"team": r["team"], "player": r["player"], "stat": stat, "line": float(r["yards"]),
+                     "best_side": o["best_side"], "p_over": o["p_over"], "p_under": o["p_under"], "edge_pct": o["edge"],
+                     "ev_$100": o["ev_per_$100"], "mean": o["mean"], "median": o["median"], "samples": o["samples"]})
+    if not rows:
+        return pd.DataFrame(columns=cols)
+    df = pd.DataFrame(rows)
+    df["abs_edge"] = df["edge_pct"].abs()
+    df = df.sort_values(["abs_edge", "ev_$100"], ascending=[False, False])
+    return df[df["abs_edge"] >= min_abs_edge_pct].drop(columns=["abs_edge"])

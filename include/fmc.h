@@ -122,6 +122,18 @@ typedef struct {
     uint64_t counts;
 } fmc_player_rec;
 
+/* Per-player histograms over the games of a launch (what edge_finder.player_prop_odds reads off `players_*`,
+ * edge_finder.py:168-231, without per-game rows; mergeable across GPUs by an integer all-reduce).  One record
+ * of FMC_PH_BINS uint32 per (matchup, team, slot); a game counts only if the name was sampled in it (the
+ * reference writes a row only then, FMC:1266-1299):
+ *   [0, FMC_PH_YDS_BINS)              yards rounded to one decimal exactly like Python's round(x, 1)
+ *                                     (FMC:1276, 1286, 1296): bin = tenths + FMC_PH_YDS_OFFSET, clamped
+ *   then 5 x FMC_PH_CNT_BINS          att|tgt, comp|rec, td, INT, sacks: bin = min(count, FMC_PH_CNT_BINS - 1) */
+#define FMC_PH_YDS_BINS 8192
+#define FMC_PH_YDS_OFFSET 1000   /* bin 1000 = 0.0 yards; range -100.0 .. +719.1 */
+#define FMC_PH_CNT_BINS 128
+#define FMC_PH_BINS (FMC_PH_YDS_BINS + 5 * FMC_PH_CNT_BINS)
+
 #define FMC_HIST_BINS 128        /* joint (points A, points B) histogram is FMC_HIST_BINS^2 per orientation */
 #define FMC_N_COUNTERS 32
 /* counters[] layout (totals over the call) */
@@ -129,7 +141,8 @@ enum {
     FMC_C_GAMES = 0, FMC_C_PLAYS, FMC_C_ITERS, FMC_C_PASS, FMC_C_COMP, FMC_C_INC, FMC_C_INT, FMC_C_SACK,
     FMC_C_RUN, FMC_C_TD, FMC_C_FGA, FMC_C_FG, FMC_C_PUNT, FMC_C_GO, FMC_C_HIST_OVERFLOW,
     FMC_C_ROUNDS, FMC_C_REQUESTS,
-    FMC_C_VISITS /* 8-byte node slots gathered for live requests (tree levels walked x lanes) */
+    FMC_C_VISITS, /* 8-byte node slots gathered for live requests (tree levels walked x lanes) */
+    FMC_C_PH_OVERFLOW /* player-histogram samples clamped into the first / last bin */
 };
 
 #define FMC_N_SLOTS 16           /* injected-draw record per (game, loop iteration); see DESIGN.md */
@@ -147,7 +160,8 @@ typedef struct {
     double *trace_dev;        /* optional per-iteration states [games][FMC_MAX_ITERS][FMC_TRACE_COLS] (test mode) */
     uint16_t *iters_dev;      /* optional [games] loop iterations of each game */
     void *stream;             /* cudaStream_t */
-    fmc_player_rec *players_dev; /* optional, only with fmc_set_usage: [games][2 teams A/B][n_slots], ZEROED by the caller */
+    fmc_player_rec *players_dev; /* optional, only with fmc_set_usage: [games][2 teams A/B][n_slots]; every line is written */
+    uint32_t *player_hist_dev;   /* optional, only with fmc_set_usage: [n_matchups][2][n_slots][FMC_PH_BINS], += (zero it first) */
 } fmc_sim_args;
 
 typedef struct fmc_ctx fmc_ctx;
@@ -195,7 +209,7 @@ int fmc_simulate_host(fmc_ctx *ctx, uint64_t seed, uint32_t *scores_host, uint32
 /* fmc_simulate_host plus the per-game player box [games][2][n_slots] (collect_players=True, FMC:1480-1505). */
 int fmc_simulate_players_host(fmc_ctx *ctx, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
                               uint64_t *counters_host, const double *stream_host, double *trace_host,
-                              uint16_t *iters_host, fmc_player_rec *players_host);
+                              uint16_t *iters_host, fmc_player_rec *players_host, uint32_t *player_hist_host);
 
 /* Raw margins of one model on n rows of the 17 numerics (play_model: first 12), NUM order of
  * FMC:676-682, float64 row-major [n][17]; out float64 [n][n_outputs].  Trees [tree_begin, tree_end)

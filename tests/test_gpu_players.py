@@ -184,3 +184,50 @@ def test_players_full_size_properties(engine, contexts):
         torch.cuda.synchronize()
         parts.append(b)
     assert torch.equal(torch.cat(parts, dim=0), box)
+
+
+def test_player_histograms_equal_box(engine, contexts):
+    """The device's per-player histograms (atomics at game end, yards rounded to tenths with the fma midpoint test)
+    equal the histograms the host builds from the per-game box with Python's round(x, 1)."""
+    n = 200_000
+    spec = _spec(contexts, "Kansas State", "Iowa State", n)
+    engine.set_matchups([spec])
+    r = engine.simulate_host(123, want_scores=False, want_hist=False, want_players=True, want_player_hist=True)
+    assert r["counters"]["ph_overflow"] == 0
+    want = usage.player_hist_from_box(r["players"], spec.usage)
+    got = r["player_hist"][0]
+    assert got.shape == want.shape == (2, engine.n_slots, usage.PH_BINS)
+    assert np.array_equal(got, want)
+    assert int(got[:, :, :usage.PH_YDS_BINS].sum()) > 10 * n
+    # prop odds from the histograms == from the rows
+    names = ("Kansas State", "Iowa State")
+    a = usage.player_prop_odds_from_box(r["players"], names, spec.usage, "Kansas State", "Blake Watson", "rush_yards", 45.5)
+    b = usage.player_prop_odds_from_hist(got, names, spec.usage, "Kansas State", "Blake Watson", "rush_yards", 45.5)
+    for k, v in a.items():
+        assert (abs(b[k] - v) < 1e-9) if isinstance(v, float) else (b[k] == v), k
+
+
+def test_simulate_slate_with_players(engine, contexts):
+    """api.simulate_slate in player mode: per-matchup player histograms (one launch for the slate) equal the
+    single-matchup runs; the prop sheet is priced from them."""
+    from fast_monte_carlo_b200 import api
+    sheet = os.path.join(GOLDEN, "players_focus.csv")
+    pairs = [("Kansas State", "Iowa State"), ("Ohio State", "Kansas State"), ("UTSA", "Texas")]
+    res = api.simulate_slate(pairs, n=1500, seed=17, engine=engine, focus_csv=sheet, usage_dir=GOLDEN)
+    assert res["_counters"]["games"] == 3 * 3000 and res["_counters"]["ph_overflow"] == 0
+    S = res[pairs[0]]["player_hist"].shape[1]
+    for m, (a, b) in enumerate(pairs):
+        e = res[(a, b)]
+        assert e["player_hist"].shape == (2, S, usage.PH_BINS) and e["games"] == 3000
+        spec = _spec(contexts, a, b, 3000)
+        if spec.usage[0].trivial and spec.usage[1].trivial:
+            assert int(e["player_hist"].sum()) == 0
+            continue
+        # same matchup index as in the slate (it is part of the Philox counter): m empty matchups in front
+        engine.set_matchups([MatchupSpec("pad", "pad", spec.sp_a, spec.sp_b, 0, 0, 0, 0, usage=spec.usage)] * m + [spec])
+        single = engine.simulate_host(17, want_scores=False, want_hist=False, want_player_hist=True)["player_hist"][m]
+        k = single.shape[1]
+        assert np.array_equal(e["player_hist"][:, :k].astype(np.uint32), single)
+    props = res[("Kansas State", "Iowa State")]["props"]
+    assert len(props) >= 10 and {"Taylen Green", "Carson Hansen"} <= set(props["player"])
+    assert len(res[("UTSA", "Texas")]["props"]) == 0                    # nobody tracked there

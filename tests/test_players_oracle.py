@@ -148,6 +148,15 @@ def test_unmodified_edge_finder_reads_our_players_file(models, oracle, contexts,
     props = ef.scan_props_for_matchup(stem, "Kansas State", "Iowa State", prop_sheet_path=sheet, directory=str(tmp_path),
                                       min_abs_edge_pct=0.0)
     assert len(props) >= 10 and {"Taylen Green", "Bo Nix"} <= set(props["player"])
+    ours = usage.scan_props_from_hist(usage.player_hist_from_box(r["players"], us), names, us, sheet)
+    assert len(ours) == len(props)
+    a = props.sort_values(["team", "player", "stat", "line"]).reset_index(drop=True)
+    b = ours.sort_values(["team", "player", "stat", "line"]).reset_index(drop=True)
+    for c in a.columns:
+        if a[c].dtype.kind == "f":
+            assert np.allclose(a[c].to_numpy(), b[c].to_numpy(), rtol=1e-9, atol=1e-9), c
+        else:
+            assert a[c].tolist() == b[c].tolist(), c
     with pytest.raises(ValueError):
         usage.player_prop_odds_from_box(r["players"], names, us, "Kansas State", "Nobody Here", "rush_yards", 10.5)
 
@@ -155,3 +164,33 @@ def test_unmodified_edge_finder_reads_our_players_file(models, oracle, contexts,
 def gold_cols():
     from fast_monte_carlo_b200.api import PLAYER_COLS
     return PLAYER_COLS
+
+
+def test_prop_odds_from_histograms_equal_from_rows(models, oracle, contexts):
+    """The per-player histograms (the form ranks merge with one all-reduce) answer every prop question exactly
+    like the per-game box / `players_*` rows do."""
+    ta, tb = contexts["Kansas State"], contexts["Iowa State"]
+    us = [usage.resolve_team(ta, models), usage.resolve_team(tb, models)]
+    n = 1500
+    r = oracle.simulate(oracle.make_config(models, ta.sp, tb.sp), n, seed=8, usage=oracle.make_usage(us),
+                        n_slots=max(len(u.slots) for u in us))
+    names = ("Kansas State", "Iowa State")
+    h = usage.player_hist_from_box(r["players"], us)
+    assert h.shape == (2, 8, usage.PH_BINS)
+    for t in (0, 1):
+        for s, (role, nm) in enumerate(us[t].slots):
+            rec = r["players"][:, t, s]
+            seen = int(((rec[:, 1] > 0) | (rec[:, 5] > 0)).sum())
+            assert int(h[t, s, :usage.PH_YDS_BINS].sum()) == seen
+            for stat, (rl, fld) in usage._STAT_FIELD.items():
+                if rl != role or seen == 0:
+                    continue
+                for line in (0.5, 2.5, 3.0, 40.5, 62.4, 180.5):
+                    a = usage.player_prop_odds_from_box(r["players"], names, us, names[t], nm, stat, line)
+                    b = usage.player_prop_odds_from_hist(h, names, us, names[t], nm, stat, line)
+                    assert set(a) == set(b)
+                    for k, v in a.items():
+                        if isinstance(v, float):
+                            assert abs(b[k] - v) <= 1e-9 * max(1.0, abs(v)), (nm, stat, line, k, b[k], v)
+                        else:
+                            assert b[k] == v, (nm, stat, line, k)
