@@ -231,3 +231,27 @@ def test_simulate_slate_with_players(engine, contexts):
     props = res[("Kansas State", "Iowa State")]["props"]
     assert len(props) >= 10 and {"Taylen Green", "Carson Hansen"} <= set(props["player"])
     assert len(res[("UTSA", "Texas")]["props"]) == 0                    # nobody tracked there
+
+
+def test_set_usage_error_paths(engine, contexts, models_s2):
+    """The C ABI's own checks (fmc_set_usage / fmc_simulate): capacity, order of calls, outputs without usage."""
+    import copy
+    from fast_monte_carlo_b200 import native
+    spec = _spec(contexts, "Kansas State", "Iowa State", 100)
+    engine.set_matchups([spec])
+    bad = copy.deepcopy(spec.usage[0])
+    g = models_s2["pass_stage1"].group("passer_name")
+    ru = bad.role["pass"]
+    ru.names = [g.categories[i] for i in range(5)]           # five passers the models know: one name row too many
+    ru.share = np.full(5, 0.2)
+    ru.slot = [-1] * 5
+    ru.col = {m: [models_s2[m].group("passer_name").column_of(nm) if m != "run_yards" else -1 for nm in ru.names]
+              for m in ru.col}
+    with pytest.raises(native.FmcError, match="names of one role"):
+        engine.ctx.set_usage([(bad, spec.usage[1])], 8)
+    with pytest.raises(native.FmcError, match="n_matchups differs"):
+        engine.ctx.set_usage([spec.usage, spec.usage], 8)
+    (ta, _), (tb, _) = contexts["UTSA"], contexts["Texas"]
+    engine.set_matchups([MatchupSpec("UTSA", "Texas", ta.sp, tb.sp, 10, 0, 10, 0)])
+    with pytest.raises(native.FmcError, match="set_usage"):
+        engine.simulate_host(1, want_players=True)

@@ -194,3 +194,25 @@ def test_prop_odds_from_histograms_equal_from_rows(models, oracle, contexts):
                             assert abs(b[k] - v) <= 1e-9 * max(1.0, abs(v)), (nm, stat, line, k, b[k], v)
                         else:
                             assert b[k] == v, (nm, stat, line, k)
+
+
+def test_usage_capacity_errors(models):
+    """Table limits of the kernels are reported by name, before anything is launched."""
+    rush = models["run_yards"].group("rusher_name").categories
+    known = [n for n in rush if n not in ("Unknown",)][:9]
+    tc = priors.TeamContext("X", 2025, 1, 1.0, 2.0, 3.0,
+                            rush_share=pd.DataFrame({"rusher_name": known, "share": [1.0 / 9] * 9}))
+    with pytest.raises(ValueError, match="rush names that the models have one-hot columns for"):
+        usage.resolve_team(tc, models)
+    many = [f"Walk On {i}" for i in range(33)]
+    tc = priors.TeamContext("X", 2025, 1, 1.0, 2.0, 3.0,
+                            rush_share=pd.DataFrame({"rusher_name": many, "share": [1.0] * 33}))
+    with pytest.raises(ValueError, match="usage entries"):
+        usage.resolve_team(tc, models)
+    ok = priors.TeamContext("X", 2025, 1, 1.0, 2.0, 3.0,
+                            rush_share=pd.DataFrame({"rusher_name": many[:32], "share": [1.0] * 32}))
+    assert usage.name_rows(usage.resolve_team(ok, models).role["rush"]) == [-1] * 32     # unknown names need no row
+    bad = priors.TeamContext("X", 2025, 1, 1.0, 2.0, 3.0,
+                             rush_share=pd.DataFrame({"rusher_name": ["A", "B"], "share": [0.0, 0.0]}))
+    with pytest.raises(ValueError, match="shares"):
+        usage.resolve_team(bad, models)
