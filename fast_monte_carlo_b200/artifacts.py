@@ -65,6 +65,7 @@ MODEL_IDS = {
     "run_yards": 3,
     "sack_yards": 4,
     "play_model": 5,
+    "play_binary": 5,  # play_model.json (16 features, FMC:319-337): shares the play-model slot with play_model.xgb
     "run_fumble": 6,
 }
 
@@ -251,7 +252,8 @@ def _logit(p: float) -> float:
 
 
 def _forest_from_xgb_learner(name: str, learner: dict, *, zero_is_missing: bool,
-                             groups: List[OneHotGroup], num_base: int, n_num: int) -> Forest:
+                             groups: List[OneHotGroup], num_base: int, n_num: int,
+                             categorical_code: Optional[int] = None) -> Forest:
     """Re-lay one XGBoost `learner` dict (JSON or UBJSON, same keys) as a Forest.
 
     Semantics restated in SURVEY Appendix D.1: node i is a leaf iff left_children[i] == -1, leaf
@@ -289,10 +291,25 @@ def _forest_from_xgb_learner(name: str, learner: dict, *, zero_is_missing: bool,
         d = np.asarray(t["default_left"], dtype=np.uint8)
         st = np.asarray(t.get("split_type", np.zeros_like(lc)), dtype=np.int64)
         sh = np.asarray(t.get("sum_hessian", np.zeros_like(sc)), dtype=np.float64)
-        if np.any(st != 0):
-            raise NotImplementedError(f"{name}: categorical splits are not supported (SURVEY 8f row 3)")
         n = lc.shape[0]
         leaf = lc < 0
+        if np.any(st != 0):
+            # Categorical split (XGBoost common/categorical.h `Decision`): a row goes RIGHT iff its category is
+            # in the node's set.  Supported only where the row's category code is a known constant
+            # (`categorical_code`): the node becomes a numeric test on a column that always holds 0.0,
+            # threshold -1 (0 < -1 false -> right) when the code is in the set, +1 (-> left) otherwise.
+            if categorical_code is None:
+                raise NotImplementedError(f"{name}: categorical splits need a constant category code (SURVEY 8f row 3)")
+            cats = np.asarray(t.get("categories", []), dtype=np.int64)
+            cnodes = np.asarray(t.get("categories_nodes", []), dtype=np.int64)
+            cseg = np.asarray(t.get("categories_segments", []), dtype=np.int64)
+            csz = np.asarray(t.get("categories_sizes", []), dtype=np.int64)
+            sc = sc.copy()
+            for j, node in enumerate(cnodes):
+                members = set(int(x) for x in cats[cseg[j]:cseg[j] + csz[j]])
+                sc[node] = -1.0 if int(categorical_code) in members else 1.0
+            if np.any((st != 0) & ~np.isin(np.arange(n), cnodes) & ~leaf):
+                raise ValueError(f"{name}: categorical node without a category set")
         if not np.all(rc[~leaf] == lc[~leaf] + 1):
             raise ValueError(f"{name}: right child is not left+1")
         roots.append(off)
@@ -374,6 +391,56 @@ def load_play_model_xgb(path: str, scaler_path: Optional[str], coach_encoder_pat
         if [str(c) for c in le.classes_] != coach_names:
             raise ValueError("coach_label_encoder.pkl does not match play_model.xgb coach columns")
     fo.extra["classes"] = list(PLAY_CLASSES)
+    return fo
+
+
+def load_play_model_json(path: str, features_path: str, label_encoder_path: str,
+                         calibration_path: Optional[str] = None) -> Forest:
+    """play_model.json: the binary PASS/RUN booster of train_run_pass.py (multi:softprob over the classes of
+    label_encoder.pkl, 16 features of features.pkl incl. the categorical `head_coach`), loaded at FMC:319-337 and
+    evaluated by `play_call_pass_prob_binary` (FMC:407-427).
+
+    The forest is re-laid in the canonical numeric order (NUM_FEATURES, columns 0..16) with `head_coach` as column
+    17.  The reference feeds `pd.Categorical([coach])` -- ONE category, so the category code the booster sees is 0
+    for every team (FMC:310-313); numeric splits on that column therefore see 0.0 and categorical splits fold on
+    code 0.  DataFrame-fed DMatrix: zeros are values, not missing."""
+    _install_sklearn_shims()
+    import joblib
+    with open(path, "r") as f:
+        learner = json.load(f)["learner"]
+    names = [str(c) for c in joblib.load(features_path)]
+    classes = [str(c) for c in joblib.load(label_encoder_path).classes_]
+    temp = 1.0
+    if calibration_path and os.path.exists(calibration_path):
+        with open(calibration_path, "r") as f:
+            temp = float(json.load(f).get("temperature", 1.0))
+    return play_binary_from_learner(learner, names, classes, temp)
+
+
+def play_binary_from_learner(learner: dict, names: List[str], classes: List[str], temperature: float = 1.0) -> Forest:
+    """The `learner` dict of play_model.json + the contents of features.pkl / label_encoder.pkl -> Forest."""
+    if int(learner["learner_model_param"]["num_feature"]) != len(names):
+        raise ValueError("play_model.json: num_feature does not match features.pkl")
+    if "pass" not in classes:
+        raise ValueError("label_encoder.pkl has no 'pass' class")
+    remap = np.zeros(len(names), dtype=np.int64)
+    for c, nm in enumerate(names):
+        if nm in NUM_FEATURES:
+            remap[c] = NUM_FEATURES.index(nm)
+        elif nm == "head_coach":
+            remap[c] = N_NUM
+        else:
+            raise ValueError(f"play_model.json: unknown feature {nm!r}")
+    fo = _forest_from_xgb_learner("play_binary", learner, zero_is_missing=False,
+                                  groups=[OneHotGroup("head_coach", N_NUM, ["<category code 0>"])],
+                                  num_base=0, n_num=N_NUM, categorical_code=0)
+    internal = fo.left >= 0
+    fo.feat = np.where(internal, remap[np.where(internal, fo.feat, 0)], -1).astype(np.int32)
+    fo.n_features = N_NUM + 1
+    if fo.n_outputs != len(classes):
+        raise ValueError("play_model.json: num_class does not match label_encoder.pkl")
+    fo.extra.update(classes=list(classes), pass_class=classes.index("pass"), temperature=float(temperature),
+                    features=list(names))
     return fo
 
 
@@ -538,6 +605,9 @@ def compile_reference_dir(d: str, *, stage2_json: Optional[str] = None) -> Model
     if os.path.exists(j("play_model.xgb")):
         forests["play_model"] = load_play_model_xgb(j("play_model.xgb"), j("scaler.pkl"),
                                                     j("coach_label_encoder.pkl"))
+    if os.path.exists(j("play_model.json")) and os.path.exists(j("features.pkl")) and os.path.exists(j("label_encoder.pkl")):
+        forests["play_binary"] = load_play_model_json(j("play_model.json"), j("features.pkl"), j("label_encoder.pkl"),
+                                                      j("calibration.json"))
     if os.path.exists(j("run_fumble.json")):
         forests["run_fumble"] = load_xgb_json(
             j("run_fumble.json"), "run_fumble",

@@ -234,6 +234,7 @@ extern "C" int fmc_create(int device, fmc_ctx **out) {
     }
     std::memset(&c->params, 0, sizeof(c->params));
     c->params.play_temp = 1.0;
+    c->params.pass_class = 1;
     c->params.qy_noise = 0.5;
     c->params.stage2_standin[0] = (double)0.78f;
     c->params.stage2_standin[1] = (double)0.05f;
@@ -300,6 +301,7 @@ extern "C" int fmc_set_params(fmc_ctx *c, const fmc_params *p) {
     if (!c || !p) return fail(FMC_ERR_INVALID, "fmc_set_params: bad argument");
     if (p->policy < 0 || p->policy > 1 || p->sampler < 0 || p->sampler > 1 || p->stage2_mode < 0 || p->stage2_mode > 1)
         return fail(FMC_ERR_INVALID, "fmc_set_params: unknown mode");
+    if (p->pass_class < 0 || p->pass_class > 4) return fail(FMC_ERR_INVALID, "fmc_set_params: pass_class out of range");
     c->params = *p;
     c->tables_dirty = true;
     return FMC_OK;
@@ -533,6 +535,9 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
     a.root_stream = c->sim_tables.d_stream; a.consts = c->sim_tables.d_consts;
     a.seed_lo = (uint32_t)g->seed; a.seed_hi = (uint32_t)(g->seed >> 32);
     a.policy = c->params.policy; a.sampler = c->params.sampler; a.stage2_mode = c->params.stage2_mode;
+    a.pass_class = c->params.pass_class;
+    if (a.policy == 1 && a.pass_class >= c->forest[FMC_PLAY_MODEL].n_outputs)
+        return fail(FMC_ERR_INVALID, "fmc_simulate: pass_class is not a class of the play model");
     a.play_temp = (float)c->params.play_temp; a.qy_noise = c->params.qy_noise;
     for (int k = 0; k < 3; ++k) a.standin[k] = c->params.stage2_standin[k];
     const HostForest &pm = c->forest[FMC_PLAY_MODEL];

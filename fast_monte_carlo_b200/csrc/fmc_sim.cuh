@@ -78,6 +78,7 @@ struct SimKernelArgs {
     const uint2 *consts;               // constants side streams
     uint32_t seed_lo, seed_hi;
     int policy, sampler, stage2_mode;
+    int pass_class;                    // index of "pass" among the play model's classes (FMC:423)
     float play_temp;
     double qy_noise;
     double standin[3];
@@ -405,6 +406,19 @@ __device__ __forceinline__ void call_run(Lane &L, const SimKernelArgs &a, const 
     credit(a, M, L, team, 1, L.p1, PC_ATT, false, 0.0);
 }
 
+// FMC:420-425: float32 softmax of the play model's margins / T; returns exp of the "pass" class and the sum.
+// Out of line: only the model policies reach it, and its registers stay out of the heuristic path.
+__device__ __noinline__ void play_softmax(const float *m, int nc, int pass_class, float temp, float &e_pass, float &sum) {
+    float zv[5], zmax = 0.f;
+    sum = 0.f; e_pass = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k < nc) { zv[k] = m[k] / temp; if (k == 0 || zv[k] > zmax) zmax = zv[k]; }
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+        if (k < nc) { const float e = expf_cr(zv[k] - zmax); sum += e; if (k == pass_class) e_pass = e; }
+}
+
 // Advance one lane until it posts a request (returns key = family * 2 + offense) or has nothing
 // left to do (returns -1).  `res` points at this lane's result record of the previous round.
 template <bool TEST, bool PLAYERS>
@@ -515,12 +529,8 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
         const double ytg0 = L.ytg;
         if (L.stage == ST_WAIT_PM) {
             // FMC:420-425: float32 softmax of margins / T, P(pass) clipped to [.02, .98]
-            const float *m = reinterpret_cast<const float *>(res);
-            float zv[5], zmax = 0.f, sum = 0.f, e1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) { zv[k] = m[k] / a.play_temp; if (k == 0 || zv[k] > zmax) zmax = zv[k]; }
-#pragma unroll
-            for (int k = 0; k < 5; ++k) { const float e = expf_cr(zv[k] - zmax); sum += e; if (k == 1) e1 = e; }
+            float e1, sum;
+            play_softmax(reinterpret_cast<const float *>(res), M.tbl[5][team].n_outputs, a.pass_class, a.play_temp, e1, sum);
             const double p_pass = softclip((double)(e1 / sum), 0.02, 0.98);
             double a0 = 1.0 - p_pass, a1 = p_pass;
             const double s = a0 + a1;
@@ -678,6 +688,10 @@ __device__ __forceinline__ void write_features(float *col, const Lane &L, int fa
             if (a.pm_scaled[k]) v[k] = (float)((raw[k] - a.pm_mean[k]) / a.pm_scale[k]);
 #pragma unroll
         for (int k = 0; k < 6; ++k) col[k * 32] = v[k];
+        // play_model.json also splits on goal_to_go, fourth_and_short, fg_range (features.pkl)
+        col[6 * 32] = (L.dist >= (L.ytg - 0.5)) ? 1.f : 0.f;
+        col[7 * 32] = (L.down == 4 && L.dist <= 2.0) ? 1.f : 0.f;
+        col[8 * 32] = (L.ytg <= 33.0) ? 1.f : 0.f;
         return;
     }
     const bool zm = fam <= 1;   // CSR-fed boosters: exact zero == missing

@@ -42,18 +42,24 @@ class MatchupSpec:
 class Engine:
     def __init__(self, models: Optional[art.ModelSet] = None, *, device: int = 0,
                  policy: str = "heuristic", sampler: str = "normal", stage2: str = "auto",
-                 play_temp: float = 1.0, qy_noise: float = 0.5,
+                 play_temp: Optional[float] = None, qy_noise: float = 0.5,
                  stage2_standin: Sequence[float] = (0.78, 0.05, 0.17), player: str = "Unknown"):
         self.models = models if models is not None else art.load_default_models()
         self.ctx = native.Context(device)
         self.player = player
-        for name in SIM_MODELS + ("run_fumble",):
+        if policy == "play_json" and "play_binary" not in self.models:
+            raise ValueError("policy='play_json' but the model set has no play_binary forest (play_model.json + "
+                             "features.pkl + label_encoder.pkl in FMC_MODEL_DIR)")
+        # the play-model slot holds ONE forest: play_model.json (policy 'play_json', what FMC:319-337 loads) or
+        # play_model.xgb (policy 'play_model')
+        play_name = "play_binary" if policy == "play_json" else "play_model"
+        for name in SIM_MODELS[:-1] + (play_name, "run_fumble"):
             if name in self.models:
                 f = self.models[name]
                 mid = art.MODEL_IDS[name]
                 self.ctx.load_forest(mid, f)
                 cols = [-1, -1]
-                if name != "play_model":
+                if name not in ("play_model", "play_binary"):
                     for gi, g in enumerate(f.groups[:2]):
                         cols[gi] = g.column_of(player)
                 self.ctx.set_active_columns(mid, cols[0], cols[1])
@@ -64,7 +70,15 @@ class Engine:
         if policy == "play_model" and "play_model" not in self.models:
             raise ValueError("policy='play_model' but the model set has no play_model forest")
         self.policy, self.sampler, self.stage2 = policy, sampler, stage2
-        self.ctx.set_params(policy={"heuristic": 0, "play_model": 1}[policy],
+        pass_class = 1
+        if policy == "play_json":
+            pass_class = int(self.models["play_binary"].extra["pass_class"])
+            if play_temp is None:
+                play_temp = float(self.models["play_binary"].extra.get("temperature", 1.0))   # calibration.json
+        if play_temp is None:
+            play_temp = 1.0
+        self.play_temp = float(play_temp)
+        self.ctx.set_params(policy={"heuristic": 0, "play_model": 1, "play_json": 1}[policy], pass_class=pass_class,
                             sampler={"normal": 0, "quantile_interp": 1}[sampler],
                             stage2_mode={"standin": 0, "booster": 1}[stage2],
                             play_temp=play_temp, qy_noise=qy_noise, stage2_standin=stage2_standin)
@@ -72,8 +86,8 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------
     def coach_col(self, team: str) -> int:
-        if "play_model" not in self.models:
-            return -1
+        if self.policy == "play_json" or "play_model" not in self.models:
+            return -1      # play_model.json: the category code the booster sees is 0 for every team (FMC:310-313)
         g = self.models["play_model"].group("coach")
         return g.column_of(HEAD_COACH_MAP.get(team)) if g is not None else -1
 

@@ -48,7 +48,7 @@ class ForestDesc(C.Structure):
 
 class Params(C.Structure):
     _fields_ = [
-        ("policy", C.c_int32), ("sampler", C.c_int32), ("stage2_mode", C.c_int32), ("reserved", C.c_int32),
+        ("policy", C.c_int32), ("sampler", C.c_int32), ("stage2_mode", C.c_int32), ("pass_class", C.c_int32),
         ("play_temp", C.c_double), ("qy_noise", C.c_double), ("stage2_standin", C.c_double * 3),
     ]
 
@@ -301,9 +301,10 @@ class Context:
         _check(self._L.fmc_set_active_columns(self._h, int(model_id), int(col0), int(col1)))
 
     def set_params(self, *, policy=0, sampler=0, stage2_mode=0, play_temp=1.0, qy_noise=0.5,
-                   stage2_standin=(0.78, 0.05, 0.17)) -> None:
+                   stage2_standin=(0.78, 0.05, 0.17), pass_class=1) -> None:
         p = Params()
         p.policy = int(policy); p.sampler = int(sampler); p.stage2_mode = int(stage2_mode)
+        p.pass_class = int(pass_class)
         p.play_temp = float(play_temp); p.qy_noise = float(qy_noise)
         for k in range(3):
             p.stage2_standin[k] = float(np.float32(stage2_standin[k]))   # inplace_predict returns float32

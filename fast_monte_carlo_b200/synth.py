@@ -108,3 +108,84 @@ def xgb_json_dict(f: art.Forest) -> dict:
                                  num_class=str(f.n_outputs if f.n_outputs > 1 else 0),
                                  num_feature=str(f.n_features), num_target="1"),
         objective=dict(name=objective)), version=[3, 0, 4])
+
+
+# ----------------------------------------------------------------------------------------------
+# play_model.json (the binary PASS/RUN booster of train_run_pass.py) is not in the reference snapshot either.
+# ----------------------------------------------------------------------------------------------
+PLAY_JSON_FEATURES = ["down", "distance", "yardsToGoal", "is_red_zone", "score_diff", "seconds_remaining",
+                      "offenseTimeouts", "defenseTimeouts", "sp_rating_off", "sp_offense_rating_off",
+                      "sp_defense_rating_def", "sp_rating_def", "head_coach", "goal_to_go", "fourth_and_short",
+                      "fg_range"]                      # features.pkl
+
+
+def synthetic_play_model_json(seed: int = 7, rounds: int = 60, max_depth: int = 6) -> dict:
+    """A booster of the trained SHAPE of play_model.json (train_run_pass.py:171-199: multi:softprob, 2 classes
+    [pass, run], max_depth 6, 16 features with the categorical `head_coach`), in the XGBoost JSON schema, with
+    random split structure: numeric splits on the 15 numerics at plausible raw thresholds and categorical
+    splits on `head_coach` (split_type 1, category sets that do / do not contain code 0).  NOT a trained model."""
+    rng = np.random.default_rng(seed)
+    n_feat = len(PLAY_JSON_FEATURES)
+
+    def threshold(c):
+        nm = PLAY_JSON_FEATURES[c]
+        if nm == "down":
+            return float(rng.choice([1.5, 2.5, 3.5]))
+        if nm == "distance":
+            return float(np.round(rng.uniform(0.5, 15.0), 2))
+        if nm == "yardsToGoal":
+            return float(np.round(rng.uniform(1.0, 99.0), 1))
+        if nm == "score_diff":
+            return float(rng.integers(-21, 22)) + float(rng.choice([0.0, 0.5]))   # incl. thresholds exactly at 0
+        if nm == "seconds_remaining":
+            return float(rng.integers(30, 3600))
+        if nm in ("offenseTimeouts", "defenseTimeouts"):
+            return float(rng.choice([1.5, 2.5, 3.0]))
+        if nm.startswith("sp_"):
+            return float(np.round(rng.uniform(-25.0, 45.0), 1))
+        return 0.5                                      # 0/1 flags
+
+    trees, info = [], []
+    for r in range(rounds):
+        for k in range(2):
+            lc, rc, si, sc, dl, st = [], [], [], [], [], []
+            cats, cnodes, cseg, csz = [], [], [], []
+            depth_of = [0]
+            lc.append(-1); rc.append(-1); si.append(0); sc.append(0.0); dl.append(0); st.append(0)
+            i = 0
+            while i < len(lc):
+                d = depth_of[i]
+                if d < max_depth and rng.random() < (0.95 if d < 2 else 0.62):
+                    c = int(rng.integers(0, n_feat))
+                    a = len(lc)
+                    for _ in range(2):
+                        lc.append(-1); rc.append(-1); si.append(0); sc.append(0.0); dl.append(0); st.append(0)
+                        depth_of.append(d + 1)
+                    lc[i], rc[i], si[i], dl[i] = a, a + 1, c, int(rng.integers(0, 2))
+                    if PLAY_JSON_FEATURES[c] == "head_coach":
+                        st[i] = 1
+                        members = sorted(set(int(x) for x in rng.integers(0, 6, size=int(rng.integers(1, 4)))))
+                        cnodes.append(i); cseg.append(len(cats)); csz.append(len(members)); cats.extend(members)
+                        sc[i] = float(len(members))
+                    else:
+                        sc[i] = threshold(c)
+                else:
+                    sc[i] = float(np.float32(rng.normal(0.0, 0.15) + (0.1 if k == 0 else -0.1) * (r == 0)))
+                i += 1
+            trees.append(dict(left_children=lc, right_children=rc, split_indices=si,
+                              split_conditions=[float(np.float32(x)) for x in sc], default_left=dl, split_type=st,
+                              categories=cats, categories_nodes=cnodes, categories_segments=cseg, categories_sizes=csz,
+                              sum_hessian=[1.0] * len(lc), base_weights=[float(np.float32(x)) for x in sc],
+                              tree_param=dict(num_nodes=str(len(lc)), num_feature=str(n_feat))))
+            info.append(k)
+    return dict(learner=dict(
+        attributes=dict(best_iteration=str(rounds - 1)),
+        feature_names=list(PLAY_JSON_FEATURES),
+        feature_types=["c" if n == "head_coach" else ("float" if n in ("distance", "yardsToGoal") or n.startswith("sp_") else "int")
+                       for n in PLAY_JSON_FEATURES],
+        gradient_booster=dict(name="gbtree", model=dict(
+            gbtree_model_param=dict(num_parallel_tree="1", num_trees=str(len(trees))),
+            iteration_indptr=list(range(0, len(trees) + 1, 2)), tree_info=info, trees=trees)),
+        learner_model_param=dict(base_score="5E-1", boost_from_average="1", num_class="2",
+                                 num_feature=str(n_feat), num_target="1"),
+        objective=dict(name="multi:softprob")), version=[3, 0, 4])

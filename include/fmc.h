@@ -76,13 +76,16 @@ typedef struct {
 /* Engine switches.  Defaults (all zero except the doubles noted) reproduce FMC as shipped. */
 typedef struct {
     int32_t policy;       /* 0: pass_prob_v1 heuristic (FMC:719-735, the path taken when play_model.json is
-                                absent, FMC:326-328);  1: softmax(play_model.xgb margins / T)[pass] (FMC:420-425) */
+                                absent, FMC:326-328);  1: softmax(margins / T)[pass] of the forest loaded as
+                                FMC_PLAY_MODEL (FMC:420-425): play_model.json re-laid by the artifact compiler
+                                (2 classes, 16 features) or play_model.xgb (5 classes, 180 features) */
     int32_t sampler;      /* 0: Normal(q50, (q90-q10)/2.56) sampler FMC:817-852;
                                 1: sim_helpers.QuantileYards.sample (sim_helpers.py:32-38) */
     int32_t stage2_mode;  /* 0: fixed raw probabilities `stage2_standin` (the booster is missing from the
                                 reference snapshot);  1: evaluate FMC_PASS_STAGE2 */
-    int32_t reserved;
-    double play_temp;     /* _PLAY_TEMP, FMC:50 (default 1.0) */
+    int32_t pass_class;   /* policy 1: index of "pass" among the model's classes (label_encoder.pkl order, FMC:333, 423;
+                                0 for play_model.json's [pass, run], 1 for play_model.xgb) */
+    double play_temp;     /* _PLAY_TEMP, FMC:50 / calibration.json FMC:335-337 (default 1.0) */
     double qy_noise;      /* sim_helpers noise (default 0.5) */
     double stage2_standin[3]; /* raw [incomplete, intercepted, sack] before the nudges of FMC:764-770 */
 } fmc_params;

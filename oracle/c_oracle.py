@@ -21,7 +21,7 @@ SLOT = dict(U_call=0, U_comp=1, Z_yards=2, U_ex=3, U_boost=4, U_fin=5, U_s2=6, Z
             U_go=8, U_fg=9, Z_gross=10, Z_ret=11, U_tb=12, U_p1=13, U_wr=14, U_yq=15)
 NORMAL_SLOTS = (2, 7, 10, 11)
 MODEL_IDS = {"pass_stage1": 0, "pass_stage2": 1, "pass_yards": 2, "run_yards": 3, "sack_yards": 4,
-             "play_model": 5, "run_fumble": 6}
+             "play_model": 5, "play_binary": 5, "run_fumble": 6}
 COUNTER_NAMES = ("plays", "iters", "pass", "comp", "inc", "int", "sack", "run", "td", "fga", "fg", "punt", "go")
 STAGE2_STANDIN = tuple(float(np.float32(x)) for x in (0.78, 0.05, 0.17))
 
@@ -37,6 +37,7 @@ class FoConfig(C.Structure):
         ("qy_noise", C.c_double),
         ("stage2_mode", C.c_int),
         ("standin", C.c_double * 3),
+        ("pass_class", C.c_int),
     ]
 
 
@@ -107,9 +108,13 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def load_models(ms) -> None:
+def load_models(ms, play: str = "play_model") -> None:
+    """`play`: which forest occupies the play-model slot: "play_model" (play_model.xgb) or "play_binary"
+    (play_model.json)."""
     L = lib()
     for name, f in ms.forests.items():
+        if name in ("play_model", "play_binary") and name != play:
+            continue
         mid = MODEL_IDS[name]
         base = np.ascontiguousarray(f.base_margin, dtype=np.float64)
         arrs = dict(feat=np.ascontiguousarray(f.feat, np.int32), thr=np.ascontiguousarray(f.thr, np.float32),
@@ -144,7 +149,7 @@ def predict(name: str, num17: np.ndarray, active: np.ndarray, n_outputs: int,
 
 
 def make_config(ms, spA, spB, *, policy="heuristic", coach_cols=(-1, -1), play_temp=1.0, sampler="normal",
-                qy_noise=0.5, stage2="standin", player="Unknown") -> FoConfig:
+                qy_noise=0.5, stage2="standin", player="Unknown", pass_class=None) -> FoConfig:
     cfg = FoConfig()
     for t, sp in enumerate((spA, spB)):
         for k in range(3):
@@ -157,7 +162,12 @@ def make_config(ms, spA, spB, *, policy="heuristic", coach_cols=(-1, -1), play_t
                     cols[gi] = g.column_of(player)
         cfg.active[mid][0], cfg.active[mid][1] = cols
     cfg.coach_col[0], cfg.coach_col[1] = int(coach_cols[0]), int(coach_cols[1])
-    cfg.policy = {"heuristic": 0, "play_model": 1}[policy]
+    cfg.policy = {"heuristic": 0, "play_model": 1, "play_json": 1}[policy]
+    if pass_class is None:
+        pass_class = ms["play_binary"].extra["pass_class"] if policy == "play_json" else 1
+    cfg.pass_class = int(pass_class)
+    if policy == "play_json":
+        coach_cols = (-1, -1)
     cfg.play_temp = float(play_temp)
     cfg.sampler = {"normal": 0, "quantile_interp": 1}[sampler]
     cfg.qy_noise = float(qy_noise)
@@ -193,6 +203,13 @@ def simulate(cfg: FoConfig, n: int, *, game0: int = 0, matchup: int = 0, stream:
     assert rc == 0, rc
     return dict(scores=scores, iters=iters, trace=tr, players=players,
                 counters={k: int(counters[i]) for i, k in enumerate(COUNTER_NAMES)})
+
+
+def play_pass_prob(cfg: FoConfig, off: int, down: int, dist: float, ytg: float, sd: int, sec: int) -> float:
+    L = lib()
+    L.fo_play_pass_prob.restype = C.c_double
+    L.fo_play_pass_prob.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int]
+    return float(L.fo_play_pass_prob(C.byref(cfg), int(off), int(down), float(dist), float(ytg), int(sd), int(sec)))
 
 
 def philox(ctr, key):

@@ -50,6 +50,7 @@ class Booster:
             self.learner = json.load(f)["learner"]
         m = self.learner["gradient_booster"]["model"]
         self._trees = []
+        self._cats = []          # per tree: {node: set of categories that go RIGHT} (common/categorical.h Decision)
         for t in m["trees"]:
             self._trees.append((
                 np.asarray(t["left_children"], dtype=np.int64),
@@ -58,6 +59,12 @@ class Booster:
                 np.asarray(t["split_conditions"], dtype=np.float64).astype(np.float32),
                 np.asarray(t["default_left"], dtype=np.int64),
             ))
+            sets = {}
+            cats = t.get("categories", [])
+            for j, node in enumerate(t.get("categories_nodes", [])):
+                a, n = t["categories_segments"][j], t["categories_sizes"][j]
+                sets[int(node)] = set(int(c) for c in cats[a:a + n])
+            self._cats.append(sets)
         self._tree_info = list(m["tree_info"])
         lmp = self.learner["learner_model_param"]
         self._n_class = max(1, int(lmp.get("num_class", "0")))
@@ -75,11 +82,14 @@ class Booster:
         tree_end = len(self._trees) if tree_end is None else tree_end
         for t in range(tree_begin, tree_end):
             lc, rc, si, sc, dl = self._trees[t]
+            cat_sets = self._cats[t]
             i = 0
             while lc[i] != -1:
                 v = present.get(int(si[i]))
                 if v is None:
                     i = lc[i] if dl[i] else rc[i]
+                elif i in cat_sets:      # categorical split: a category in the node's set goes right
+                    i = rc[i] if int(v) in cat_sets[i] else lc[i]
                 else:
                     i = lc[i] if v < sc[i] else rc[i]
             k = self._tree_info[t]
@@ -121,7 +131,15 @@ class Booster:
 
     def predict(self, dmat, output_margin=False, iteration_range=None, **kw):
         X = dmat.data if isinstance(dmat, DMatrix) else dmat
-        if hasattr(X, "to_numpy"):
+        if hasattr(X, "dtypes") and hasattr(X, "columns"):
+            # DataFrame (enable_categorical=True): a categorical column is presented by its category CODE
+            cols = []
+            for c in X.columns:
+                col = X[c]
+                cols.append(col.cat.codes.to_numpy(dtype=np.float64) if str(col.dtype) == "category"
+                            else col.to_numpy(dtype=np.float64))
+            X = np.stack(cols, axis=1)
+        elif hasattr(X, "to_numpy"):
             X = X.to_numpy(dtype=np.float64)
         tb, te = 0, None
         if iteration_range is not None and iteration_range != (0, 0):

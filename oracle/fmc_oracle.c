@@ -88,6 +88,9 @@ typedef struct {
     double qy_noise;             /* sim_helpers noise (default 0.5) */
     int stage2_mode;             /* 0 = stand-in probabilities, 1 = booster FO_PASS_STAGE2 */
     double standin[3];           /* raw [incomplete, intercepted, sack] as float32-exact doubles */
+    int pass_class;              /* policy 1: index of "pass" among the play model's classes: 1 for play_model.xgb
+                                    ([field_goal, pass, punt, run, timeout]), label_encoder.pkl order for
+                                    play_model.json ([pass, run] -> 0; FMC:333, 423) */
 } FoConfig;
 
 /* Usage tables of one team (TeamContext.qb_share / rush_share / target_share, FMC:262-264) reduced to what
@@ -515,6 +518,12 @@ static double play_call_pass_prob(const FoGame *G, const FoState *s, int sd) {
     r.num[0] = (double)s->down; r.num[1] = s->dist; r.num[2] = s->ytg; r.num[3] = (s->ytg <= 20) ? 1.0 : 0.0;
     r.num[4] = (double)sd; r.num[5] = (double)s->sec; r.num[6] = 3.0; r.num[7] = 3.0;
     r.num[8] = c->sp[off][0]; r.num[9] = c->sp[off][1]; r.num[10] = c->sp[de][2]; r.num[11] = c->sp[de][0];
+    /* play_model.json also reads goal_to_go, fourth_and_short, fg_range (features.pkl; FMC:1015-1017) */
+    r.num[12] = (s->dist >= (s->ytg - 0.5)) ? 1.0 : 0.0;
+    r.num[13] = (s->down == 4 && s->dist <= 2.0) ? 1.0 : 0.0;
+    r.num[14] = (s->ytg <= 33) ? 1.0 : 0.0;
+    r.num[15] = (s->sec > 1800) ? 1.0 : 2.0;
+    r.num[16] = ((s->sec % 1800) <= 120) ? 1.0 : 0.0;
     for (int i = 0; i < f->n_scaled; ++i) {
         int k = f->scaler_cols[i];
         r.num[k] = (r.num[k] - f->scaler_mean[i]) / f->scaler_scale[i];
@@ -526,7 +535,7 @@ static double play_call_pass_prob(const FoGame *G, const FoState *s, int sd) {
     float T = (float)c->play_temp, zmax = 0.0f, sum = 0.0f;
     for (int k = 0; k < f->n_outputs; ++k) { z[k] = (float)m[k] / T; if (k == 0 || z[k] > zmax) zmax = z[k]; }
     for (int k = 0; k < f->n_outputs; ++k) { e[k] = expf_cr(z[k] - zmax); sum += e[k]; }
-    double p = (double)(e[1] / sum);       /* class order [field_goal, pass, punt, run, timeout] */
+    double p = (double)(e[c->pass_class] / sum);
     return softclip(p, 0.02, 0.98);
 }
 
@@ -860,6 +869,16 @@ double fo_pass_prob_v1(int down, double distance, double ytg, int sec, int sd) {
 double fo_go_for_it_prob(double ytg, double dist, int sd, int sec) { return go_for_it_prob(ytg, dist, sd, sec); }
 double fo_field_goal_prob(double d) { return field_goal_prob(d); }
 /* out = {matchup_bias, yardage_multiplier, mismatch_z, explosive_prob(ytg), rz_finish_prob_pass, rz_finish_prob_run} */
+/* P(pass) of play_call_pass_prob_binary (FMC:407-427) for one state; `off` = team index on offense */
+double fo_play_pass_prob(const FoConfig *cfg, int off, int down, double dist, double ytg, int sd, int sec) {
+    FoGame G;
+    game_constants(&G, cfg);
+    FoState s;
+    memset(&s, 0, sizeof(s));
+    s.offense = off; s.down = down; s.dist = dist; s.ytg = ytg; s.sec = sec;
+    return play_call_pass_prob(&G, &s, sd);
+}
+
 void fo_modifiers(double off_offense, double def_defense, double ytg, int down, double *out) {
     FoConfig c;
     FoGame G;
