@@ -70,7 +70,8 @@ def test_reference_golden_players(engine, contexts):
         assert got[c].tolist() == want[c].tolist(), c
 
 
-@pytest.mark.parametrize("a,b", [("Kansas State", "Iowa State"), ("UTSA", "Iowa State"), ("Ohio State", "Kansas State")])
+@pytest.mark.parametrize("a,b", [("Kansas State", "Iowa State"), ("UTSA", "Iowa State"), ("Ohio State", "Kansas State"),
+                                 ("Ohio State", "UTSA")])
 def test_players_injected_stream_vs_oracle(engine, oracle, models_s2, contexts, a, b):
     """Ohio State: usage from the fallback files (21 rushers, 12 targets, most of them unknown to every model)."""
     n = 4096
@@ -85,7 +86,10 @@ def test_players_injected_stream_vs_oracle(engine, oracle, models_s2, contexts, 
     t0, t1 = got["trace"], ref["trace"]
     assert bool(((t0 == t1) | (np.isnan(t0) & np.isnan(t1))).all())
     assert np.array_equal(got["players"].dense(), ref["players"])          # float64 yards bit for bit
-    assert got["players"].dense()[..., 1].sum() > n                          # something was tracked
+    if engine.n_slots:
+        assert got["players"].dense()[..., 1].sum() > n                      # something was tracked
+    else:                                                                    # usage files only: names matter, no box
+        assert got["players"].dense().shape == (n, 2, 0, 6) and engine.ctx.has_usage
     assert len(contexts["Ohio State"][1].role["rush"].names) == 21 and not contexts["Ohio State"][1].slots
 
 
