@@ -170,6 +170,30 @@ struct Draws {
     const SimKernelArgs &a;
     const double *rec;        // injected record base for this game (or nullptr)
     uint4 ctr;                // x,y = game; z = matchup; w = iter << 2 | block
+#ifndef FMC_DRAWS_ALL_BLOCKS
+    // ONE cached Philox block: the draw sites of an iteration visit the record block by block (play call /
+    // completion / yards / explosive in block 0, boost / finish / stage 2 / return in block 1, fourth down in 2-3),
+    // so a single block costs no extra Philox calls and twelve registers less than caching all four.
+    int cur;
+    uint4 w;
+    __device__ Draws(const SimKernelArgs &a_, const MatchupDev &M, int matchup, const Lane &L) : a(a_) {
+        rec = (TEST && a.stream) ? a.stream + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_N_SLOTS
+                                 : nullptr;
+        ctr = make_uint4((uint32_t)L.game, (uint32_t)(L.game >> 32), (uint32_t)matchup, (uint32_t)L.iter << 2);
+        cur = -1;
+    }
+    __device__ __forceinline__ uint32_t word(int slot) {
+        const int b = slot >> 2;
+        if (b != cur) {
+            uint4 c = ctr;
+            c.w |= (uint32_t)b;
+            w = philox4x32_10(c, make_uint2(a.seed_lo, a.seed_hi));
+            cur = b;
+        }
+        const int j = slot & 3;
+        return j == 0 ? w.x : (j == 1 ? w.y : (j == 2 ? w.z : w.w));
+    }
+#else
     uint32_t have;            // bit b: block b cached
     uint4 w[4];
     __device__ Draws(const SimKernelArgs &a_, const MatchupDev &M, int matchup, const Lane &L) : a(a_) {
@@ -190,6 +214,7 @@ struct Draws {
         const int j = slot & 3;
         return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
     }
+#endif
     __device__ __forceinline__ double u(int slot) { return (TEST && rec) ? rec[slot] : u01(word(slot)); }
     __device__ __forceinline__ double z(int slot) { return (TEST && rec) ? rec[slot] : ppnd16(u01(word(slot))); }
 };
