@@ -17,7 +17,6 @@ It runs once per team; sampling, one-hots and the box scores themselves run in t
 """
 from __future__ import annotations
 
-import math
 import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple

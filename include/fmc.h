@@ -209,7 +209,8 @@ int fmc_simulate_host(fmc_ctx *ctx, uint64_t seed, uint32_t *scores_host, uint32
                       uint64_t *counters_host, const double *stream_host, double *trace_host,
                       uint16_t *iters_host);
 
-/* fmc_simulate_host plus the per-game player box [games][2][n_slots] (collect_players=True, FMC:1480-1505). */
+/* fmc_simulate_host plus the per-game player box [games][2][n_slots] (collect_players=True, FMC:1480-1505) and / or
+ * the per-player histograms [n_matchups][2][n_slots][FMC_PH_BINS]; either may be NULL.  Needs fmc_set_usage. */
 int fmc_simulate_players_host(fmc_ctx *ctx, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
                               uint64_t *counters_host, const double *stream_host, double *trace_host,
                               uint16_t *iters_host, fmc_player_rec *players_host, uint32_t *player_hist_host);
