@@ -113,6 +113,7 @@ struct Lane {
     int stage;
     int plays;                 // plays of the current game
     int p1, wr;                // player mode: usage entries sampled for the current play (passer | rusher, target)
+    int home;                  // index of the running player box this game (and its successors) accumulates in
 };
 
 // A game's state between rounds: nine registers instead of sixteen, so that the tree walk (which runs with
@@ -319,6 +320,8 @@ struct SimShared {
     unsigned int aged[kNumKeys];      // the key's tail was held back last round: evaluate everything now
     unsigned int item_prefix[kNumKeys + 1];
     unsigned int item_next;
+    unsigned int dense_off[kNumKeys];  // first thread of each key's evaluated requests after the regrouping
+    unsigned int n_eval, rest;         // evaluated requests this round; counter for the other lanes
     unsigned long long stat[FMC_N_COUNTERS];
 };
 
@@ -336,6 +339,15 @@ __host__ __device__ constexpr int chunk_floats(bool players) { return (kSimRows 
 constexpr size_t kSimSharedBytes = ((sizeof(SimShared) + 15) / 16) * 16;
 __host__ __device__ constexpr size_t sim_feat_bytes(bool players) { return (size_t)kSimChunks * chunk_floats(players) * 4; }
 constexpr size_t kSimResultBytes = (size_t)kSimChunks * 32 * 3 * 8;
+// Regrouping (FMC_REGROUP): after the compaction every game moves to the thread at its request's rank, so that a
+// warp resumes games of ONE (family, orientation) next round instead of six different stages.  The ten words of a
+// game's record travel through shared memory: eight in the result buffer (free between the read-back and the walk),
+// two in kSimXchgExtraBytes.
+#ifndef FMC_REGROUP
+#define FMC_REGROUP 1
+#endif
+constexpr size_t kSimXchgExtraBytes = FMC_REGROUP ? (size_t)2 * kSimThreads * 4 : 0;
+static_assert(kSimResultBytes >= (size_t)8 * kSimThreads * 4, "the result buffer must hold eight exchange words per thread");
 
 // keys in processing order, heaviest family first (LPT-style dynamic scheduling):
 // PQ, RQ (1200 depth-3 trees x3 outputs), S2, PM, SQ, S1
@@ -371,14 +383,14 @@ __device__ __forceinline__ int sample_usage(const UsageDev &U, int role, double 
 // pstats[team][role][name] of a tracked name (FMC:1073-1075, 1108-1148, 1163-1192, 1207-1249): the lane owns its
 // game's box lines, so a plain read-modify-write.  counts: 10-bit fields att|tgt, comp|rec, td, INT, sacks.
 enum : unsigned long long { PC_ATT = 1ULL, PC_COMP = 1ULL << 10, PC_TD = 1ULL << 20, PC_INT = 1ULL << 30, PC_SACK = 1ULL << 40 };
-__device__ __forceinline__ fmc_player_rec *lane_box(const SimKernelArgs &a) {
-    return a.box_scratch + (size_t)(blockIdx.x * kSimThreads + threadIdx.x) * 2 * (size_t)a.n_slots;
+__device__ __forceinline__ fmc_player_rec *lane_box(const SimKernelArgs &a, int home) {
+    return a.box_scratch + (size_t)(blockIdx.x * kSimThreads + home) * 2 * (size_t)a.n_slots;
 }
 __device__ __forceinline__ void credit(const SimKernelArgs &a, const MatchupDev &M, const Lane &L, int team, int role,
                                        int entry, unsigned long long counts, bool has_yds, double yds) {
     const int slot = M.usage[team].slot[role][entry];
     if (slot < 0) return;
-    fmc_player_rec *r = lane_box(a) + team * a.n_slots + slot;
+    fmc_player_rec *r = lane_box(a, L.home) + team * a.n_slots + slot;
     if (has_yds) r->yds += yds;
     r->counts += counts;
 }
@@ -475,7 +487,7 @@ __device__ __forceinline__ int advance_lane(Lane &L, const SimKernelArgs &a, Sim
                 }
                 if (PLAYERS && a.n_slots > 0) {
                     const int lines = 2 * a.n_slots;
-                    flush_box(lane_box(a), a.players ? a.players + oi * (size_t)lines : nullptr,
+                    flush_box(lane_box(a, L.home), a.players ? a.players + oi * (size_t)lines : nullptr,
                               a.player_hist ? a.player_hist + (size_t)matchup * (size_t)lines * FMC_PH_BINS : nullptr, lines,
                               &sh.stat[FMC_C_PH_OVERFLOW]);
                 }
@@ -785,11 +797,15 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     {
         Lane L0;
         L0.game = 0; L0.dist = 0.0; L0.ytg = 0.0; L0.sec = 0; L0.down = 0; L0.offense = 0; L0.period = 0; L0.going = 0;
-        L0.iter = 0; L0.score[0] = 0; L0.score[1] = 0; L0.plays = 0; L0.p1 = 0; L0.wr = 0;
+        L0.iter = 0; L0.score[0] = 0; L0.score[1] = 0; L0.plays = 0; L0.p1 = 0; L0.wr = 0; L0.home = 0;
         L0.stage = ST_IDLE;
         P = pack_lane(L0);
     }
     unsigned long long rounds = 0, requests = 0, visits = 0;
+    int home = tid;        // running player box of the game this thread holds (travels with the game when games regroup)
+    uint32_t *xchg = reinterpret_cast<uint32_t *>(results);                                   // words 0..7
+    uint32_t *xchg2 = reinterpret_cast<uint32_t *>(smem_raw + kSimSharedBytes + kSimFeatBytes + kSimResultBytes);   // words 8..9
+    (void)xchg; (void)xchg2;
 
     for (int visit = 0;; ++visit) {
         // ---- pick the next matchup that still has games; CTAs start at different matchups so that a
@@ -822,6 +838,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
         for (;;) {
             // ---- A: advance to the next request (a held-back lane re-posts the one it has)
             Lane L = unpack_lane(P);
+            L.home = home;
             const int key = held >= 0 ? held : advance_lane<TEST, PLAYERS>(L, a, sh, results + (size_t)pos * 3);
             __syncwarp();
             // ---- B: compaction
@@ -837,7 +854,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
             const int total = __syncthreads_count(key >= 0);
             if (total == 0) break;
             if (tid == 0) {
-                unsigned int o = 0, it = 0;
+                unsigned int o = 0, it = 0, dn = 0;
                 for (int j = 0; j < kNumKeys; ++j) {
                     const int k = kKeyOrder[j];
                     unsigned int c = sh.cnt[parity][k];
@@ -849,12 +866,58 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
                     o += (c + 31u) & ~31u;          // lists start on chunk boundaries
                     sh.item_prefix[j] = it;
                     it += ((c + 31u) >> 5) * (unsigned int)splits_of(k >> 1);
+                    sh.dense_off[k] = dn;
+                    dn += c;
                 }
                 sh.item_prefix[kNumKeys] = it;
                 sh.item_next = 0;
+                sh.n_eval = dn;
+                sh.rest = 0;
             }
             if (tid < kNumKeys) sh.cnt[parity ^ 1][tid] = 0;
             __syncthreads();
+#if FMC_REGROUP
+            // ---- B2: regroup.  The game goes to thread dense_off[key] + rank (evaluated requests, key-major in the
+            // order the keys are walked), every other game to the threads behind them.
+            bool evald = key >= 0 && rank < sh.evalc[key];
+            {
+                const unsigned int slot = evald ? sh.dense_off[key] + rank : sh.n_eval + atomicAdd(&sh.rest, 1u);
+                const unsigned int npos = evald ? sh.off[key] + rank : 0u;
+                P = pack_lane(L);
+                xchg[0 * kSimThreads + slot] = (uint32_t)P.game;
+                xchg[1 * kSimThreads + slot] = (uint32_t)(P.game >> 32);
+                xchg[2 * kSimThreads + slot] = (uint32_t)__double2loint(P.dist);
+                xchg[3 * kSimThreads + slot] = (uint32_t)__double2hiint(P.dist);
+                xchg[4 * kSimThreads + slot] = (uint32_t)__double2loint(P.ytg);
+                xchg[5 * kSimThreads + slot] = (uint32_t)__double2hiint(P.ytg);
+                xchg[6 * kSimThreads + slot] = P.a;
+                xchg[7 * kSimThreads + slot] = P.b;
+                xchg2[0 * kSimThreads + slot] = P.c;
+                xchg2[1 * kSimThreads + slot] = npos | ((uint32_t)(key + 1) << 11) | ((evald ? 1u : 0u) << 16) | ((uint32_t)home << 17);
+            }
+            __syncthreads();
+            int mykey;
+            {
+                P.game = (unsigned long long)xchg[0 * kSimThreads + tid] | ((unsigned long long)xchg[1 * kSimThreads + tid] << 32);
+                P.dist = __hiloint2double((int)xchg[3 * kSimThreads + tid], (int)xchg[2 * kSimThreads + tid]);
+                P.ytg = __hiloint2double((int)xchg[5 * kSimThreads + tid], (int)xchg[4 * kSimThreads + tid]);
+                P.a = xchg[6 * kSimThreads + tid];
+                P.b = xchg[7 * kSimThreads + tid];
+                P.c = xchg2[0 * kSimThreads + tid];
+                const uint32_t w = xchg2[1 * kSimThreads + tid];
+                pos = (int)(w & 0x7FFu);
+                mykey = (int)((w >> 11) & 31u) - 1;
+                evald = ((w >> 16) & 1u) != 0u;
+                home = (int)(w >> 17);
+            }
+            held = (!evald && mykey >= 0) ? mykey : -1;
+            if (evald) {
+                const Lane Ln = unpack_lane(P);
+                write_features<PLAYERS>(feats + (size_t)(pos >> 5) * kChunkFloats + (pos & 31), Ln, mykey >> 1, a, sh.M);
+            }
+            const bool posted = evald;
+            __syncthreads();
+#else
             held = -1;
             if (key >= 0) {
                 if (rank < sh.evalc[key]) {
@@ -865,7 +928,9 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
                 }
             }
             P = pack_lane(L);
+            const bool posted = key >= 0 && held < 0;
             __syncthreads();
+#endif
             // ---- C: evaluate.  Work item = (key, chunk of 32 requests, output)
             const unsigned int n_items = sh.item_prefix[kNumKeys];
             for (;;) {
@@ -897,7 +962,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
             __syncthreads();
             parity ^= 1;
             rounds += 1;
-            requests += (key >= 0 && held < 0) ? 1ULL : 0ULL;
+            requests += posted ? 1ULL : 0ULL;
         }
     }
     // ---- flush counters
@@ -908,6 +973,6 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     if (a.counters && tid < FMC_N_COUNTERS && sh.stat[tid]) atomicAdd(&a.counters[tid], sh.stat[tid]);
 }
 
-inline size_t sim_smem_bytes(bool players = false) { return kSimSharedBytes + sim_feat_bytes(players) + kSimResultBytes; }
+inline size_t sim_smem_bytes(bool players = false) { return kSimSharedBytes + sim_feat_bytes(players) + kSimResultBytes + kSimXchgExtraBytes; }
 
 }  // namespace fmc
