@@ -32,5 +32,29 @@ eng = Engine(art.ModelSet(forests, source="big"), stage2="standin")
 eng.predict("pass_stage2", rows)
 e = int(L.fmc_debug_errors()); total += e
 print("multi-window forest: debug errors", e)
+# player mode (dynamic one-hot rows, running box, per-player histograms) and the play_model.json policy
+from fast_monte_carlo_b200 import priors, usage
+gold = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+focus = usage.build_focus_usage_tables(os.path.join(gold, "players_focus.csv"))
+sp = priors.load_sp_flex(priors.packaged_priors_path())
+tcs = {t: priors.build_team_context_from_sp_flex(t, 2025, 1, sp, focus=focus, usage_dir=gold)
+       for t in ("Kansas State", "Iowa State", "Ohio State", "UTSA")}
+learner = art.play_binary_from_learner(synth.synthetic_play_model_json()["learner"], synth.PLAY_JSON_FEATURES, ["pass", "run"], 1.3)
+forests = dict(ms.forests); forests["play_binary"] = learner
+msp = art.ModelSet(forests, source="players")
+for kw in (dict(stage2="booster"), dict(stage2="booster", policy="play_json")):
+    eng = Engine(msp, **kw)
+    specs = []
+    off = 0
+    for a, b, n in (("Kansas State", "Iowa State", 30000), ("Ohio State", "UTSA", 9000), ("Ohio State", "Kansas State", 5)):
+        specs.append(MatchupSpec(a, b, tcs[a].sp, tcs[b].sp, n, 0, n, off,
+                                 usage=(usage.resolve_team(tcs[a], msp), usage.resolve_team(tcs[b], msp))))
+        off += n
+    eng.set_matchups(specs)
+    r = eng.simulate_host(9, want_players=True, want_player_hist=True)
+    e = int(L.fmc_debug_errors()); total += e
+    print("players", kw, "games", r["counters"]["games"], "box lines", int(r["players"].dense()[..., 1].sum()),
+          "hist", int(r["player_hist"].sum()), "debug errors", e)
+    eng.close()
 print("TOTAL debug errors", total)
 sys.exit(1 if total else 0)
