@@ -16,8 +16,17 @@ __device__ __forceinline__ void step8(uint2 &n, uint32_t fcol, uint32_t wl, uint
     asm("{.reg .pred p; setp.gtu.f32 p, %1, %2; @p add.u32 %0, %0, 8;}" : "+r"(a) : "f"(fv), "f"(__uint_as_float(n.x)));
     asm("{.reg .u64 ad; mov.b64 ad, {%2, %3}; ld.global.nc.v2.u32 {%0, %1}, [ad];}" : "=r"(n.x), "=r"(n.y) : "r"(a), "r"(wh));
 }
+// VAR 3: rank-coded features in ONE register (DESIGN.md "what is left"): no feature LDS; the node carries a rotate
+// amount (top 5 bits of hi32) and a top-aligned integer threshold (lo32); fcol stands in for the lane's rank word
 template <int VAR>
 __device__ __forceinline__ void step8v(uint2 &n, uint32_t fcol, uint32_t wl, uint32_t wh) {
+    if (VAR == 3 || VAR == 4) {      // VAR 4: the rotate amount in the LOW 5 bits of hi32 (shf.wrap reads them directly: no extract)
+        const uint32_t v = __funnelshift_l(fcol, fcol, VAR == 3 ? (n.y >> 27) : n.y);
+        uint32_t a = (n.y & 0xFFFF8u) | wl;
+        asm("{.reg .pred p; setp.gt.u32 p, %1, %2; @p add.u32 %0, %0, 8;}" : "+r"(a) : "r"(v), "r"(n.x));
+        asm("{.reg .u64 ad; mov.b64 ad, {%2, %3}; ld.global.nc.v2.u32 {%0, %1}, [ad];}" : "=r"(n.x), "=r"(n.y) : "r"(a), "r"(wh));
+        return;
+    }
     float fv;
     if (VAR == 1) fv = __uint_as_float(fcol); else fv = lds_f32(fcol + (n.y >> 20));
     uint32_t a = (n.y & 0xFFFF8u) | wl;
@@ -159,6 +168,9 @@ int main() {
             run("8B normal 8 chains", kv<0, 8>, 8, depth);
             run("8B no LDS 8 chains", kv<1, 8>, 8, depth);
             run("8B no setp 8 chains", kv<2, 8>, 8, depth);
+            run("8B rank register 8 chains", kv<3, 8>, 8, depth);
+            run("8B rank register 12 chains", kv<3, 12>, 12, depth);
+            run("8B rank reg, no extract 8 ch", kv<4, 8>, 8, depth);
             run("8B normal 4 chains", kv<0, 4>, 4, depth);
             run("8B normal 12 chains", kv<0, 12>, 12, depth);
             run("8B normal 16 chains", kv<0, 16>, 16, depth);
