@@ -187,6 +187,7 @@ struct fmc_ctx {
     struct NameRows { int8_t row[3][FMC_MAX_USAGE]; };
     std::vector<NameRows> name_rows;     // per team: the 0/1 feature row of every usage entry (-1: no model knows the name)
     int n_slots = 0;
+    int n_prow = 0, n_trow = 0, n_rrow = 0;   // name rows the current usage tables need (max over the teams)
     fmc_player_rec *d_box_scratch = nullptr;   // running box of every resident lane [grid x threads][2][n_slots]
     size_t box_scratch_bytes = 0;
     bool tables_dirty = true;
@@ -348,6 +349,14 @@ extern "C" int fmc_set_usage(fmc_ctx *c, int32_t n, const fmc_team_usage *teams,
             if (!(tot > 0.0)) return fail(FMC_ERR_INVALID, "fmc_set_usage: shares sum to zero");
         }
     c->usage.assign(teams, teams + 2 * (size_t)n);
+    c->n_prow = c->n_trow = c->n_rrow = 0;
+    for (size_t i = 0; i < rows.size(); ++i)
+        for (int r = 0; r < 3; ++r) {
+            int used = 0;
+            for (int e = 0; e < FMC_MAX_USAGE; ++e) used = rows[i].row[r][e] + 1 > used ? rows[i].row[r][e] + 1 : used;
+            int &dst = r == 0 ? c->n_prow : (r == 1 ? c->n_rrow : c->n_trow);
+            if (used > dst) dst = used;
+        }
     c->name_rows.swap(rows);
     c->n_slots = n_slots;
     c->tables_dirty = true;
@@ -356,7 +365,7 @@ extern "C" int fmc_set_usage(fmc_ctx *c, int32_t n, const fmc_team_usage *teams,
 
 // Dynamic one-hot columns of (family, team on offense): the sampled names of a play are feature rows
 // (fmc_sim.cuh kDynRow0...), every other name column folds to 0.
-static void dyn_columns(const fmc_team_usage &tu, const fmc_ctx::NameRows &nr, int fam, PackSpec &s) {
+static void dyn_columns(const fmc_team_usage &tu, const fmc_ctx::NameRows &nr, int fam, int n_prow, PackSpec &s) {
     s.n_dyn = 0;
     auto add = [&](int role, int row0) {
         const fmc_usage &u = tu.role[role];
@@ -364,7 +373,7 @@ static void dyn_columns(const fmc_team_usage &tu, const fmc_ctx::NameRows &nr, i
             if (u.col[fam][e] >= 0) { s.dyn_col[s.n_dyn] = u.col[fam][e]; s.dyn_row[s.n_dyn] = (int8_t)(row0 + nr.row[role][e]); s.n_dyn++; }
     };
     if (fam == FMC_RUN_YARDS) add(1, kDynRow0);
-    else if (fam != FMC_PLAY_MODEL) { add(0, kDynRow0); add(2, kDynRow0 + FMC_MAX_PASSER_ROWS); }
+    else if (fam != FMC_PLAY_MODEL) { add(0, kDynRow0); add(2, kDynRow0 + n_prow); }   // target rows follow the passer rows in use
 }
 
 static bool family_needed(const fmc_ctx *c, int fam) {
@@ -403,7 +412,7 @@ static int build_tables(fmc_ctx *c) {
         s.active[0] = f.active[0]; s.active[1] = f.active[1];
         if (!c->usage.empty()) {      // player mode: every name comes from the usage tables
             s.active[0] = -1; s.active[1] = -1;
-            dyn_columns(c->usage[(size_t)j.matchup * 2 + off], c->name_rows[(size_t)j.matchup * 2 + off], fam, s);
+            dyn_columns(c->usage[(size_t)j.matchup * 2 + off], c->name_rows[(size_t)j.matchup * 2 + off], fam, c->n_prow, s);
         }
         if (fam == FMC_PLAY_MODEL) { s.active[0] = mu.coach_col[off]; s.active[1] = -1; }
         s.fold_value[6] = 3.0; s.fold_value[7] = 3.0;    // timeouts are never spent (FMC:911-912)
@@ -569,8 +578,11 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
 #endif
     const bool test = a.stream || a.trace;      // parity-test instantiation
     if (players) {
-        if (test) sim_kernel<true, true><<<grid, kSimThreads, sim_smem_bytes(true), st>>>(a);
-        else sim_kernel<false, true><<<grid, kSimThreads, sim_smem_bytes(true), st>>>(a);
+        a.n_prow = c->n_prow; a.n_trow = c->n_trow; a.n_rrow = c->n_rrow;
+        a.name_rows = c->n_prow + c->n_trow > c->n_rrow ? c->n_prow + c->n_trow : c->n_rrow;
+        const size_t smem = sim_smem_bytes_players(a.name_rows);
+        if (test) sim_kernel<true, true><<<grid, kSimThreads, smem, st>>>(a);
+        else sim_kernel<false, true><<<grid, kSimThreads, smem, st>>>(a);
     } else {
         if (test) sim_kernel<true, false><<<grid, kSimThreads, sim_smem_bytes(false), st>>>(a);
         else sim_kernel<false, false><<<grid, kSimThreads, sim_smem_bytes(false), st>>>(a);

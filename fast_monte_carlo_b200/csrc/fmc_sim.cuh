@@ -95,6 +95,9 @@ struct SimKernelArgs {
     uint32_t *player_hist;             // player mode: [n_matchups][2][n_slots][FMC_PH_BINS] (optional output)
     fmc_player_rec *box_scratch;       // player mode: [lanes of the grid][2][n_slots] running box of each lane's game
     int n_slots;
+    // player mode: name rows actually needed by the matchups of this launch (a chunk has kSimRows + name_rows rows):
+    // passer rows [kDynRow0, +n_prow), target rows behind them, rusher rows [kDynRow0, +n_rrow)
+    int n_prow, n_trow, n_rrow, name_rows;
 };
 
 enum Stage : int {
@@ -714,13 +717,17 @@ __device__ __forceinline__ void write_features(float *col, const Lane &L, int fa
         if (fam == 3) {
             const int r1 = U.row[1][L.p1];
 #pragma unroll
-            for (int e = 0; e < FMC_MAX_NAME_ROWS; ++e) col[(kDynRow0 + e) * 32] = (e == r1) ? 1.f : 0.f;
+            for (int e = 0; e < FMC_MAX_NAME_ROWS; ++e)
+                if (e < a.n_rrow) col[(kDynRow0 + e) * 32] = (e == r1) ? 1.f : 0.f;
         } else {
             const int r1 = U.row[0][L.p1], r2 = U.row[2][L.wr];
 #pragma unroll
-            for (int e = 0; e < FMC_MAX_PASSER_ROWS; ++e) col[(kDynRow0 + e) * 32] = (e == r1) ? 1.f : 0.f;
+            for (int e = 0; e < FMC_MAX_PASSER_ROWS; ++e)
+                if (e < a.n_prow) col[(kDynRow0 + e) * 32] = (e == r1) ? 1.f : 0.f;
+            float *tcol = col + (kDynRow0 + a.n_prow) * 32;
 #pragma unroll
-            for (int e = 0; e < FMC_MAX_NAME_ROWS; ++e) col[(kDynRow0 + FMC_MAX_PASSER_ROWS + e) * 32] = (e == r2) ? 1.f : 0.f;
+            for (int e = 0; e < FMC_MAX_NAME_ROWS; ++e)
+                if (e < a.n_trow) tcol[e * 32] = (e == r2) ? 1.f : 0.f;
         }
     }
     const int sd = L.score[team] - L.score[team ^ 1];
@@ -785,8 +792,9 @@ __device__ __forceinline__ double eval_output(int fam, const TableRef &T, int ou
 template <bool TEST, bool PLAYERS>
 __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const SimKernelArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int kChunkFloats = chunk_floats(PLAYERS);
-    constexpr size_t kSimFeatBytes = sim_feat_bytes(PLAYERS);
+    // player mode sizes a chunk by the name rows the launch needs (runtime); the shipped configuration is compile-time
+    const int kChunkFloats = PLAYERS ? (kSimRows + a.name_rows) * 32 : chunk_floats(false);
+    const size_t kSimFeatBytes = (size_t)kSimChunks * (size_t)kChunkFloats * 4;
     SimShared &sh = *reinterpret_cast<SimShared *>(smem_raw);
     float *feats = reinterpret_cast<float *>(smem_raw + kSimSharedBytes);
     double *results = reinterpret_cast<double *>(smem_raw + kSimSharedBytes + kSimFeatBytes);
@@ -1003,5 +1011,9 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
 }
 
 inline size_t sim_smem_bytes(bool players = false) { return kSimSharedBytes + sim_feat_bytes(players) + kSimResultBytes + kSimXchgExtraBytes; }
+// player mode with `name_rows` name rows per chunk (<= kDynRows)
+inline size_t sim_smem_bytes_players(int name_rows) {
+    return kSimSharedBytes + (size_t)kSimChunks * (size_t)(kSimRows + name_rows) * 32 * 4 + kSimResultBytes + kSimXchgExtraBytes;
+}
 
 }  // namespace fmc
