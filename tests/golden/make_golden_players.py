@@ -26,8 +26,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import ref_harness as rh                  # noqa: E402
+from streams import adversarial_stream                # noqa: E402
 from oracle.c_oracle import make_stream               # noqa: E402
 
 SHEET = """team,player,pos,usage,stat,yards
@@ -96,9 +98,31 @@ def main():
             rows.append([r[c] for c in PLAYER_COLS])
         print(f"game {g}: {first} {scores[g,0]} - {second} {scores[g,1]}  iters {iters[g]}  "
               f"player rows so far {len(rows)}  ({time.time()-t0:.0f}s)", flush=True)
+    # ---- the same under ADVERSARIAL draws (tests/streams.py): u = 0 picks the first entry with a positive share
+    # (zero-share entries are skipped by searchsorted(..., 'right')), u just below 1 the last one, and so on
+    n_adv = int(os.environ.get("FMC_GOLDEN_ADV_GAMES", "12"))
+    adv = adversarial_stream(n_adv, 77)
+    a_traces = np.full((n_adv, rh.MAX_ITERS, 8), np.nan)
+    a_scores = np.zeros((n_adv, 2), dtype=np.int32)
+    a_iters = np.zeros(n_adv, dtype=np.int32)
+    a_meta, a_rows = [], []
+    for g in range(n_adv):
+        a, b = PAIRS[(g // 2) % len(PAIRS)]
+        first, second = (b, a) if (g & 1) else (a, b)
+        ca, cb = rh.team_context(mod, first), rh.team_context(mod, second)
+        res, trc, used = rh.run_game_injected(mod, ca, cb, adv[g])
+        a_traces[g, :trc.shape[0]] = trc
+        a_scores[g] = (res["off_score"], res["def_score"])
+        a_iters[g] = trc.shape[0]
+        a_meta.append(dict(team_a=a, team_b=b, first=first, second=second, pattern=g % 6))
+        for r in mod.flatten_player_box_rows(res, sim_id=g, start_flag="B" if (g & 1) else "A"):
+            a_rows.append([r[c] for c in PLAYER_COLS])
+        print(f"adversarial game {g} pattern {g % 6}: {first} {a_scores[g,0]} - {second} {a_scores[g,1]}  iters {a_iters[g]}  "
+              f"player rows so far {len(a_rows)}  ({time.time()-t0:.0f}s)", flush=True)
     np.savez_compressed(os.path.join(HERE, "ref_players.npz"), stream_seed=11, traces=traces, scores=scores, iters=iters,
                         meta=json.dumps(meta), teams=json.dumps(teams), player_cols=json.dumps(PLAYER_COLS),
-                        player_rows=json.dumps(rows))
+                        player_rows=json.dumps(rows), adv_stream_seed=77, adv_traces=a_traces, adv_scores=a_scores,
+                        adv_iters=a_iters, adv_meta=json.dumps(a_meta), adv_player_rows=json.dumps(a_rows))
     print("done in %.0fs" % (time.time() - t0))
 
 

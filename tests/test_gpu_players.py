@@ -259,3 +259,29 @@ def test_set_usage_error_paths(engine, contexts, models_s2):
     engine.set_matchups([MatchupSpec("UTSA", "Texas", ta.sp, tb.sp, 10, 0, 10, 0)])
     with pytest.raises(native.FmcError, match="set_usage"):
         engine.simulate_host(1, want_players=True)
+
+
+def test_reference_golden_players_adversarial(engine, contexts):
+    """The reference's OWN player-mode games under adversarial draws (first / last usage entry, skipped zero-share
+    entries, +-4 sigma yardage, 112-112 shoot-outs)."""
+    from streams import adversarial_stream
+    t = np.load(os.path.join(GOLDEN, "ref_players.npz"))
+    meta = json.loads(str(t["adv_meta"]))
+    cols = json.loads(str(t["player_cols"]))
+    stream = adversarial_stream(len(meta), int(t["adv_stream_seed"]))
+    frames = []
+    for g, m in enumerate(meta):
+        spec = _spec(contexts, m["team_a"], m["team_b"], 1, g0=g)
+        engine.set_matchups([spec])
+        r = engine.simulate_host(0, stream=stream[g:g + 1], want_trace=True, want_iters=True, want_players=True)
+        k = int(t["adv_iters"][g])
+        assert r["iters"][0] == k, (g, m["pattern"])
+        assert np.array_equal(r["trace"][0, :k], t["adv_traces"][g, :k]), (g, m["pattern"])
+        f = g & 1
+        assert (r["scores"][0, f], r["scores"][0, f ^ 1]) == tuple(t["adv_scores"][g])
+        frames.append(usage.player_rows(r["players"], g, (m["team_a"], m["team_b"]), spec.usage))
+    got = _frame(pd.concat(frames, ignore_index=True).values.tolist(), cols)
+    want = _frame(json.loads(str(t["adv_player_rows"])), cols)
+    assert len(got) == len(want) > 10
+    for c in cols:
+        assert got[c].tolist() == want[c].tolist(), c

@@ -216,3 +216,31 @@ def test_usage_capacity_errors(models):
                              rush_share=pd.DataFrame({"rusher_name": ["A", "B"], "share": [0.0, 0.0]}))
     with pytest.raises(ValueError, match="shares"):
         usage.resolve_team(bad, models)
+
+
+def test_oracle_players_adversarial_streams(models, oracle, gold, contexts):
+    """The reference's own player-mode games under ADVERSARIAL draws (tests/streams.py): u = 0 must pick the first
+    usage entry with a positive share (zero-share entries are skipped), u just below 1 the last entry, +-4 sigma
+    yardage, 112-112 shoot-outs -- trajectories bit for bit and the players table row for row."""
+    from streams import adversarial_stream
+    t = gold["t"]
+    meta = json.loads(str(t["adv_meta"]))
+    stream = adversarial_stream(len(meta), int(t["adv_stream_seed"]))
+    frames = []
+    for g, m in enumerate(meta):
+        ta, tb = contexts[m["team_a"]], contexts[m["team_b"]]
+        us = [usage.resolve_team(ta, models), usage.resolve_team(tb, models)]
+        cfg = oracle.make_config(models, ta.sp, tb.sp)
+        r = oracle.simulate(cfg, 1, game0=g, stream=stream[g:g + 1], trace=True, threads=1,
+                            usage=oracle.make_usage(us), n_slots=max(len(u.slots) for u in us))
+        n = int(t["adv_iters"][g])
+        assert r["iters"][0] == n, (g, m["pattern"])
+        assert np.array_equal(r["trace"][0, :n], t["adv_traces"][g, :n]), (g, m["pattern"])
+        f = g & 1
+        assert (r["scores"][0, f], r["scores"][0, f ^ 1]) == tuple(t["adv_scores"][g])
+        frames.append(usage.player_rows(r["players"], g, (m["team_a"], m["team_b"]), us))
+    got = _frame(pd.concat(frames, ignore_index=True).values.tolist(), gold["cols"])
+    want = _frame(json.loads(str(t["adv_player_rows"])), gold["cols"])
+    assert len(got) == len(want) > 10
+    for c in gold["cols"]:
+        assert got[c].tolist() == want[c].tolist(), c
