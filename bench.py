@@ -244,11 +244,19 @@ def synthetic_usage(ms):
                  for t in (KSU[0], ISU[0]))
 
 
+def host_threads() -> int:
+    """Host cores this process may use (the CPU arm always uses all of them, whatever OMP_NUM_THREADS says)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:      # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_run(ms, games: int, stage2: str, game0: int = 0, players: bool = False):
     from oracle import c_oracle as co
     co.load_models(ms)
     cfg = co.make_config(ms, KSU[1], ISU[1], stage2="booster" if stage2 == "synthetic" else "standin")
-    threads = co.lib().fo_max_threads()
+    threads = host_threads()      # explicit: torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm
     kw = {}
     if players:
         use = synthetic_usage(ms)

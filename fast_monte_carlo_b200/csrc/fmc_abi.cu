@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "fmc_sim.cuh"
+#include "fmc_sim_memo.cuh"
 
 using namespace fmc;
 
@@ -197,6 +198,21 @@ struct fmc_ctx {
     unsigned long long *d_next = nullptr;
     std::vector<unsigned long long> h_next;
     std::vector<int32_t> packed_slots;   // [n_matchups][FMC_N_MODELS][2]
+    // exact memo (fmc_memo.hpp): rank specs of the current tables, table regions, mode
+    RankSpec *d_specs = nullptr;
+    std::vector<uint8_t> memo_ok;        // [n_matchups][kMemoFams][2] the forest's ranks fit the key
+    std::vector<std::string> memo_why;   // why not, for diagnostics
+    int memo_mode = 1, memo_max_trips = 8, memo_break_parked = 16;
+    uint64_t memo_max_bytes = 0;
+    char *d_memo = nullptr;
+    size_t memo_bytes = 0;
+    MemoRegion memo_region[kMemoFams];
+    bool memo_valid = false;             // mode 2: the table belongs to the current node tables
+    cudaEvent_t ev_done = nullptr;       // completion of the last fmc_simulate launch
+    bool launched = false;
+    // fmc_simulate_host: device scratch + pinned staging, kept between calls
+    struct Scratch { void *dev = nullptr; size_t dev_bytes = 0; };
+    Scratch scr[8];
     // fmc_tree_predict: packed + uploaded tables are kept per (model, tree range, hot columns) until the model
     // or its columns change -- a stream of predict calls on the same model re-uses them
     struct PredEntry {
@@ -213,6 +229,17 @@ struct fmc_ctx {
     uint64_t pred_clock = 0;
 };
 
+extern "C" void fmc_destroy(fmc_ctx *c);
+// inside fmc_create: a failing CUDA call must not leak the half-built context
+#define CKC(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            fmc_destroy(c);                                                                        \
+            return fail(FMC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+        }                                                                                          \
+    } while (0)
+
 extern "C" const char *fmc_last_error(void) { return g_err.c_str(); }
 extern "C" int fmc_abi_version(void) { return FMC_ABI_VERSION; }
 
@@ -226,11 +253,11 @@ extern "C" int fmc_create(int device, fmc_ctx **out) {
     if (device < 0 || device >= n) return fail(FMC_ERR_INVALID, "fmc_create: bad device index");
     fmc_ctx *c = new fmc_ctx();
     c->device = device;
-    CK(cudaSetDevice(device));
-    CK(cudaGetDeviceProperties(&c->prop, device));
+    CKC(cudaSetDevice(device));
+    CKC(cudaGetDeviceProperties(&c->prop, device));
     if (c->prop.major != 10) {
         std::string nm = c->prop.name;
-        delete c;
+        fmc_destroy(c);
         return fail(FMC_ERR_NO_DEVICE, "device '" + nm + "' is not sm_100 (this library is built for sm_100a only)");
     }
     std::memset(&c->params, 0, sizeof(c->params));
@@ -240,10 +267,14 @@ extern "C" int fmc_create(int device, fmc_ctx **out) {
     c->params.stage2_standin[0] = (double)0.78f;
     c->params.stage2_standin[1] = (double)0.05f;
     c->params.stage2_standin[2] = (double)0.17f;
-    CK(cudaFuncSetAttribute(sim_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(false)));
-    CK(cudaFuncSetAttribute(sim_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(false)));
-    CK(cudaFuncSetAttribute(sim_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(true)));
-    CK(cudaFuncSetAttribute(sim_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(true)));
+    CKC(cudaFuncSetAttribute(sim_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(false)));
+    CKC(cudaFuncSetAttribute(sim_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(false)));
+    CKC(cudaFuncSetAttribute(sim_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(true)));
+    CKC(cudaFuncSetAttribute(sim_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_smem_bytes(true)));
+    CKC(cudaFuncSetAttribute(sim_memo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_memo_smem_bytes()));
+    CKC(cudaFuncSetAttribute(sim_memo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_memo_smem_bytes()));
+    CKC(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    std::memset(c->memo_region, 0, sizeof(c->memo_region));
     *out = c;
     return FMC_OK;
 }
@@ -253,7 +284,11 @@ extern "C" void fmc_destroy(fmc_ctx *c) {
     cudaSetDevice(c->device);
     c->sim_tables.release();
     for (auto &e : c->pred) e.arena.release();
+    cudaDeviceSynchronize();
     cudaFree(c->d_matchups); cudaFree(c->d_next); cudaFree(c->d_box_scratch);
+    cudaFree(c->d_specs); cudaFree(c->d_memo);
+    for (auto &q : c->scr) cudaFree(q.dev);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     delete c;
 }
 
@@ -269,6 +304,19 @@ extern "C" int fmc_load_forest(fmc_ctx *c, int32_t id, const fmc_forest_desc *d)
     if (!c || !d || id < 0 || id >= FMC_N_MODELS) return fail(FMC_ERR_INVALID, "fmc_load_forest: bad argument");
     if (d->n_outputs < 1 || d->n_outputs > 8 || d->n_nodes <= 0 || d->n_trees <= 0 || d->n_num > kNumMax)
         return fail(FMC_ERR_INVALID, "fmc_load_forest: bad shape");
+    if (!d->feat || !d->thr || !d->left || !d->right || !d->default_left || !d->value || !d->tree_root || !d->tree_out)
+        return fail(FMC_ERR_INVALID, "fmc_load_forest: NULL array");
+    for (int32_t i = 0; i < d->n_nodes; ++i) {
+        const int32_t l = d->left[i], r = d->right[i];
+        if (l < 0) continue;                                  // leaf
+        if (l >= d->n_nodes || r < 0 || r >= d->n_nodes) return fail(FMC_ERR_INVALID, "fmc_load_forest: child index out of range");
+        if (d->feat[i] < 0 || d->feat[i] >= d->n_features) return fail(FMC_ERR_INVALID, "fmc_load_forest: split column out of range");
+    }
+    for (int32_t t = 0; t < d->n_trees; ++t) {
+        if (d->tree_root[t] < 0 || d->tree_root[t] >= d->n_nodes) return fail(FMC_ERR_INVALID, "fmc_load_forest: tree root out of range");
+        if (d->tree_out[t] < 0 || d->tree_out[t] >= d->n_outputs) return fail(FMC_ERR_INVALID, "fmc_load_forest: tree output out of range");
+    }
+    if (d->num_base < 0 || d->n_num < 0 || d->num_base + d->n_num > d->n_features) return fail(FMC_ERR_INVALID, "fmc_load_forest: numeric columns out of range");
     const int32_t keep0 = c->forest[id].active[0], keep1 = c->forest[id].active[1];
     const bool had = c->forest[id].loaded;
     c->forest[id].assign(*d);
@@ -281,6 +329,9 @@ extern "C" int fmc_load_forest(fmc_ctx *c, int32_t id, const fmc_forest_desc *d)
 
 extern "C" int fmc_set_scaler(fmc_ctx *c, int32_t id, int32_t n, const int32_t *cols, const double *mean, const double *scale) {
     if (!c || id < 0 || id >= FMC_N_MODELS || n < 0 || n > 16) return fail(FMC_ERR_INVALID, "fmc_set_scaler: bad argument");
+    if (n > 0 && (!cols || !mean || !scale)) return fail(FMC_ERR_INVALID, "fmc_set_scaler: NULL array");
+    for (int i = 0; i < n; ++i)
+        if (cols[i] < 0 || cols[i] >= kNumMax) return fail(FMC_ERR_INVALID, "fmc_set_scaler: column outside the 17 numerics");
     HostForest &f = c->forest[id];
     f.n_scaled = n;
     for (int i = 0; i < n; ++i) { f.scaler_cols[i] = cols[i]; f.scaler_mean[i] = mean[i]; f.scaler_scale[i] = scale[i]; }
@@ -305,6 +356,17 @@ extern "C" int fmc_set_params(fmc_ctx *c, const fmc_params *p) {
     if (p->pass_class < 0 || p->pass_class > 4) return fail(FMC_ERR_INVALID, "fmc_set_params: pass_class out of range");
     c->params = *p;
     c->tables_dirty = true;
+    return FMC_OK;
+}
+
+extern "C" int fmc_set_memo(fmc_ctx *c, int32_t mode, uint64_t max_bytes, int32_t max_trips, int32_t break_parked) {
+    if (!c || mode < 0 || mode > 2) return fail(FMC_ERR_INVALID, "fmc_set_memo: mode must be 0, 1 or 2");
+    if (max_trips < 0 || max_trips > 4096 || break_parked < 0 || break_parked > 32) return fail(FMC_ERR_INVALID, "fmc_set_memo: bad scheduling knob");
+    c->memo_mode = mode;
+    c->memo_max_bytes = max_bytes;
+    c->memo_max_trips = max_trips > 0 ? max_trips : 8;
+    c->memo_break_parked = break_parked > 0 ? break_parked : 16;
+    c->memo_valid = false;
     return FMC_OK;
 }
 
@@ -388,6 +450,10 @@ static int build_tables(fmc_ctx *c) {
     for (int fam = 0; fam < kNumFam; ++fam)
         if (family_needed(c, fam) && !c->forest[fam].loaded)
             return fail(FMC_ERR_INVALID, "model " + std::to_string(fam) + " is required by the current fmc_params but not loaded");
+    // a launch in flight still reads the tables, the matchup records and the work counters that are replaced below
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    c->memo_valid = false;
     const int n = (int)c->matchups.size();
     std::vector<MatchupDev> md(n);
     struct Pending { int matchup, fam, off, table; };
@@ -397,7 +463,7 @@ static int build_tables(fmc_ctx *c) {
     c->packed_slots.assign((size_t)n * FMC_N_MODELS * 2, 0);
     // ---- specialise + pack every (matchup, orientation, family) forest; the jobs are independent, a slate
     // of hundreds of matchups is packed by all host threads
-    struct Job { int matchup, off, fam; PackedForest pf; std::string err; };
+    struct Job { int matchup, off, fam; PackedForest pf; std::string err, memo_why; RankSpec spec; };
     std::vector<Job> jobs;
     for (int i = 0; i < n; ++i)
         for (int off = 0; off < 2; ++off)
@@ -421,6 +487,18 @@ static int build_tables(fmc_ctx *c) {
         s.n_scaled = f.n_scaled;
         for (int k = 0; k < f.n_scaled; ++k) { s.scaler_cols[k] = f.scaler_cols[k]; s.scaler_mean[k] = f.scaler_mean[k]; s.scaler_scale[k] = f.scaler_scale[k]; }
         j.err = pack_forest(f, s, j.pf);
+        if (j.err.empty() && fam < kMemoFams) {
+            RankSpecInput in;
+            in.xgb = f.kind == FMC_KIND_XGB;
+            in.zm = in.xgb && f.zero_is_missing;
+            in.play_model = fam == FMC_PLAY_MODEL;
+            if (in.play_model)
+                for (int k = 0; k < f.n_scaled; ++k) {
+                    const int col = f.scaler_cols[k];
+                    if (col >= 0 && col < 6) { in.pm_scaled[col] = 1; in.pm_mean[col] = f.scaler_mean[k]; in.pm_scale[col] = f.scaler_scale[k]; }
+                }
+            j.memo_why = build_rank_spec(j.pf.row_thr, in, j.spec);
+        }
     };
     {
         unsigned nt = std::thread::hardware_concurrency();
@@ -466,8 +544,18 @@ static int build_tables(fmc_ctx *c) {
             }
         }
     }
+    std::vector<RankSpec> specs((size_t)n * kMemoFams * 2);
+    std::memset(specs.data(), 0, specs.size() * sizeof(RankSpec));
+    c->memo_ok.assign((size_t)n * kMemoFams * 2, 0);
+    c->memo_why.assign((size_t)n * kMemoFams * 2, "family not in use");
     for (Job &j : jobs) {
         if (!j.err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(j.fam) + ": " + j.err);
+        if (j.fam < kMemoFams) {
+            const size_t si = ((size_t)j.matchup * kMemoFams + j.fam) * 2 + j.off;
+            specs[si] = j.spec;
+            c->memo_ok[si] = j.spec.enabled ? 1 : 0;
+            c->memo_why[si] = j.memo_why;
+        }
         PackedForest &pf = j.pf;
         const HostForest &f = c->forest[j.fam];
         if (pf.n_outputs > 5) return fail(FMC_ERR_CAPACITY, "more than 5 outputs in a simulation model");
@@ -499,6 +587,10 @@ static int build_tables(fmc_ctx *c) {
     CK(cudaMalloc(&c->d_matchups, md.size() * sizeof(MatchupDev)));
     CK(cudaMalloc(&c->d_next, (size_t)n * 8));
     CK(cudaMemcpy(c->d_matchups, md.data(), md.size() * sizeof(MatchupDev), cudaMemcpyHostToDevice));
+    cudaFree(c->d_specs);
+    c->d_specs = nullptr;
+    CK(cudaMalloc(&c->d_specs, specs.size() * sizeof(RankSpec)));
+    CK(cudaMemcpy(c->d_specs, specs.data(), specs.size() * sizeof(RankSpec), cudaMemcpyHostToDevice));
     c->h_next.resize(n);
     c->tables_dirty = false;
     return FMC_OK;
@@ -526,6 +618,59 @@ extern "C" int fmc_packed_slots(fmc_ctx *c, int32_t m, int32_t *out) {
     return FMC_OK;
 }
 
+// Sizes the memo regions for a launch of `games` games and (re)allocates them; families that are not in use get
+// no region.  Returns the bytes in use (0 = no memo).
+static size_t memo_layout(fmc_ctx *c, uint64_t games, MemoRegion (&R)[kMemoFams]) {
+    auto pow2_at_least = [](uint64_t v) { uint64_t p = 1; while (p < v) p <<= 1; return p; };
+    auto clampu = [](uint64_t v, uint64_t lo, uint64_t hi) { return v < lo ? lo : (v > hi ? hi : v); };
+    uint64_t slots[kMemoFams];
+    // distinct keys per game measured on configs[1] (scripts/memo_study.py): the boosters see tens of distinct rank
+    // vectors per game (their second-resolution clock thresholds), the quantile families a few hundred thousand in all
+    slots[0] = clampu(pow2_at_least(games * 24), 1u << 14, 1u << 27);
+    slots[1] = clampu(pow2_at_least(games * 12), 1u << 13, 1u << 26);
+    slots[2] = slots[3] = clampu(pow2_at_least(games / 2 + 1), 1u << 12, 1u << 22);
+    slots[4] = clampu(pow2_at_least(games / 4 + 1), 1u << 12, 1u << 21);
+    slots[5] = clampu(pow2_at_least(games * 16), 1u << 13, 1u << 25);
+    bool used[kMemoFams];
+    for (int f = 0; f < kMemoFams; ++f) used[f] = family_needed(c, f);
+    uint64_t budget = c->memo_max_bytes;
+    if (budget == 0) {
+        size_t fr = 0, tot = 0;
+        if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) fr = 0;
+        budget = (uint64_t)(fr + c->memo_bytes) / 4;
+        if (budget > (16ull << 30)) budget = 16ull << 30;
+    }
+    auto total = [&]() { uint64_t t = 0; for (int f = 0; f < kMemoFams; ++f) if (used[f]) t += slots[f] << memo_slot_shift(f); return t; };
+    while (total() > budget) {      // halve the largest region until the tables fit
+        int big = -1;
+        for (int f = 0; f < kMemoFams; ++f)
+            if (used[f] && slots[f] > 1024 && (big < 0 || (slots[f] << memo_slot_shift(f)) > (slots[big] << memo_slot_shift(big)))) big = f;
+        if (big < 0) return 0;
+        slots[big] >>= 1;
+    }
+    const size_t need = (size_t)total();
+    if (need == 0) return 0;
+    if (need > c->memo_bytes) {
+        cudaFree(c->d_memo); c->d_memo = nullptr; c->memo_bytes = 0;
+        if (cudaMalloc(&c->d_memo, need) != cudaSuccess) { cudaGetLastError(); return 0; }
+        c->memo_bytes = need;
+        c->memo_valid = false;
+    }
+    uint64_t off = 0;
+    for (int f = 0; f < kMemoFams; ++f) {
+        MemoRegion r;
+        r.base = 0; r.slot_mask = 0; r.slot_shift = (uint32_t)memo_slot_shift(f);
+        if (used[f]) {
+            r.base = (unsigned long long)(uintptr_t)c->d_memo + off;
+            r.slot_mask = (uint32_t)(slots[f] - 1);
+            off += slots[f] << memo_slot_shift(f);
+        }
+        if (r.base != R[f].base || r.slot_mask != R[f].slot_mask) c->memo_valid = false;     // the layout changed
+        R[f] = r;
+    }
+    return need;
+}
+
 extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
     if (!c || !g) return fail(FMC_ERR_INVALID, "fmc_simulate: bad argument");
     CK(cudaSetDevice(c->device));
@@ -536,7 +681,13 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
     }
     if (g->n_matchups != (int)c->matchups.size()) return fail(FMC_ERR_INVALID, "fmc_simulate: n_matchups mismatch");
     cudaStream_t st = (cudaStream_t)g->stream;
-    for (size_t i = 0; i < c->matchups.size(); ++i) c->h_next[i] = c->matchups[i].game_begin;
+    // one launch in flight per context: the work counters, the running player boxes and the memo are per context
+    if (c->launched) CK(cudaStreamWaitEvent(st, c->ev_done, 0));
+    uint64_t games = 0;
+    for (size_t i = 0; i < c->matchups.size(); ++i) {
+        c->h_next[i] = c->matchups[i].game_begin;
+        games += c->matchups[i].game_end - c->matchups[i].game_begin;
+    }
     CK(cudaMemcpyAsync(c->d_next, c->h_next.data(), c->h_next.size() * 8, cudaMemcpyHostToDevice, st));
     SimKernelArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -566,6 +717,7 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
         a.players = g->players_dev; a.player_hist = g->player_hist_dev;
         const size_t need = (size_t)grid * kSimThreads * 2 * (size_t)c->n_slots * sizeof(fmc_player_rec);
         if (need > c->box_scratch_bytes) {
+            CK(cudaDeviceSynchronize());
             cudaFree(c->d_box_scratch); c->d_box_scratch = nullptr; c->box_scratch_bytes = 0;
             CK(cudaMalloc(&c->d_box_scratch, need));
             c->box_scratch_bytes = need;
@@ -583,12 +735,43 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
         const size_t smem = sim_smem_bytes_players(a.name_rows);
         if (test) sim_kernel<true, true><<<grid, kSimThreads, smem, st>>>(a);
         else sim_kernel<false, true><<<grid, kSimThreads, smem, st>>>(a);
+    } else if (c->memo_mode != 0 && c->matchups.size() <= 1024) {
+        // exact memo in front of the walk (fmc_sim_memo.cuh)
+        MemoArgs mm;
+        std::memset(&mm, 0, sizeof(mm));
+        const bool was_valid = c->memo_valid;
+        size_t bytes = memo_layout(c, games, c->memo_region);
+        if (bytes && !(c->memo_mode == 2 && was_valid && c->memo_valid)) CK(cudaMemsetAsync(c->d_memo, 0, bytes, st));
+        for (int f = 0; f < kMemoFams; ++f) mm.region[f] = c->memo_region[f];
+        mm.specs = c->d_specs;
+        mm.enabled = bytes ? 1 : 0;
+        mm.max_trips = c->memo_max_trips;
+        mm.break_parked = c->memo_break_parked;
+        c->memo_valid = bytes != 0;
+        if (test) sim_memo_kernel<true><<<grid, kSimThreads, sim_memo_smem_bytes(), st>>>(a, mm);
+        else sim_memo_kernel<false><<<grid, kSimThreads, sim_memo_smem_bytes(), st>>>(a, mm);
     } else {
         if (test) sim_kernel<true, false><<<grid, kSimThreads, sim_smem_bytes(false), st>>>(a);
         else sim_kernel<false, false><<<grid, kSimThreads, sim_smem_bytes(false), st>>>(a);
     }
     CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev_done, st));
+    c->launched = true;
     return FMC_OK;
+}
+
+// Device scratch of fmc_simulate_host, kept in the context between calls (grow-only): no cudaMalloc / cudaFree per call.
+static cudaError_t scratch(fmc_ctx *c, int slot, size_t bytes, void **out) {
+    fmc_ctx::Scratch &q = c->scr[slot];
+    if (bytes > q.dev_bytes) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return e;
+        cudaFree(q.dev); q.dev = nullptr; q.dev_bytes = 0;
+        if ((e = cudaMalloc(&q.dev, bytes)) != cudaSuccess) return e;
+        q.dev_bytes = bytes;
+    }
+    *out = q.dev;
+    return cudaSuccess;
 }
 
 static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
@@ -616,30 +799,32 @@ static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, 
     int rc = FMC_OK;
     cudaError_t e = cudaSuccess;
     auto bail = [&](cudaError_t err, const char *what) { rc = fail(FMC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(err)); };
+    // the copies below run on the legacy default stream: order them after a launch the caller left in flight
+    if (c->launched && (e = cudaEventSynchronize(c->ev_done)) != cudaSuccess) return fail(FMC_ERR_CUDA, std::string("previous launch: ") + cudaGetErrorString(e));
     do {
-        if (scores_host && games) { if ((e = cudaMalloc(&d_scores, games * 4)) != cudaSuccess) { bail(e, "cudaMalloc scores"); break; } }
+        if (scores_host && games) { if ((e = scratch(c, 0, games * 4, (void **)&d_scores)) != cudaSuccess) { bail(e, "cudaMalloc scores"); break; } }
         if (hist_host) {
-            if ((e = cudaMalloc(&d_hist, hist_n * 4)) != cudaSuccess) { bail(e, "cudaMalloc hist"); break; }
+            if ((e = scratch(c, 1, hist_n * 4, (void **)&d_hist)) != cudaSuccess) { bail(e, "cudaMalloc hist"); break; }
             if ((e = cudaMemsetAsync(d_hist, 0, hist_n * 4)) != cudaSuccess) { bail(e, "memset hist"); break; }
         }
-        if ((e = cudaMalloc(&d_cnt, FMC_N_COUNTERS * 8)) != cudaSuccess) { bail(e, "cudaMalloc counters"); break; }
+        if ((e = scratch(c, 2, FMC_N_COUNTERS * 8, (void **)&d_cnt)) != cudaSuccess) { bail(e, "cudaMalloc counters"); break; }
         if ((e = cudaMemsetAsync(d_cnt, 0, FMC_N_COUNTERS * 8)) != cudaSuccess) { bail(e, "memset counters"); break; }
         if (stream_host && games) {
             const size_t b = games * FMC_MAX_ITERS * FMC_N_SLOTS * 8;
-            if ((e = cudaMalloc(&d_stream, b)) != cudaSuccess) { bail(e, "cudaMalloc stream"); break; }
+            if ((e = scratch(c, 3, b, (void **)&d_stream)) != cudaSuccess) { bail(e, "cudaMalloc stream"); break; }
             if ((e = cudaMemcpy(d_stream, stream_host, b, cudaMemcpyHostToDevice)) != cudaSuccess) { bail(e, "H2D stream"); break; }
         }
         if (trace_host && games) {
             const size_t b = games * FMC_MAX_ITERS * FMC_TRACE_COLS * 8;
-            if ((e = cudaMalloc(&d_trace, b)) != cudaSuccess) { bail(e, "cudaMalloc trace"); break; }
+            if ((e = scratch(c, 4, b, (void **)&d_trace)) != cudaSuccess) { bail(e, "cudaMalloc trace"); break; }
             if ((e = cudaMemsetAsync(d_trace, 0xFF, b)) != cudaSuccess) { bail(e, "memset trace"); break; }   // NaN fill
         }
-        if (iters_host && games) { if ((e = cudaMalloc(&d_iters, games * 2)) != cudaSuccess) { bail(e, "cudaMalloc iters"); break; } }
+        if (iters_host && games) { if ((e = scratch(c, 5, games * 2, (void **)&d_iters)) != cudaSuccess) { bail(e, "cudaMalloc iters"); break; } }
         if (players_host && players_n) {
-            if ((e = cudaMalloc(&d_players, players_n * sizeof(fmc_player_rec))) != cudaSuccess) { bail(e, "cudaMalloc players"); break; }
+            if ((e = scratch(c, 6, players_n * sizeof(fmc_player_rec), (void **)&d_players)) != cudaSuccess) { bail(e, "cudaMalloc players"); break; }
         }
         if (player_hist_host && phist_n) {
-            if ((e = cudaMalloc(&d_phist, phist_n * 4)) != cudaSuccess) { bail(e, "cudaMalloc player hist"); break; }
+            if ((e = scratch(c, 7, phist_n * 4, (void **)&d_phist)) != cudaSuccess) { bail(e, "cudaMalloc player hist"); break; }
             if ((e = cudaMemsetAsync(d_phist, 0, phist_n * 4)) != cudaSuccess) { bail(e, "memset player hist"); break; }
         }
         fmc_sim_args g;
@@ -659,8 +844,9 @@ static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, 
         if (d_players && (e = cudaMemcpy(players_host, d_players, players_n * sizeof(fmc_player_rec), cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H players"); break; }
         if (d_phist && (e = cudaMemcpy(player_hist_host, d_phist, phist_n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H player hist"); break; }
     } while (0);
-    cudaFree(d_scores); cudaFree(d_hist); cudaFree(d_cnt); cudaFree(d_stream); cudaFree(d_trace); cudaFree(d_iters);
-    cudaFree(d_players); cudaFree(d_phist);
+    // big test-mode buffers (injected draws, traces: 46 KB per game) are not worth keeping
+    for (int slot : {3, 4})
+        if (c->scr[slot].dev_bytes > (256u << 20)) { cudaFree(c->scr[slot].dev); c->scr[slot].dev = nullptr; c->scr[slot].dev_bytes = 0; }
     return rc;
 }
 
@@ -872,6 +1058,9 @@ static int64_t pack_host_impl(const fmc_forest_desc *d, int32_t mode, int32_t co
     s.n_dyn = n_dyn;
     for (int i = 0; i < n_dyn; ++i) { s.dyn_col[i] = dyn_cols[i]; s.dyn_row[i] = (int8_t)dyn_rows[i]; }
     if (fold_value17) for (int k = 0; k < kNumMax; ++k) s.fold_value[k] = fold_value17[k];
+    if (n_scaled < 0 || n_scaled > 16) return fail(FMC_ERR_INVALID, "fmc_pack_forest_host: n_scaled must be 0..16");
+    for (int j = 0; j < n_scaled; ++j)
+        if (scaler_cols[j] < 0 || scaler_cols[j] >= kNumMax) return fail(FMC_ERR_INVALID, "fmc_pack_forest_host: scaler column outside the 17 numerics");
     s.n_scaled = n_scaled;
     for (int j = 0; j < n_scaled && j < 16; ++j) { s.scaler_cols[j] = scaler_cols[j]; s.scaler_mean[j] = scaler_mean[j]; s.scaler_scale[j] = scaler_scale[j]; }
     s.tree_begin = tree_begin; s.tree_end = tree_end;
@@ -891,6 +1080,58 @@ static int64_t pack_host_impl(const fmc_forest_desc *d, int32_t mode, int32_t co
     if (stream_out && (int64_t)pf.stream.size() <= stream_cap) std::memcpy(stream_out, pf.stream.data(), pf.stream.size() * 8);
     if (consts_out && (int64_t)pf.consts.size() <= consts_cap) std::memcpy(consts_out, pf.consts.data(), pf.consts.size() * 8);
     return (int64_t)pf.slots.size();
+}
+
+// Host-only: the exact-memo key (fmc_memo.hpp) of n states on the forest specialised like fmc_set_matchups would
+// specialise it -- the same build_rank_spec / memo_key code the kernel runs.  CPU tests use it to check, against the
+// oracle, that states sharing a key share their margins bit for bit.
+extern "C" int64_t fmc_memo_keys_host(const fmc_forest_desc *d, int32_t family, int32_t col0, int32_t col1,
+                                      const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
+                                      const double *scaler_mean, const double *scaler_scale, int64_t n,
+                                      const double *states, uint64_t *keys_out, int32_t *info_out) {
+    if (!d || family < 0 || family >= kMemoFams || n < 0 || (n > 0 && (!states || !keys_out)))
+        return fail(FMC_ERR_INVALID, "fmc_memo_keys_host: bad argument");
+    if (n_scaled < 0 || n_scaled > 16) return fail(FMC_ERR_INVALID, "fmc_memo_keys_host: n_scaled must be 0..16");
+    HostForest f;
+    f.assign(*d);
+    prescale(f);
+    PackSpec s;
+    preset_sim(s);
+    s.active[0] = col0; s.active[1] = col1;
+    if (fold_value17) for (int k = 0; k < kNumMax; ++k) s.fold_value[k] = fold_value17[k];
+    RankSpecInput in;
+    in.xgb = f.kind == FMC_KIND_XGB;
+    in.zm = in.xgb && f.zero_is_missing;
+    in.play_model = family == FMC_PLAY_MODEL;
+    s.n_scaled = n_scaled;
+    for (int j = 0; j < n_scaled; ++j) {
+        if (scaler_cols[j] < 0 || scaler_cols[j] >= kNumMax) return fail(FMC_ERR_INVALID, "fmc_memo_keys_host: scaler column outside the 17 numerics");
+        s.scaler_cols[j] = scaler_cols[j]; s.scaler_mean[j] = scaler_mean[j]; s.scaler_scale[j] = scaler_scale[j];
+        if (in.play_model && scaler_cols[j] < 6) { in.pm_scaled[scaler_cols[j]] = 1; in.pm_mean[scaler_cols[j]] = scaler_mean[j]; in.pm_scale[scaler_cols[j]] = scaler_scale[j]; }
+    }
+    PackedForest pf;
+    const std::string err = pack_forest(f, s, pf);
+    if (!err.empty()) return fail(FMC_ERR_CAPACITY, err);
+    std::vector<RankSpec> rsv(1);
+    RankSpec &rs = rsv[0];
+    const std::string why = build_rank_spec(pf.row_thr, in, rs);
+    if (info_out) {
+        info_out[0] = (int32_t)rs.enabled; info_out[1] = (int32_t)rs.n_thr[0]; info_out[2] = (int32_t)rs.n_thr[1];
+        info_out[3] = (int32_t)pf.constants;
+    }
+    if (!rs.enabled) { g_err = why; return 0; }
+    for (int64_t i = 0; i < n; ++i) {
+        const double *x = states + i * 5;
+        const int down = (int)x[0], sd = (int)x[3], sec = (int)x[4];
+        float v1 = (float)x[1], v2 = (float)x[2];
+        if (in.play_model) {
+            if (in.pm_scaled[1]) v1 = (float)((x[1] - in.pm_mean[1]) / in.pm_scale[1]);
+            if (in.pm_scaled[2]) v2 = (float)((x[2] - in.pm_mean[2]) / in.pm_scale[2]);
+        }
+        keys_out[i] = in.xgb ? memo_key<true>(&rs, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2)
+                             : memo_key<false>(&rs, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2);
+    }
+    return 1;
 }
 
 extern "C" int64_t fmc_pack_forest_host(const fmc_forest_desc *d, int32_t mode, int32_t col0, int32_t col1,

@@ -124,6 +124,9 @@ struct HostForest {
 };
 
 struct PackedForest {
+    // split thresholds of the WALKED nodes per feature row (exact-memo keys, fmc_memo.hpp): what a request's
+    // feature values are compared against, hence all that its outputs depend on
+    std::vector<std::vector<float>> row_thr;
     std::vector<uint64_t> slots;        // node table; child offsets are relative to the table start until relocate()
     std::vector<uint8_t> slot_is_node;  // 1: hi32 carries a child offset (relocatable), 0: raw float64 leaf
     std::vector<uint64_t> stream;       // root slots, kIlp per group, outputs concatenated
@@ -408,6 +411,8 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
                         const uint32_t c = push_slot(0, true);
                         push_slot(0, true);
                         w = node_word(f32_bits(n.thr), (uint32_t)(n.row * kFeatBytes) << kFeatShift, c);
+                        if ((size_t)n.row >= out.row_thr.size()) out.row_thr.resize((size_t)n.row + 1);
+                        out.row_thr[(size_t)n.row].push_back(n.thr);
                         out.internal++;
                         order.push_back(n.l); slot_of.push_back(c); depth_q.push_back(depth_q[qi] + 1);
                         order.push_back(n.r); slot_of.push_back(c + 1); depth_q.push_back(depth_q[qi] + 1);

@@ -735,7 +735,7 @@ __device__ __forceinline__ void write_features(float *col, const Lane &L, int fa
     v[0] = (float)L.down; v[1] = (float)L.dist; v[2] = (float)L.ytg; v[3] = (L.ytg <= 20.0) ? 1.f : 0.f;
     v[4] = (float)sd; v[5] = (float)L.sec;
     if (fam == 5) {   // play_model.xgb: StandardScaler on everything but is_red_zone (dense rows, no missing)
-        const double raw[6] = {(double)L.down, L.dist, L.ytg, 0.0, (double)sd, (double)L.sec};
+        const double raw[6] = {(double)L.down, L.dist, L.ytg, (L.ytg <= 20.0) ? 1.0 : 0.0, (double)sd, (double)L.sec};
 #pragma unroll
         for (int k = 0; k < 6; ++k)
             if (a.pm_scaled[k]) v[k] = (float)((raw[k] - a.pm_mean[k]) / a.pm_scale[k]);
@@ -745,6 +745,8 @@ __device__ __forceinline__ void write_features(float *col, const Lane &L, int fa
         col[6 * 32] = (L.dist >= (L.ytg - 0.5)) ? 1.f : 0.f;
         col[7 * 32] = (L.down == 4 && L.dist <= 2.0) ? 1.f : 0.f;
         col[8 * 32] = (L.ytg <= 33.0) ? 1.f : 0.f;
+        col[9 * 32] = (L.sec > 1800) ? 1.f : 2.f;          // half / two_minute: any NUM_FEATURES name may be in features.pkl
+        col[10 * 32] = ((L.sec % 1800) <= 120) ? 1.f : 0.f;
         return;
     }
     const bool zm = fam <= 1;   // CSR-fed boosters: exact zero == missing
@@ -1005,6 +1007,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
     // ---- flush counters
     atomicAdd(&sh.stat[FMC_C_REQUESTS], requests);
     atomicAdd(&sh.stat[FMC_C_VISITS], visits);
+    if (lane == 0) atomicAdd(&sh.stat[FMC_C_WARP_STEPS], visits);      // lane 0 of a walking warp is always live
     if (tid == 0) sh.stat[FMC_C_ROUNDS] = rounds;
     __syncthreads();
     if (a.counters && tid < FMC_N_COUNTERS && sh.stat[tid]) atomicAdd(&a.counters[tid], sh.stat[tid]);

@@ -6,6 +6,7 @@ but as an object so that several engines (one per GPU / rank) can coexist.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -43,9 +44,17 @@ class Engine:
     def __init__(self, models: Optional[art.ModelSet] = None, *, device: int = 0,
                  policy: str = "heuristic", sampler: str = "normal", stage2: str = "auto",
                  play_temp: Optional[float] = None, qy_noise: float = 0.5,
-                 stage2_standin: Sequence[float] = (0.78, 0.05, 0.17), player: str = "Unknown"):
+                 stage2_standin: Sequence[float] = (0.78, 0.05, 0.17), player: str = "Unknown",
+                 memo: Optional[str] = None, memo_bytes: int = 0):
+        """`memo`: "on" (default) | "off" | "persistent" -- the exact rank-keyed memo in front of the tree walk, the
+        engine's counterpart of the reference's own memo caches (FMC:68-94); results never depend on it.  The
+        environment variable FMC_MEMO overrides the default (the GPU test-suite is run under both settings)."""
         self.models = models if models is not None else art.load_default_models()
         self.ctx = native.Context(device)
+        self.memo = memo if memo is not None else os.environ.get("FMC_MEMO", "on")
+        self.ctx.set_memo(self.memo, max_bytes=memo_bytes,
+                          max_trips=int(os.environ.get("FMC_MEMO_TRIPS", "0")),
+                          break_parked=int(os.environ.get("FMC_MEMO_BREAK", "0")))
         self.player = player
         if policy == "play_json" and "play_binary" not in self.models:
             raise ValueError("policy='play_json' but the model set has no play_binary forest (play_model.json + "

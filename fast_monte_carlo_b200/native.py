@@ -25,7 +25,8 @@ N_SLOTS = 16
 MAX_ITERS = 360
 TRACE_COLS = 8
 COUNTER_NAMES = ("games", "plays", "iters", "pass", "comp", "inc", "int", "sack", "run", "td", "fga", "fg",
-                 "punt", "go", "hist_overflow", "rounds", "requests", "visits", "ph_overflow")
+                 "punt", "go", "hist_overflow", "rounds", "requests", "visits", "ph_overflow", "warp_steps",
+                 "memo_probes", "memo_hits", "trips")
 PH_YDS_BINS, PH_YDS_OFFSET, PH_CNT_BINS = 8192, 1000, 128
 PH_BINS = PH_YDS_BINS + 5 * PH_CNT_BINS
 
@@ -143,6 +144,7 @@ def load_library():
     L.fmc_set_params.argtypes = [C.c_void_p, C.POINTER(Params)]
     L.fmc_set_matchups.argtypes = [C.c_void_p, C.c_int32, C.POINTER(Matchup)]
     L.fmc_simulate.argtypes = [C.c_void_p, C.POINTER(SimArgs)]
+    L.fmc_set_memo.argtypes = [C.c_void_p, C.c_int32, C.c_uint64, C.c_int32, C.c_int32]
     L.fmc_simulate_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]
     L.fmc_simulate_players_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -165,6 +167,9 @@ def load_library():
     L.fmc_pack_forest_host.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    L.fmc_memo_keys_host.restype = C.c_int64
+    L.fmc_memo_keys_host.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = L
     return L
 
@@ -175,6 +180,7 @@ EXPORTED_SYMBOLS = (
     "fmc_simulate_host", "fmc_tree_predict", "fmc_tree_predict_host", "fmc_packed_slots", "fmc_sync",
     "fmc_gather_probe", "fmc_debug_errors",
     "fmc_pack_forest_host", "fmc_pack_forest_host_dyn", "fmc_set_usage", "fmc_simulate_players_host",
+    "fmc_set_memo", "fmc_memo_keys_host",
 )
 
 
@@ -253,6 +259,35 @@ def pack_forest_host(f, *, mode: int, cols=(-1, -1), fold_values=None, tree_begi
                 stream_off=[int(x) for x in info[8:16]], n_groups=[int(x) for x in info[16:24]],
                 consts_off=[int(x) for x in info[24:32]])
     return slots[:n].copy(), stream[:int(info[5])].copy(), consts[:int(info[6])].copy(), meta
+
+
+def memo_keys_host(f, family: int, states: np.ndarray, *, cols=(-1, -1), fold_values=None):
+    """Host-only: exact-memo keys of `states` ([n, 5] = down, distance, yardsToGoal, score_diff, seconds) on forest `f`
+    specialised like the simulation specialises it.  Returns (keys uint64[n] | None when not memoisable, info dict)."""
+    L = load_library()
+    d, keep = forest_desc(f)
+    fv = np.zeros(17, dtype=np.float64)
+    if fold_values is not None:
+        fv[:] = fold_values
+    ns = 0
+    sc = sm = ss = None
+    if getattr(f, "scaler_cols", None) is not None:
+        sc = np.ascontiguousarray(f.scaler_cols, np.int32)
+        sm = np.ascontiguousarray(f.scaler_mean, np.float64)
+        ss = np.ascontiguousarray(f.scaler_scale, np.float64)
+        ns = int(sc.shape[0])
+    st = np.ascontiguousarray(states, dtype=np.float64).reshape(-1, 5)
+    keys = np.zeros(st.shape[0], dtype=np.uint64)
+    info = np.zeros(4, dtype=np.int32)
+    rc = L.fmc_memo_keys_host(C.byref(d), int(family), int(cols[0]), int(cols[1]), fv.ctypes.data, ns,
+                              None if sc is None else sc.ctypes.data, None if sm is None else sm.ctypes.data,
+                              None if ss is None else ss.ctypes.data, st.shape[0], st.ctypes.data, keys.ctypes.data,
+                              info.ctypes.data)
+    if rc < 0:
+        _check(int(rc))
+    meta = dict(memoisable=bool(info[0]), n_thr_distance=int(info[1]), n_thr_ytg=int(info[2]), constants=int(info[3]),
+                why=L.fmc_last_error().decode() if rc == 0 else "")
+    return (keys if rc == 1 else None), meta
 
 
 class Context:
@@ -355,6 +390,14 @@ class Context:
                         u.col[MODEL_INDEX[name]][e] = int(cols[e])
         _check(self._L.fmc_set_usage(self._h, len(teams), C.cast(arr, C.c_void_p), int(n_slots)))
         self.n_slots, self.has_usage = int(n_slots), True
+
+    MEMO_MODES = {"off": 0, "on": 1, "persistent": 2}
+
+    def set_memo(self, mode="on", max_bytes: int = 0, max_trips: int = 0, break_parked: int = 0) -> None:
+        """Exact rank-keyed memo in front of the tree walk (fmc_set_memo): "off" | "on" (default, cleared at every
+        launch) | "persistent" (kept between launches on the same tables).  Results never depend on it."""
+        m = self.MEMO_MODES[mode] if isinstance(mode, str) else int(mode)
+        _check(self._L.fmc_set_memo(self._h, m, int(max_bytes), int(max_trips), int(break_parked)))
 
     def packed_slots(self, matchup: int = 0) -> np.ndarray:
         out = np.zeros((N_MODELS, 2), dtype=np.int32)

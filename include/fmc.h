@@ -11,7 +11,9 @@
  *
  * Conventions: plain C types only; every call returns 0 on success or a negative fmc_status and
  * leaves a message retrievable with fmc_last_error() (thread-local).  One context per GPU, used
- * from one host thread at a time.  Pointers named *_dev are device pointers owned by the caller
+ * from one host thread at a time, with ONE fmc_simulate in flight: a second fmc_simulate (on any stream) is
+ * ordered after the previous one on the device, and every call that re-specialises or re-uploads the node
+ * tables first waits for the launches in flight.  Pointers named *_dev are device pointers owned by the caller
  * (e.g. torch tensors); pointers named *_host are host memory.  Calls taking `stream` are
  * asynchronous on that CUDA stream (a cudaStream_t passed as void*, NULL = default stream).
  * There is no CPU fallback: without a usable sm_100 device fmc_create fails.
@@ -25,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FMC_ABI_VERSION 3
+#define FMC_ABI_VERSION 4
 
 typedef enum {
     FMC_OK = 0,
@@ -145,7 +147,11 @@ enum {
     FMC_C_RUN, FMC_C_TD, FMC_C_FGA, FMC_C_FG, FMC_C_PUNT, FMC_C_GO, FMC_C_HIST_OVERFLOW,
     FMC_C_ROUNDS, FMC_C_REQUESTS,
     FMC_C_VISITS, /* 8-byte node slots gathered for live requests (tree levels walked x lanes) */
-    FMC_C_PH_OVERFLOW /* player-histogram samples clamped into the first / last bin */
+    FMC_C_PH_OVERFLOW, /* player-histogram samples clamped into the first / last bin */
+    FMC_C_WARP_STEPS,  /* warp-level node gathers of the tree walk (tree levels walked x trees per group, per warp) */
+    FMC_C_MEMO_PROBES, /* requests looked up in the exact memo (fmc_set_memo) */
+    FMC_C_MEMO_HITS,   /* ... of which were answered from it (the rest were walked: FMC_C_REQUESTS) */
+    FMC_C_TRIPS        /* warp-level passes of the state machine (memo kernel) */
 };
 
 #define FMC_N_SLOTS 16           /* injected-draw record per (game, loop iteration); see DESIGN.md */
@@ -198,6 +204,19 @@ int fmc_set_matchups(fmc_ctx *ctx, int32_t n, const fmc_matchup *m);
  * fmc_simulate runs the player instantiation of the kernel: the sampled names become extra 0/1 feature rows
  * of a request, so the node tables stay specialised per orientation only. */
 int fmc_set_usage(fmc_ctx *ctx, int32_t n_matchups, const fmc_team_usage *teams, int32_t n_slots);
+
+/* Exact memo of model outputs in front of the tree walk -- the B200 counterpart of the reference's own memo caches
+ * (_PLAY_CACHE / _PASS1_CACHE / _PASS2_CACHE / _*_Q_CACHE, FMC:68-94, 343-357, 740-747, 780-812), but EXACT: the key
+ * is the vector of threshold ranks of the request's features on the specialised forest, so a hit returns bit for
+ * bit what the walk would (csrc/fmc_memo.hpp).  Results never depend on the mode.
+ *   mode 0: off -- every request is walked (the roofline / tree-eval measurements use this);
+ *   mode 1: on (default), the table is cleared at the start of every fmc_simulate;
+ *   mode 2: on, the table is kept between calls for as long as the node tables stay the same.
+ * max_bytes: device memory the tables may take (0 = default: up to 1/4 of the free memory, at most 16 GiB; they
+ * are sized by the games of the launch).  max_trips / break_parked: scheduling knobs of the memo kernel (plays a
+ * lane may chain per round; lanes of a warp that must wait before the warp stops chaining); 0 = default.
+ * Player mode (fmc_set_usage) and slates of more than 1024 matchups always run unmemoised. */
+int fmc_set_memo(fmc_ctx *ctx, int32_t mode, uint64_t max_bytes, int32_t max_trips, int32_t break_parked);
 
 /* Replaces simulate_matchup's pool of _run_pair workers (FMC:1467-1521): plays every game of every
  * matchup range to completion on the GPU.  Asynchronous on args->stream. */
@@ -261,6 +280,18 @@ int64_t fmc_pack_forest_host(const fmc_forest_desc *desc, int32_t mode, int32_t 
                              const double *scaler_mean, const double *scaler_scale, int32_t tree_begin,
                              int32_t tree_end, uint64_t *slots_out, int64_t slots_cap, uint64_t *stream_out,
                              int64_t stream_cap, uint64_t *consts_out, int64_t consts_cap, int32_t *info_out);
+
+/* Host-only, needs no GPU: exact-memo keys (fmc_set_memo, csrc/fmc_memo.hpp) of n simulation states on `desc`
+ * specialised as fmc_set_matchups specialises family `family` (simulation preset: numerics 6..11 folded to
+ * fold_value17[], hot columns col0 / col1).  states = float64 [n][5]: down, distance, yardsToGoal, score_diff,
+ * seconds_remaining (the derived flags follow from them, FMC:996-1021).  keys_out[n] = the 64-bit keys of matchup 0,
+ * team 0.  Returns 1, 0 when the forest's rank vector does not fit a key (fmc_last_error says why; such a family is
+ * always walked) or a negative fmc_status.  info_out[4] = {memoisable, thresholds on distance, on yardsToGoal,
+ * constant trees}.  Evaluates no tree: tests group oracle margins by key to check that equal keys mean equal outputs. */
+int64_t fmc_memo_keys_host(const fmc_forest_desc *desc, int32_t family, int32_t col0, int32_t col1,
+                           const double *fold_value17, int32_t n_scaled, const int32_t *scaler_cols,
+                           const double *scaler_mean, const double *scaler_scale, int64_t n, const double *states,
+                           uint64_t *keys_out, int32_t *info_out);
 
 #ifdef __cplusplus
 }

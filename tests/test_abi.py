@@ -22,7 +22,7 @@ def test_exports_every_declared_symbol(native_lib):
     for n in names:
         assert hasattr(native_lib, n), f"{n} declared in include/fmc.h but not exported"
     assert set(names) == set(native.EXPORTED_SYMBOLS)
-    assert native_lib.fmc_abi_version() == 3
+    assert native_lib.fmc_abi_version() == 4
 
 
 def test_no_cpu_fallback(native_lib):
