@@ -56,7 +56,13 @@ def parse():
                          "(fast_monte_carlo_b200/data/players_focus_synthetic.csv), per-game player box written")
     ap.add_argument("--cpu-games", type=int, default=0, help="games of the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--memo", default=None, choices=["on", "off", "persistent"],
+                    help="exact rank-keyed memo in front of the tree walk (default: on; FMC_MEMO overrides the default)")
+    ap.add_argument("--roofline-steps", type=int, default=2, help="timed memo-off launches behind the roofline record")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-tree-eval", action="store_true")
+    ap.add_argument("--tree-states", type=int, default=1 << 26, help="states of the configs[2] tree-eval sub-record")
     return ap.parse_args()
 
 
@@ -124,6 +130,8 @@ def workload(args, n_gpus):
                     if getattr(args, "players", False) else "Unknown (no usage tables shipped)"),
         "parallelism": f"games sharded over {n_gpus} GPU(s); one NCCL all-reduce of the histograms per step",
         "l2": "flushed between timed steps (256 MiB write); node tables are meant to be cache-resident",
+        "memo": "exact rank-keyed memo of model outputs in front of the tree walk, cleared at every step (--memo off: every "
+                "request is walked; the roofline record is measured that way)",
     }
 
 
@@ -313,6 +321,109 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------------------------
+# roofline pieces
+# ----------------------------------------------------------------------------------------------
+def ncu_summary(name="sim_kernel_ncu_latest.json"):
+    p = os.path.join(ROOT, "profiles", name)
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+def l1_pipe_roofline(warp_steps, lane_visits, kernel_s, n_sms, sm_mhz, ncu, algo_bytes, traffic, kernel):
+    """The bound of the tree walk is the L1 data pipe (one wavefront per clock per SM): every tree level of a warp
+    costs one feature LDS wavefront plus the wavefronts of its 8-byte node gather.  `warp_steps` is counted by the
+    kernel itself (FMC_C_WARP_STEPS / fmc_predict_stats); wavefronts per step come from the committed ncu capture
+    of the same kernel (profiles/: l1tex__data_pipe_lsu_wavefronts over the step counter of the profiled launch,
+    else 1 + lgds wavefronts per global load request)."""
+    d = (ncu or {}).get("derived", {})
+    per_step = d.get("l1_wavefronts_per_warp_step") or (1.0 + d.get("lgds_wavefronts_per_global_ld_request", 2.37))
+    wavefronts = warp_steps * per_step
+    peak = n_sms * sm_mhz * 1e6              # wavefronts / s
+    achieved = wavefronts / kernel_s
+    hbm, hbm_src = measured_peaks()
+    return {
+        "bound": "l1-data-pipe", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "Gwavefront/s",
+        "frac": achieved / peak, "traffic": traffic, "kernel": kernel, "kernel_ms_per_launch": kernel_s * 1e3,
+        "warp_level_node_gathers_per_launch": warp_steps, "l1_wavefronts_per_gather_level": per_step,
+        "peak_source": f"{n_sms} SMs x {sm_mhz:.0f} MHz (median SM clock sampled during the timed launches) x 1 wavefront/clk/SM",
+        "ncu_crosscheck": {"l1_data_pipe_wavefronts_per_sm_cycle": d.get("l1_data_pipe_wavefronts_per_sm_cycle"),
+                           "source": (ncu or {}).get("report")},
+        "gathered": {"node_slots_per_launch": lane_visits, "gbs": lane_visits * 8.0 / kernel_s / 1e9},
+        "algorithmic": {"bytes_per_launch": algo_bytes, "gbs": algo_bytes / kernel_s / 1e9,
+                        "note": "SURVEY 8(d): 8 B per internal-node visit + leaf fetch per tree on the UNPRUNED forests x requests"},
+        "hbm": {"peak_gbs": hbm, "peak_source": hbm_src, "traffic_bytes_per_launch": traffic,
+                "frac": (traffic / kernel_s / 1e9 / hbm) if traffic else None,
+                "note": "the node tables are cache-resident by design: DRAM carries score words, histogram atomics and spills"},
+    }
+
+
+def tree_states(n, seed=3):
+    """SURVEY 8(d) config 3 states (see scripts/bench_trees.py)."""
+    import numpy as np
+    from fast_monte_carlo_b200 import priors
+    sp = priors.load_sp_flex(priors.packaged_priors_path()).drop_duplicates(subset=["RATING", "OFFENSE", "DEFENSE"])
+    teams = sp[["RATING", "OFFENSE", "DEFENSE"]].to_numpy(dtype=float)
+    rng = np.random.default_rng(seed)
+    x = np.zeros((n, 17))
+    x[:, 0] = rng.choice([1, 2, 3, 4], size=n, p=[.38, .31, .21, .10])
+    x[:, 1] = np.clip(np.round(rng.normal(8, 4, n), 1), 0.5, 30)
+    x[:, 2] = rng.integers(1, 100, n)
+    x[:, 3] = x[:, 2] <= 20
+    x[:, 4] = np.round(rng.normal(0, 14, n))
+    x[:, 5] = rng.integers(1, 3601, n)
+    x[:, 6] = x[:, 7] = 3
+    o = rng.integers(0, len(teams), n); d = (o + rng.integers(1, len(teams), n)) % len(teams)
+    x[:, 8] = teams[o, 0]; x[:, 9] = teams[o, 1]; x[:, 10] = teams[d, 2]; x[:, 11] = teams[d, 0]
+    x[:, 12] = x[:, 1] >= x[:, 2] - 0.5
+    x[:, 13] = (x[:, 0] == 4) & (x[:, 1] <= 2)
+    x[:, 14] = x[:, 2] <= 33
+    x[:, 15] = np.where(x[:, 5] > 1800, 1, 2)
+    x[:, 16] = (x[:, 5] % 1800) <= 120
+    return x
+
+
+def tree_eval_record(eng, ms, local, n_total=1 << 26, batch=1 << 22):
+    """BASELINE configs[2]: play_model.xgb + the nine quantile models on 2^26 synthetic states through fmc_tree_predict
+    (device buffers), with the same L1-data-pipe accounting as the simulation kernel."""
+    import torch
+    from fast_monte_carlo_b200 import artifacts as art
+    names = ("play_model", "pass_yards", "run_yards", "sack_yards")
+    rows = torch.from_numpy(tree_states(batch)).cuda(local)
+    outs = {nm: torch.empty((batch, ms[nm].n_outputs), dtype=torch.float64, device=rows.device) for nm in names}
+    st = torch.cuda.current_stream()
+
+    def run_batch():
+        for nm in names:
+            eng.ctx.tree_predict_device(art.MODEL_IDS[nm], rows.data_ptr(), batch, outs[nm].data_ptr(), cuda_stream=st.cuda_stream)
+
+    run_batch(); torch.cuda.synchronize()
+    eng.ctx.predict_stats(reset=True)
+    n_batches = max(1, n_total // batch)
+    sampler = ClockSampler(local); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n_batches):
+        run_batch()
+    e1.record(); torch.cuda.synchronize()
+    clocks = sampler.stop()
+    sec = e0.elapsed_time(e1) / 1e3
+    stats = eng.ctx.predict_stats(reset=True)
+    n_done = n_batches * batch
+    algo = sum(algorithmic_bytes_per_row(ms[nm]) for nm in names) * n_done
+    mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    rf = l1_pipe_roofline(stats["warp_steps"], stats["visits"], sec, eng.ctx.sm_count, mhz,
+                          ncu_summary("predict_kernel_ncu_latest.json"), algo, None, "predict_kernel")
+    return {"workload": f"configs[2]: {n_done:,} synthetic states x (play_model.xgb + pass/run/sack q10/q50/q90 = "
+                        f"{sum(ms[nm].n_trees for nm in names)} trees), fmc_tree_predict on resident rows, batches of {batch:,}",
+            "states_per_sec": n_done / sec, "ms": sec * 1e3, "gpu_launches": n_batches * len(names), "clocks": clocks,
+            "roofline": rf}
+
+
+# ----------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------
 def run_ours(args):
@@ -330,12 +441,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
 
-    from fast_monte_carlo_b200 import native
+    from fast_monte_carlo_b200 import api, native, priors
     from fast_monte_carlo_b200.engine import Engine, MatchupSpec
     ms = load_models(args.stage2)
-    eng = Engine(ms, device=local, stage2="booster" if args.stage2 == "synthetic" else "standin")
+    eng = Engine(ms, device=local, stage2="booster" if args.stage2 == "synthetic" else "standin", memo=args.memo)
     if args.workload in ("slate", "season"):
-        from fast_monte_carlo_b200 import api
         pairs, sp_df = slate_pairs() if args.workload == "slate" else season_pairs()
         spec = api.slate_specs(pairs, args.slate_games, sp_df, rank, world)
         G = sum(m.game_end - m.game_begin for m in spec)          # this rank's games per step
@@ -373,92 +483,171 @@ def run_ours(args):
             dist.all_reduce(hist64)
             dist.all_reduce(counters)
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-        flush.zero_()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    def timed(n_steps, n_warm):
+        """n_warm untimed + n_steps timed steps, L2 flushed between steps; returns (total ms, per-step ms, counters of
+        one step summed over ranks, clocks)."""
+        for _ in range(n_warm):
+            step()
+            flush.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for i in range(n_steps):
+            ev[i][0].record()
+            step()
+            ev[i][1].record()
+            flush.zero_()
+        k1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clk = sampler.stop()
+        tot = k0.elapsed_time(k1)
+        per = [x.elapsed_time(y) for x, y in ev]
+        c = counters.cpu().numpy()
+        sc = {k: int(c[i]) for i, k in enumerate(native.COUNTER_NAMES)}
+        t = torch.tensor([tot, sum(per)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), per, sc, clk
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    plays_local = 0
-    step_counters = None
-    for i in range(args.steps):
-        ev[i][0].record()
-        step()
-        ev[i][1].record()
-        flush.zero_()
-    k1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    clocks = sampler.stop()
-    total_ms = k0.elapsed_time(k1)
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    c = counters.cpu().numpy()
-    step_counters = {k: int(c[i]) for i, k in enumerate(native.COUNTER_NAMES)}   # all ranks (after all-reduce)
-    t = torch.tensor([total_ms, sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kernel_ms = float(t[0]), float(t[1])
+    # ---- headline: the engine as shipped (exact memo on unless --memo off) --------------------------------------
+    total_ms, kernel_ms, step_ms, step_counters, clocks = timed(args.steps, max(args.warmup, 3))
     plays_step = step_counters["plays"]
     games_step = step_counters["games"]
     assert games_step == total_games, (games_step, total_games)
     value = plays_step * args.steps / (total_ms / 1e3)
 
-    # ---- end-to-end through the C-ABI host-buffer call --------------------------------------------------
-    e2e_plays, e2e_t = 0, 0.0
-    e2e_steps_s = []
-    h2d = d2h = 0
-    sampler2 = ClockSampler(local)
-    sampler2.start()
-    table_bytes = sum(int(eng.ctx.packed_slots(i).sum()) for i in range(n_m)) * 8
-    for i in range(args.e2e_steps + 1):
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        eng.set_matchups(spec)                                   # forces re-specialisation + H2D of the tables
-        r = eng.simulate_host(SEED, want_scores=True, want_hist=True, want_players=box is not None)
-        h = torch.from_numpy(r["hist"].astype(np.int64))
-        if world > 1:
-            hd = h.to(dev)
-            dist.all_reduce(hd)
-            h = hd.cpu()
-        dt = time.perf_counter() - t0
-        if i == 0:
-            continue                                             # warm-up
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        pp = torch.tensor([r["counters"]["plays"]], dtype=torch.int64, device=dev)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dist.all_reduce(pp)
-        e2e_t += float(tt[0])
-        e2e_plays += int(pp[0])
-        e2e_steps_s.append(float(tt[0]))
-        h2d = table_bytes + 200 + 8
-        d2h = G * 4 + int(np.prod(r["hist"].shape)) * 4 + native.N_COUNTERS * 8 + (box.numel() * 8 if box is not None else 0)
-    e2e_value = e2e_plays / e2e_t if e2e_t > 0 else None
-    e2e_clocks = sampler2.stop()
+    # ---- end to end through the reference's Python entry point (FMC:1467-1521 simulate_matchup), host buffers ----
+    # every sample: api.simulate_matchup -> fmc_simulate_host (tables specialised + uploaded when the pair changes,
+    # kernel, per-game score words + histogram + counters copied back) -> the 2n-row sims_df the reference returns;
+    # under torchrun every rank plays its slice of the 2n games (game_range) and the histograms are all-reduced
+    e2e = None
+    if args.workload == "matchup" and not args.players:
+        sp_df = priors.load_sp_flex(priors.packaged_priors_path())
+        A = priors.build_team_context_from_sp_flex(KSU[0], 2025, 1, sp_df)
+        B = priors.build_team_context_from_sp_flex(ISU[0], 2025, 1, sp_df)
+        samples, plays_e2e = [], 0
+        sampler2 = ClockSampler(local)
+        sampler2.start()
+        for i in range(args.e2e_steps + 1):
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            df, _ = api.simulate_matchup(A, B, n=total_games // 2, seed=SEED, show_progress=False, engine=eng,
+                                         game_range=(rank * G, (rank + 1) * G))
+            h = torch.from_numpy(df.attrs["hist"].astype(np.int64))
+            if world > 1:
+                hd = h.to(dev)
+                dist.all_reduce(hd)
+                h = hd.cpu()
+            dt = time.perf_counter() - t0
+            assert len(df) == G and int(h.sum()) == total_games
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            pp = torch.tensor([df.attrs["counters"]["plays"]], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(pp)
+            if i == 0:
+                first = float(tt[0])
+                continue                                          # warm-up (also: first specialisation of the pair)
+            samples.append(float(tt[0]))
+            plays_e2e += int(pp[0])
+            del df
+        table_bytes = int(eng.ctx.packed_slots(0).sum()) * 8
+        e2e = {"value": plays_e2e / sum(samples), "unit": UNIT,
+               "h2d_bytes_per_step": 8 * n_m + 64, "d2h_bytes_per_step": G * 4 + 2 * native.HIST_BINS ** 2 * 4 + native.N_COUNTERS * 8,
+               "step_seconds": samples, "first_call_seconds": first, "clocks": sampler2.stop(),
+               "tables_h2d_bytes_first_call": table_bytes,
+               "how": "api.simulate_matchup (the reference's Python entry point) -> fmc_simulate_host through ctypes: kernel, "
+                      "per-game score words + histogram + counters copied to host, 2n-row sims_df built; host wall clock, "
+                      "max over ranks.  The pair's tables are specialised + uploaded in the first (untimed) call and kept "
+                      "while the pair stays the same (first_call_seconds includes it)"}
+    else:
+        # slates / player mode: the C-ABI host-buffer call (tables re-specialised + uploaded every sample)
+        samples, plays_e2e = [], 0
+        sampler2 = ClockSampler(local)
+        sampler2.start()
+        table_bytes = sum(int(eng.ctx.packed_slots(i).sum()) for i in range(n_m)) * 8
+        for i in range(args.e2e_steps + 1):
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            eng.ctx.invalidate_tables()                            # every sample pays specialisation + upload again
+            eng.set_matchups(spec)
+            r = eng.simulate_host(SEED, want_scores=True, want_hist=True, want_players=box is not None)
+            h = torch.from_numpy(r["hist"].astype(np.int64))
+            if world > 1:
+                hd = h.to(dev)
+                dist.all_reduce(hd)
+                h = hd.cpu()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            pp = torch.tensor([r["counters"]["plays"]], dtype=torch.int64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(pp)
+            if i == 0:
+                continue
+            samples.append(float(tt[0]))
+            plays_e2e += int(pp[0])
+        e2e = {"value": plays_e2e / sum(samples) if samples else None, "unit": UNIT, "h2d_bytes_per_step": 200 + 8 * n_m,
+               "d2h_bytes_per_step": G * 4 + int(np.prod(hist.shape)) * 4 + native.N_COUNTERS * 8 + (box.numel() * 8 if box is not None else 0),
+               "step_seconds": samples, "clocks": sampler2.stop(), "tables_h2d_bytes_first_call": table_bytes,
+               "how": "fmc_simulate_host through ctypes: kernel, per-game scores + histogram + counters (+ player box) copied "
+                      "to host; host wall clock, max over ranks"}
+
+    # ---- roofline of the tree walk: the same workload with the memo OFF, so that no tree work is hidden ----------
+    roof = None
+    memo_rec = {"mode": eng.memo, "probes_per_step": step_counters["memo_probes"], "hits_per_step": step_counters["memo_hits"],
+                "hit_rate": step_counters["memo_hits"] / max(step_counters["memo_probes"], 1),
+                "walked_requests_per_step": step_counters["requests"],
+                "note": "exact rank-keyed memo (csrc/fmc_memo.hpp), cleared at the start of every step; results are "
+                        "bit-identical with it off (tests/test_gpu_memo.py)"}
+    if not args.no_roofline:
+        eng.ctx.set_memo("off")
+        r_total, r_kernel, r_steps, r_counters, r_clocks = timed(args.roofline_steps, 1)
+        eng.ctx.set_memo(eng.memo)
+        assert r_counters["plays"] == plays_step, "the memo must not change the games"
+        if rank == 0:
+            algo = step_algorithmic_bytes(ms, r_counters, args.stage2 == "synthetic") / world
+            kern_s = (r_kernel / args.roofline_steps) / 1e3
+            mhz = r_clocks.get("sm_mhz") or r_clocks.get("sm_max_mhz") or 1965.0
+            roof = l1_pipe_roofline(r_counters["warp_steps"] / world, r_counters["visits"] / world, kern_s, eng.ctx.sm_count,
+                                    mhz, ncu_summary(), algo, ncu_traffic(G), "fmc::sim_kernel (memo off)")
+            roof["plays_per_sec_memo_off"] = r_counters["plays"] * args.roofline_steps / (r_total / 1e3)
+            roof["step_ms"] = r_steps
+            roof["clocks"] = r_clocks
+            try:
+                coh = eng.ctx.gather_probe_coherent(1 << 20, 256, 2000)
+                coh2 = eng.ctx.gather_probe_coherent(1 << 20, 512, 2000)
+                rnd_l1 = eng.ctx.gather_probe(64 << 10, 4000)
+                rnd_l2 = eng.ctx.gather_probe(8 << 20, 1000)
+                roof["gather_probe"] = {
+                    "coherent_256B_gbs": coh["gbs"], "coherent_512B_gbs": coh2["gbs"], "random_l1_gbs": rnd_l1, "random_l2_gbs": rnd_l2,
+                    "frac_of_coherent_probe": roof["gathered"]["gbs"] / coh["gbs"],
+                    "note": "fmc_gather_probe_coherent: lanes of a warp gather 8-byte slots inside one 256 B / 512 B window "
+                            "(1 MiB table, L2-resident, streamed through L1) like a tree level, nothing else per step; "
+                            "the random-lane probes of round 1 are kept for reference (a walk's lanes are not random)"}
+            except Exception as exc:                       # pragma: no cover
+                print(f"gather probe failed: {exc}", file=sys.stderr)
+
+    tree = None
+    if rank == 0 and not args.no_tree_eval:
+        try:
+            tree = tree_eval_record(eng, load_models("standin") if args.stage2 != "standin" else ms, local,
+                                    n_total=args.tree_states)
+        except Exception as exc:                           # pragma: no cover
+            print(f"tree_eval failed: {exc}", file=sys.stderr)
 
     if rank == 0:
-        # achievable gather rates on this GPU (8-byte dependent gathers, fmc_gather_probe): the denominators the
-        # north star asks for ("tree-eval kernels as a fraction of achievable L2 bandwidth")
-        try:
-            l1_gbs = eng.ctx.gather_probe(64 << 10, 4000)
-            l2_gbs = eng.ctx.gather_probe(8 << 20, 1000)
-        except Exception as exc:                       # pragma: no cover
-            l1_gbs = l2_gbs = None
-            print(f"gather probe failed: {exc}", file=sys.stderr)
-        peak, peak_src = measured_peaks()
-        algo = step_algorithmic_bytes(ms, step_counters, args.stage2 == "synthetic") / world   # per launch (one GPU)
-        kern_s = (kernel_ms / args.steps) / 1e3
-        achieved = algo / kern_s / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -466,36 +655,17 @@ def run_ours(args):
             "data": "synthetic", "config": workload(args, n_gpus),
             "games_per_sec": games_step * args.steps / (total_ms / 1e3),
             "plays_per_game": plays_step / games_step,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "step_seconds": e2e_steps_s, "clocks": e2e_clocks,
-                    "how": "fmc_simulate_host through ctypes: forest specialisation + table upload, kernel, "
-                           "per-game scores + histogram + counters copied to host; host wall clock, max over ranks"},
+            "e2e": e2e,
             "gpu_launches": args.steps,
             "step_ms": step_ms,
             "clocks": clocks,
-            "roofline": {
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(G), "peak_source": peak_src, "kernel": "fmc::sim_kernel",
-                "kernel_ms_per_launch": kernel_ms / args.steps,
-                "algorithmic_bytes_per_launch": algo,
-                "note": "algorithmic bytes = SURVEY 8(d) per-row figures on the unpruned forests x requests per "
-                        "family; the node tables are L1/L2-resident by design, so this gather traffic never reaches "
-                        "HBM and frac can exceed 1 -- DRAM traffic proper is `traffic`",
-            },
-            "gather": {
-                "node_slots_gathered_per_launch": step_counters["visits"] / world,
-                "achieved_gbs": step_counters["visits"] / world * 8.0 / kern_s / 1e9,
-                "probe_l1_gbs": l1_gbs, "probe_l2_gbs": l2_gbs,
-                "frac_of_l2_probe": (step_counters["visits"] / world * 8.0 / kern_s / 1e9 / l2_gbs) if l2_gbs else None,
-                "frac_of_l1_probe": (step_counters["visits"] / world * 8.0 / kern_s / 1e9 / l1_gbs) if l1_gbs else None,
-                "note": "8 B x node slots actually gathered by live requests on the SPECIALISED tables (counter "
-                        "FMC_C_VISITS) / kernel time, against fmc_gather_probe: dependent 8-byte read-only gathers "
-                        "through a 64 KiB (L1-resident) and an 8 MiB (L2-resident) random cyclic table",
-            },
+            "memo": memo_rec,
+            "roofline": roof,
+            "tree_eval": tree,
             "mix": {k: step_counters[k] for k in ("pass", "comp", "inc", "int", "sack", "run", "td", "fga", "fg", "punt", "go")},
             "device": eng.ctx.device_name,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(ms, args)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -24,6 +24,7 @@ usage data every name is "Unknown" and `players_df` is empty, as in the shipped 
 from __future__ import annotations
 
 import os
+import threading
 import time
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -45,6 +46,9 @@ PLAYER_COLS = [
 ]
 
 _ENGINES: Dict[tuple, Engine] = {}
+# The engine of a device is shared process-wide (like the reference's module-level models) and holds the matchup list
+# of the call in progress: calls from several threads are serialised.
+_ENGINE_LOCK = threading.RLock()
 # joint score histogram [2, 128, 128] + event counters of the most recent simulate_matchup call
 LAST_RUN: Dict[str, object] = {}
 
@@ -67,25 +71,34 @@ def _fresh_seed() -> int:
 def simulate_matchup(teamA: TeamContext, teamB: TeamContext, n: int = 100, seed: Optional[int] = None,
                      show_progress: bool = True, collect_players: bool = False,
                      players_csv: Optional[str] = None, processes: Optional[int] = None,
-                     *, engine: Optional[Engine] = None) -> Tuple[pd.DataFrame, Optional[pd.DataFrame]]:
+                     *, engine: Optional[Engine] = None,
+                     game_range: Optional[Tuple[int, int]] = None) -> Tuple[pd.DataFrame, Optional[pd.DataFrame]]:
+    """`game_range=(g0, g1)` (ours, for one process per GPU): simulate only games [g0, g1) of the 2n -- `shard_range`
+    gives a rank its slice; the rows returned are those games, and the histograms of the ranks add up to the run's
+    (`merge_histograms`).  A given seed gives the same games whatever the split."""
     eng = engine if engine is not None else get_engine()
     games = 2 * int(n)
+    g0, g1 = (0, games) if game_range is None else (int(game_range[0]), int(game_range[1]))
+    if not (0 <= g0 <= g1 <= max(games, 0)):
+        raise ValueError("game_range must lie inside [0, 2n]")
     box = None
     use = (_usage.resolve_team(teamA, eng.models), _usage.resolve_team(teamB, eng.models))
-    if games <= 0:
+    if g1 - g0 <= 0:
         sims_df = pd.DataFrame(columns=["team", "opp", "pts", "opp_pts"])
     else:
-        # the sampled names feed the models whether or not the box is collected (FMC:1058-1081, 1203-1216)
-        eng.set_matchups([MatchupSpec(teamA.name, teamB.name, teamA.sp, teamB.sp, games, 0, games, 0, usage=use)])
-        want_box = bool(collect_players) and eng.n_slots > 0
-        res = eng.simulate_host(_fresh_seed() if seed is None else int(seed), want_scores=True, want_hist=True,
-                                want_players=want_box)
+        with _ENGINE_LOCK:
+            # the sampled names feed the models whether or not the box is collected (FMC:1058-1081, 1203-1216)
+            eng.set_matchups([MatchupSpec(teamA.name, teamB.name, teamA.sp, teamB.sp, games, g0, g1, 0, usage=use)])
+            want_box = bool(collect_players) and eng.n_slots > 0
+            res = eng.simulate_host(_fresh_seed() if seed is None else int(seed), want_scores=True, want_hist=True,
+                                    want_players=want_box)
         box = res.get("players")
-        sims_df = outputs.sims_frame(teamA.name, teamB.name, res["scores"])
+        sims_df = outputs.sims_frame(teamA.name, teamB.name, res["scores"], first_game=g0)
         sims_df.attrs["counters"] = dict(res["counters"])
+        sims_df.attrs["hist"] = res["hist"][0]
         LAST_RUN.clear()
         LAST_RUN.update(hist=res["hist"][0], counters=dict(res["counters"]), teams=(teamA.name, teamB.name),
-                        scores=res["scores"], player_box=box, usage=use)
+                        scores=res["scores"], player_box=box, usage=use, game_range=(g0, g1))
     players_df = None
     if collect_players:
         players_df = (_usage.player_rows(box, 0, (teamA.name, teamB.name), use) if box is not None
@@ -114,14 +127,23 @@ def simulate_upcoming_matchup(teamA: str, teamB: str, *, year: int = 2025, week:
     sims_df, players_df = simulate_matchup(A, B, n=n, seed=seed, show_progress=show_progress,
                                            collect_players=collect_players, processes=processes, engine=engine)
     t1 = time.perf_counter()
-    summary = outputs.summary_frame(sims_df)
+    # FMC:1681-1687.  The group-by over the 2n rows and the joint score histogram the kernel accumulated hold the same
+    # information; the histogram gives the five statistics in microseconds (tests check the two agree)
+    c = sims_df.attrs.get("counters")
+    h = sims_df.attrs.get("hist")
+    if h is not None and c and c.get("hist_overflow", 1) == 0 and min(int(h[0].sum()), int(h[1].sum())) > 1:
+        summary = outputs.summary_from_hist(h, A.name, B.name)
+    else:
+        summary = outputs.summary_frame(sims_df)
 
     write_time = 0.0
     if save_csv:
         tw = time.perf_counter()
         try:
             if save_csv.lower().endswith(".parquet"):
-                raw = LAST_RUN.get("scores") if LAST_RUN.get("teams") == (A.name, B.name) else None
+                raw = sims_df.attrs.get("scores_raw")
+                if raw is None:
+                    raw = LAST_RUN.get("scores") if LAST_RUN.get("teams") == (A.name, B.name) else None
                 if raw is not None and len(raw) == len(sims_df):   # chunked, dictionary-encoded writer straight from the score array
                     outputs.write_scores_table(f"scores_{save_csv}", A.name, B.name, raw)
                 else:

@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <thread>
@@ -40,6 +41,7 @@ struct PredictArgs {
     int n_scaled;
     int scaler_cols[16];
     double scaler_mean[16], scaler_scale[16];
+    unsigned long long *stats;   // [2]: warp-level node gathers, lane-level node gathers of live rows (roofline accounting)
 };
 
 constexpr int kPredThreads = 256;
@@ -52,6 +54,7 @@ __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs
     const float inf = __int_as_float(0x7f800000);
     for (int i = tid; i < (kPredThreads / 32) * 32; i += kPredThreads)
         rows[(i >> 5) * kPredChunkFloats + kPredNinfRow * 32 + (i & 31)] = -inf;
+    unsigned long long steps = 0ULL, visits = 0ULL;
     for (long long base = (long long)blockIdx.x * kPredThreads; base < a.n; base += (long long)gridDim.x * kPredThreads) {
         for (int i = tid; i < kPredThreads * kNumMax; i += kPredThreads) {
             const int r = i / kNumMax, k = i - r * kNumMax;
@@ -87,8 +90,15 @@ __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs
             const double v = a.multi_window ? walk_output<SKL, true>(F, fcol, lane, a.base[o], levels)
                                             : walk_output<SKL, false>(F, fcol, lane, a.base[o], levels);
             if (live) a.out[(base + tid) * a.n_outputs + o] = v;
+            steps += (unsigned long long)levels * kIlp;
+            visits += live ? (unsigned long long)levels * kIlp : 0ULL;
         }
         __syncthreads();
+    }
+    if (a.stats) {
+        if (lane == 0) atomicAdd(a.stats, steps);
+        for (int s = 16; s >= 1; s >>= 1) visits += __shfl_xor_sync(0xFFFFFFFFu, visits, s);
+        if (lane == 0) atomicAdd(a.stats + 1, visits);
     }
 }
 
@@ -192,6 +202,7 @@ struct fmc_ctx {
     fmc_player_rec *d_box_scratch = nullptr;   // running box of every resident lane [grid x threads][2][n_slots]
     size_t box_scratch_bytes = 0;
     bool tables_dirty = true;
+    bool usage_pending = false;          // fmc_set_matchups kept the tables of an identical list; usage must be confirmed
     // device-side state of the last set_matchups
     TableArena sim_tables;
     MatchupDev *d_matchups = nullptr;
@@ -202,12 +213,13 @@ struct fmc_ctx {
     RankSpec *d_specs = nullptr;
     std::vector<uint8_t> memo_ok;        // [n_matchups][kMemoFams][2] the forest's ranks fit the key
     std::vector<std::string> memo_why;   // why not, for diagnostics
-    int memo_mode = 1, memo_max_trips = 8, memo_break_parked = 16;
+    int memo_mode = 1, memo_max_trips = 8, memo_break_parked = 16, memo_break_waiting = kMemoThreads / 64;
     uint64_t memo_max_bytes = 0;
     char *d_memo = nullptr;
     size_t memo_bytes = 0;
     MemoRegion memo_region[kMemoFams];
     bool memo_valid = false;             // mode 2: the table belongs to the current node tables
+    unsigned long long *d_pred_stats = nullptr;   // [2] node gathers of the fmc_tree_predict launches since the last reset
     cudaEvent_t ev_done = nullptr;       // completion of the last fmc_simulate launch
     bool launched = false;
     // fmc_simulate_host: device scratch + pinned staging, kept between calls
@@ -274,6 +286,8 @@ extern "C" int fmc_create(int device, fmc_ctx **out) {
     CKC(cudaFuncSetAttribute(sim_memo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_memo_smem_bytes()));
     CKC(cudaFuncSetAttribute(sim_memo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sim_memo_smem_bytes()));
     CKC(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    CKC(cudaMalloc(&c->d_pred_stats, 16));
+    CKC(cudaMemset(c->d_pred_stats, 0, 16));
     std::memset(c->memo_region, 0, sizeof(c->memo_region));
     *out = c;
     return FMC_OK;
@@ -286,7 +300,7 @@ extern "C" void fmc_destroy(fmc_ctx *c) {
     for (auto &e : c->pred) e.arena.release();
     cudaDeviceSynchronize();
     cudaFree(c->d_matchups); cudaFree(c->d_next); cudaFree(c->d_box_scratch);
-    cudaFree(c->d_specs); cudaFree(c->d_memo);
+    cudaFree(c->d_specs); cudaFree(c->d_memo); cudaFree(c->d_pred_stats);
     for (auto &q : c->scr) cudaFree(q.dev);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     delete c;
@@ -366,6 +380,7 @@ extern "C" int fmc_set_memo(fmc_ctx *c, int32_t mode, uint64_t max_bytes, int32_
     c->memo_max_bytes = max_bytes;
     c->memo_max_trips = max_trips > 0 ? max_trips : 8;
     c->memo_break_parked = break_parked > 0 ? break_parked : 16;
+    if (const char *e = std::getenv("FMC_MEMO_BREAK_WAITING")) { const int v = std::atoi(e); if (v > 0) c->memo_break_waiting = v; }
     c->memo_valid = false;
     return FMC_OK;
 }
@@ -374,18 +389,46 @@ extern "C" int fmc_set_matchups(fmc_ctx *c, int32_t n, const fmc_matchup *m) {
     if (!c || n <= 0 || !m) return fail(FMC_ERR_INVALID, "fmc_set_matchups: bad argument");
     for (int i = 0; i < n; ++i)
         if (m[i].game_end < m[i].game_begin) return fail(FMC_ERR_INVALID, "fmc_set_matchups: game_end < game_begin");
+    // The same pairs again (only the game ranges may differ): the specialised tables, the rank specs and, in mode 2, the
+    // memo stay valid -- a caller that simulates one matchup repeatedly (FMC:1739-1760 loops over seeds / weeks) pays the
+    // specialisation once.  Only the three range words of every device record are refreshed.
+    bool same = !c->tables_dirty && (int)c->matchups.size() == n && c->d_matchups != nullptr;
+    for (int i = 0; same && i < n; ++i)
+        same = std::memcmp(c->matchups[i].sp, m[i].sp, sizeof(m[i].sp)) == 0 &&
+               c->matchups[i].coach_col[0] == m[i].coach_col[0] && c->matchups[i].coach_col[1] == m[i].coach_col[1];
+    if (same) {
+        CK(cudaSetDevice(c->device));
+        CK(cudaDeviceSynchronize());           // a launch in flight reads the ranges
+        for (int i = 0; i < n; ++i) {
+            const unsigned long long r[3] = {m[i].game_begin, m[i].game_end, m[i].out_offset};
+            CK(cudaMemcpy(reinterpret_cast<char *>(c->d_matchups + i) + offsetof(MatchupDev, game_begin), r, sizeof(r), cudaMemcpyHostToDevice));
+        }
+        c->matchups.assign(m, m + n);
+        c->usage_pending = !c->usage.empty();   // the caller must repeat fmc_set_usage (or clear it): checked there
+        return FMC_OK;
+    }
     c->matchups.assign(m, m + n);
     c->usage.clear();          // usage belongs to a matchup list: set it again after fmc_set_matchups
     c->name_rows.clear();
     c->n_slots = 0;
+    c->usage_pending = false;
     c->tables_dirty = true;
     return FMC_OK;
 }
 
 extern "C" int fmc_set_usage(fmc_ctx *c, int32_t n, const fmc_team_usage *teams, int32_t n_slots) {
     if (!c) return fail(FMC_ERR_INVALID, "fmc_set_usage: ctx is NULL");
-    if (!teams) { c->usage.clear(); c->name_rows.clear(); c->n_slots = 0; c->tables_dirty = true; return FMC_OK; }
+    if (!teams) {
+        if (!c->usage.empty()) c->tables_dirty = true;
+        c->usage.clear(); c->name_rows.clear(); c->n_slots = 0; c->usage_pending = false;
+        return FMC_OK;
+    }
     if (n != (int)c->matchups.size()) return fail(FMC_ERR_INVALID, "fmc_set_usage: n_matchups differs from the last fmc_set_matchups");
+    if (!c->tables_dirty && c->usage.size() == 2 * (size_t)n && c->n_slots == n_slots &&
+        std::memcmp(c->usage.data(), teams, sizeof(fmc_team_usage) * 2 * (size_t)n) == 0) {
+        c->usage_pending = false;              // the same tables again: nothing to rebuild
+        return FMC_OK;
+    }
     if (n_slots < 0 || n_slots > 3 * FMC_MAX_USAGE) return fail(FMC_ERR_INVALID, "fmc_set_usage: bad n_slots");
     std::vector<fmc_ctx::NameRows> rows(2 * (size_t)n);
     for (int i = 0; i < 2 * n; ++i)
@@ -421,6 +464,7 @@ extern "C" int fmc_set_usage(fmc_ctx *c, int32_t n, const fmc_team_usage *teams,
         }
     c->name_rows.swap(rows);
     c->n_slots = n_slots;
+    c->usage_pending = false;
     c->tables_dirty = true;
     return FMC_OK;
 }
@@ -606,8 +650,18 @@ static void prescale(HostForest &f) {
     }
 }
 
+// fmc_set_matchups documents that usage must be set again afterwards: a caller that did not, after the fast path kept
+// the old tables, gets what the documented behaviour gives -- no usage.
+static void settle_usage(fmc_ctx *c) {
+    if (!c->usage_pending) return;
+    c->usage.clear(); c->name_rows.clear(); c->n_slots = 0;
+    c->usage_pending = false;
+    c->tables_dirty = true;
+}
+
 extern "C" int fmc_packed_slots(fmc_ctx *c, int32_t m, int32_t *out) {
     if (!c || !out) return fail(FMC_ERR_INVALID, "fmc_packed_slots: bad argument");
+    settle_usage(c);
     if (c->tables_dirty) {
         for (int i = 0; i < FMC_N_MODELS; ++i) prescale(c->forest[i]);
         int rc = build_tables(c);
@@ -674,6 +728,7 @@ static size_t memo_layout(fmc_ctx *c, uint64_t games, MemoRegion (&R)[kMemoFams]
 extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
     if (!c || !g) return fail(FMC_ERR_INVALID, "fmc_simulate: bad argument");
     CK(cudaSetDevice(c->device));
+    settle_usage(c);
     if (c->tables_dirty) {
         for (int i = 0; i < FMC_N_MODELS; ++i) prescale(c->forest[i]);
         int rc = build_tables(c);
@@ -747,9 +802,11 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
         mm.enabled = bytes ? 1 : 0;
         mm.max_trips = c->memo_max_trips;
         mm.break_parked = c->memo_break_parked;
+        mm.break_waiting = c->memo_break_waiting;
         c->memo_valid = bytes != 0;
-        if (test) sim_memo_kernel<true><<<grid, kSimThreads, sim_memo_smem_bytes(), st>>>(a, mm);
-        else sim_memo_kernel<false><<<grid, kSimThreads, sim_memo_smem_bytes(), st>>>(a, mm);
+        const int mgrid = c->prop.multiProcessorCount * kMemoCtasPerSm;
+        if (test) sim_memo_kernel<true><<<mgrid, kMemoThreads, sim_memo_smem_bytes(), st>>>(a, mm);
+        else sim_memo_kernel<false><<<mgrid, kMemoThreads, sim_memo_smem_bytes(), st>>>(a, mm);
     } else {
         if (test) sim_kernel<true, false><<<grid, kSimThreads, sim_smem_bytes(false), st>>>(a);
         else sim_kernel<false, false><<<grid, kSimThreads, sim_smem_bytes(false), st>>>(a);
@@ -780,6 +837,7 @@ static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, 
     if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
     if (c->matchups.empty()) return fail(FMC_ERR_INVALID, "fmc_set_matchups has not been called");
     CK(cudaSetDevice(c->device));
+    settle_usage(c);
     size_t games = 0;
     for (auto &m : c->matchups) {
         const size_t hi = (size_t)(m.out_offset + (m.game_end - m.game_begin));
@@ -912,6 +970,7 @@ extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, 
     for (int k = 0; k < 8; ++k) a.base[k] = f.base[k];
     a.n_scaled = f.n_scaled;
     for (int j = 0; j < f.n_scaled; ++j) { a.scaler_cols[j] = f.scaler_cols[j]; a.scaler_mean[j] = f.scaler_mean[j]; a.scaler_scale[j] = f.scaler_scale[j]; }
+    a.stats = c->d_pred_stats;
 #ifdef FMC_DEBUG_CHECKS
     debug_set_range(A);
 #endif
@@ -959,6 +1018,24 @@ extern "C" int64_t fmc_debug_errors(void) {
     return 0;
 #endif
 }
+// Node gathers of the fmc_tree_predict launches since the last reset: out[0] warp-level (one per warp and tree level,
+// what the L1 data pipe sees), out[1] lane-level of live rows.  Synchronises the device.
+extern "C" int fmc_predict_stats(fmc_ctx *c, uint64_t *out2, int32_t reset) {
+    if (!c || !out2) return fail(FMC_ERR_INVALID, "fmc_predict_stats: bad argument");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out2, c->d_pred_stats, 16, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(c->d_pred_stats, 0, 16));
+    return FMC_OK;
+}
+
+// Measurement helper: forget the specialised tables, so that the next fmc_simulate specialises, packs and uploads again.
+extern "C" int fmc_invalidate_tables(fmc_ctx *c) {
+    if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
+    c->tables_dirty = true;
+    return FMC_OK;
+}
+
 extern "C" int fmc_sync(fmc_ctx *c) {
     if (!c) return fail(FMC_ERR_INVALID, "ctx is NULL");
     CK(cudaSetDevice(c->device));
@@ -1034,6 +1111,85 @@ extern "C" int fmc_gather_probe(fmc_ctx *c, int64_t table_bytes, int32_t iters, 
     if (e != cudaSuccess) return fail(FMC_ERR_CUDA, std::string("gather_probe_kernel: ") + cudaGetErrorString(e));
     const double loads = (double)grid * 1024.0 * kProbeChains * (double)iters;
     *gbytes_per_s = loads * 8.0 / ((double)best * 1e-3) / 1e9;
+    return FMC_OK;
+}
+
+// Warp-coherent variant: the production walk is not a random gather -- at every level the 32 lanes of a warp sit inside
+// ONE tree, i.e. inside a window of a few hundred bytes.  Here every warp follows kProbeChains chains of WINDOWS of
+// `window_bytes` (a random cyclic permutation over the windows of the table, the same next window for all lanes) and
+// each lane reads a data-dependent slot inside the current window: the access pattern of a tree level with nothing
+// around it (no feature load, no compare).  This is the denominator a walk can be held against (< 1 by construction).
+__global__ void __launch_bounds__(1024, 1) gather_probe_coherent_kernel(const uint2 *__restrict__ tbl, uint32_t n_windows,
+                                                                       uint32_t slots_per_window, int iters, unsigned int *sink) {
+    uint32_t win[kProbeChains], off[kProbeChains];
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < kProbeChains; ++c) {
+        win[c] = (warp * 2654435761u + (uint32_t)c * 40503u) % n_windows;
+        off[c] = (lane * 7u + (uint32_t)c) & (slots_per_window - 1u);
+    }
+    uint32_t acc = 0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int c = 0; c < kProbeChains; ++c) {
+            const uint2 v = __ldg(tbl + (size_t)win[c] * slots_per_window + off[c]);
+            win[c] = v.x;
+            off[c] = (v.y + lane * 5u) & (slots_per_window - 1u);
+            acc ^= v.y;
+        }
+    }
+    if (acc == 0x12345678u) atomicAdd(sink, 1u);
+}
+
+extern "C" int fmc_gather_probe_coherent(fmc_ctx *c, int64_t table_bytes, int32_t window_bytes, int32_t iters, double *out3) {
+    if (!c || !out3 || table_bytes < 1024 || iters <= 0 || window_bytes < 8 || (window_bytes & (window_bytes - 1)) ||
+        window_bytes > table_bytes)
+        return fail(FMC_ERR_INVALID, "fmc_gather_probe_coherent: bad argument (window_bytes must be a power of two)");
+    CK(cudaSetDevice(c->device));
+    const uint32_t spw = (uint32_t)(window_bytes / 8), nw = (uint32_t)(table_bytes / window_bytes);
+    std::vector<uint32_t> perm(nw);
+    for (uint32_t i = 0; i < nw; ++i) perm[i] = i;
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    for (uint32_t i = nw - 1; i > 0; --i) {        // Sattolo: one cycle through every window
+        s = s * 6364136223846793005ull + 1442695040888963407ull;
+        const uint32_t j = (uint32_t)((s >> 33) % i);
+        std::swap(perm[i], perm[j]);
+    }
+    std::vector<uint2> h((size_t)nw * spw);
+    for (uint32_t w = 0; w < nw; ++w)
+        for (uint32_t k = 0; k < spw; ++k) {
+            s = s * 6364136223846793005ull + 1442695040888963407ull;
+            h[(size_t)w * spw + k] = make_uint2(perm[w], (uint32_t)(s >> 35));
+        }
+    uint2 *d = nullptr;
+    unsigned int *sink = nullptr;
+    CK(cudaMalloc(&d, h.size() * 8));
+    cudaError_t e = cudaMalloc(&sink, 4);
+    if (e != cudaSuccess) { cudaFree(d); return fail(FMC_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaMemcpy(d, h.data(), h.size() * 8, cudaMemcpyHostToDevice);
+    cudaMemset(sink, 0, 4);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int grid = c->prop.multiProcessorCount;
+    gather_probe_coherent_kernel<<<grid, 1024>>>(d, nw, spw, iters / 4 + 1, sink);      // warm-up
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        cudaEventRecord(e0);
+        gather_probe_coherent_kernel<<<grid, 1024>>>(d, nw, spw, iters, sink);
+        cudaEventRecord(e1);
+        e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d); cudaFree(sink);
+    if (e != cudaSuccess) return fail(FMC_ERR_CUDA, std::string("gather_probe_coherent_kernel: ") + cudaGetErrorString(e));
+    const double warp_gathers = (double)grid * 32.0 * kProbeChains * (double)iters;
+    out3[0] = warp_gathers * 32.0 * 8.0 / ((double)best * 1e-3) / 1e9;    // GB/s of gathered slots (8 bytes x lanes)
+    out3[1] = warp_gathers / ((double)best * 1e-3);                       // warp-level gather instructions per second
+    out3[2] = (double)best;                                               // ms
     return FMC_OK;
 }
 

@@ -65,6 +65,7 @@ struct MemoArgs {
     int enabled;
     int max_trips;                      // plays a lane may chain per round while it keeps hitting
     int break_parked;                   // a warp leaves the trip loop once this many of its lanes wait for the walk (or are idle)
+    int break_waiting;                  // ... or once this many warps of the CTA have left it
 };
 
 __host__ __device__ inline int memo_units(int fam) { return fam == 0 ? 1 : (fam == 1 ? 2 : 3); }

@@ -84,6 +84,20 @@ struct EvTally {
     __device__ __forceinline__ void hit(int ev) { w[ev / 5] += 1u << (6 * (ev % 5)); }
 };
 
+// CTA shape of the memo kernel (independent of sim_kernel's): with most requests answered by the memo the walk no
+// longer dominates, and the CTA-wide barriers around it cost less when fewer warps share them.
+#ifndef FMC_MEMO_THREADS
+#define FMC_MEMO_THREADS 1024
+#endif
+#ifndef FMC_MEMO_CTAS_PER_SM
+#define FMC_MEMO_CTAS_PER_SM 1
+#endif
+constexpr int kMemoThreads = FMC_MEMO_THREADS;
+constexpr int kMemoCtasPerSm = FMC_MEMO_CTAS_PER_SM;
+constexpr int kMemoChunks = kMemoThreads / 32 + kNumKeys;        // every key's list starts on a chunk boundary
+constexpr size_t kMemoFeatBytes = (size_t)kMemoChunks * chunk_floats(false) * 4;
+constexpr size_t kMemoResultBytes = (size_t)kMemoChunks * 32 * 3 * 8;
+
 struct MemoShared {
     MatchupDev M;
     int cur_matchup;
@@ -93,31 +107,32 @@ struct MemoShared {
     unsigned int item_next;
     unsigned int alive[2];
     unsigned long long stat[FMC_N_COUNTERS];
-    unsigned long long wstat[kSimThreads / 32][16];      // per-warp event totals (EV_*, then plays, iters), no atomics
+    unsigned int waiting[2];             // warps that have left the trip loop this round (by round parity)
+    unsigned long long wstat[kMemoThreads / 32][16];      // per-warp event totals (EV_*, then plays, iters), no atomics
 };
 constexpr size_t kMemoSharedBytes = ((sizeof(MemoShared) + 15) / 16) * 16;
-constexpr size_t kMemoKeyBytes = (size_t)kSimThreads * 8;
-inline size_t sim_memo_smem_bytes() { return kMemoSharedBytes + sim_feat_bytes(false) + kSimResultBytes + kMemoKeyBytes; }
+constexpr size_t kMemoKeyBytes = (size_t)kMemoThreads * 8;
+inline size_t sim_memo_smem_bytes() { return kMemoSharedBytes + kMemoFeatBytes + kMemoResultBytes + kMemoKeyBytes; }
 
 template <bool TEST>
-__global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKernelArgs a, const MemoArgs mm) {
+__global__ void __launch_bounds__(kMemoThreads, kMemoCtasPerSm) sim_memo_kernel(const SimKernelArgs a, const MemoArgs mm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kChunkFloats = chunk_floats(false);
-    constexpr size_t kFeatBytes_ = sim_feat_bytes(false);
+    constexpr size_t kFeatBytes_ = kMemoFeatBytes;
     MemoShared &sh = *reinterpret_cast<MemoShared *>(smem_raw);
     float *feats = reinterpret_cast<float *>(smem_raw + kMemoSharedBytes);
     double *results = reinterpret_cast<double *>(smem_raw + kMemoSharedBytes + kFeatBytes_);
-    unsigned long long *mkey = reinterpret_cast<unsigned long long *>(smem_raw + kMemoSharedBytes + kFeatBytes_ + kSimResultBytes);
+    unsigned long long *mkey = reinterpret_cast<unsigned long long *>(smem_raw + kMemoSharedBytes + kFeatBytes_ + kMemoResultBytes);
     const unsigned int FULL = 0xFFFFFFFFu;
 
     const uint32_t feats_saddr = (uint32_t)__cvta_generic_to_shared(feats);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < kSimChunks * 32; i += kSimThreads)
+    for (int i = tid; i < kMemoChunks * 32; i += kMemoThreads)
         feats[(size_t)(i >> 5) * kChunkFloats + kSimNinfRow * 32 + (i & 31)] = __int_as_float(0xff800000);
     if (tid < FMC_N_COUNTERS) sh.stat[tid] = 0ULL;
-    for (int i = tid; i < (kSimThreads / 32) * 16; i += kSimThreads) (&sh.wstat[0][0])[i] = 0ULL;
+    for (int i = tid; i < (kMemoThreads / 32) * 16; i += kMemoThreads) (&sh.wstat[0][0])[i] = 0ULL;
     if (tid < kNumKeys) { sh.cnt[0][tid] = 0; sh.cnt[1][tid] = 0; sh.aged[tid] = 0; }
-    if (tid == 0) { sh.cur_matchup = -1; sh.alive[0] = 0; sh.alive[1] = 0; }
+    if (tid == 0) { sh.cur_matchup = -1; sh.alive[0] = 0; sh.alive[1] = 0; sh.waiting[0] = 0; sh.waiting[1] = 0; }
     __syncthreads();
 
     PackedLane P;
@@ -147,10 +162,10 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
         {
             const uint32_t *src = reinterpret_cast<const uint32_t *>(a.matchups + m);
             uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.M);
-            for (int i = tid; i < (int)(sizeof(MatchupDev) / 4); i += kSimThreads) dst[i] = src[i];
+            for (int i = tid; i < (int)(sizeof(MatchupDev) / 4); i += kMemoThreads) dst[i] = src[i];
         }
         if (tid < kNumKeys) { sh.cnt[0][tid] = 0; sh.cnt[1][tid] = 0; sh.aged[tid] = 0; }
-        if (tid == 0) { sh.alive[0] = 0; sh.alive[1] = 0; }
+        if (tid == 0) { sh.alive[0] = 0; sh.alive[1] = 0; sh.waiting[0] = 0; sh.waiting[1] = 0; }
         __syncthreads();
         const MatchupDev &M = sh.M;
         const RankSpec *specs = mm.specs + (size_t)m * kMemoFams * 2;
@@ -229,6 +244,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                 const int team = L.offense;
                 const int sd = L.score[team] - L.score[team ^ 1];
                 const double ytg0 = L.ytg;
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
                 // -- iteration start: fourth down (handle_fourth FMC:1382-1421) and the play call
                 if (!parked && L.stage == ST_ITER) {
                     if (TEST && a.trace && L.iter < FMC_MAX_ITERS) {
@@ -283,6 +299,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                         }
                     }
                 }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
                 // -- play model (policy 1): probe, then FMC:420-425
                 if (a.policy == 1) {
                     if (!parked && !have && L.stage == ST_WAIT_PM) {
@@ -313,6 +330,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                         have = false;
                     }
                 }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
                 // -- stage 1: probe, then FMC:1086-1087
                 if (!parked && !have && L.stage == ST_WAIT_S1) {
                     const RankSpec *rs = specs + 0 * 2 + team;
@@ -325,6 +343,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                     }
                     if (hit) have = true; else { parked = true; mkey[tid] = key; }
                 }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
                 bool s2_standin = false;
                 if (have && L.stage == ST_WAIT_S1) {
                     const float m1 = __uint_as_float((uint32_t)r[0]);
@@ -335,6 +354,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                     else if (a.stage2_mode == 1) L.stage = ST_WAIT_S2;
                     else s2_standin = true;
                 }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
                 // -- stage 2: probe, then the not-complete outcome FMC:751-770, 1157-1199
                 if (!parked && !have && L.stage == ST_WAIT_S2) {
                     const RankSpec *rs = specs + 1 * 2 + team;
@@ -347,6 +367,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                     }
                     if (hit) have = true; else { parked = true; mkey[tid] = key; }
                 }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
                 if ((have && L.stage == ST_WAIT_S2) || s2_standin) {
                     double raw[3];
                     if (!s2_standin) {
@@ -383,6 +404,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                         L.stage = ST_ITER;
                     }
                 }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
                 // -- yardage families: probe, then the outcome
                 if (!parked && !have && L.stage >= ST_WAIT_PQ && L.stage <= ST_WAIT_SQ) {
                     const int fam = stage_family(L.stage);
@@ -396,6 +418,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                     }
                     if (hit) have = true; else { parked = true; mkey[tid] = key; }
                 }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
                 if (have && L.stage >= ST_WAIT_PQ && L.stage <= ST_WAIT_SQ) {
                     const double q[3] = {__longlong_as_double((long long)r[0]), __longlong_as_double((long long)r[1]),
                                          __longlong_as_double((long long)r[2])};
@@ -433,6 +456,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                     }
                     L.stage = ST_ITER;
                 }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
                 // -- warp tallies of this trip
                 {
                     const uint32_t t0 = __reduce_add_sync(FULL, ev.w[0]), t1 = __reduce_add_sync(FULL, ev.w[1]), t2 = __reduce_add_sync(FULL, ev.w[2]);
@@ -447,7 +471,10 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                 // -- stop when the warp has little left to do this round
                 const unsigned int busy = __ballot_sync(FULL, !parked && L.stage != ST_IDLE);
                 if (__popc(busy) <= 32 - mm.break_parked) break;
+                // ... or when enough of the other warps already wait at the barrier for this one
+                if (*((volatile unsigned int *)&sh.waiting[parity]) >= (unsigned int)mm.break_waiting) break;
             }
+            if (lane == 0) atomicAdd(&sh.waiting[parity], 1u);
             // ---- B: compact the requests that missed
             const int key = parked ? stage_family(L.stage) * 2 + L.offense : -1;
             unsigned int rank = 0;
@@ -467,7 +494,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
             if (total == 0) {
                 // nobody missed: nothing to walk; clear the other parity's round state and go on
                 if (tid < kNumKeys) sh.cnt[parity ^ 1][tid] = 0;
-                if (tid == 0) sh.alive[parity ^ 1] = 0u;
+                if (tid == 0) { sh.alive[parity ^ 1] = 0u; sh.waiting[parity ^ 1] = 0u; }
                 __syncthreads();
                 parity ^= 1;
                 rounds += 1;
@@ -490,6 +517,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
                 sh.item_prefix[kNumKeys] = it;
                 sh.item_next = 0;
                 sh.alive[parity ^ 1] = 0u;
+                sh.waiting[parity ^ 1] = 0u;
             }
             if (tid < kNumKeys) sh.cnt[parity ^ 1][tid] = 0;
             __syncthreads();
@@ -543,7 +571,7 @@ __global__ void __launch_bounds__(kSimThreads, 1) sim_memo_kernel(const SimKerne
     __syncthreads();
     if (tid < EV_N + 2) {
         unsigned long long s = 0ULL;
-        for (int w = 0; w < kSimThreads / 32; ++w) s += sh.wstat[w][tid];
+        for (int w = 0; w < kMemoThreads / 32; ++w) s += sh.wstat[w][tid];
         const int ci = tid < EV_N ? kEvCounter[tid] : (tid == EV_N ? FMC_C_PLAYS : FMC_C_ITERS);
         sh.stat[ci] += s;
     }

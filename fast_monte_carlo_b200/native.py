@@ -167,6 +167,9 @@ def load_library():
     L.fmc_pack_forest_host.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                        C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
+    L.fmc_gather_probe_coherent.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
+    L.fmc_invalidate_tables.argtypes = [C.c_void_p]
+    L.fmc_predict_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]
     L.fmc_memo_keys_host.restype = C.c_int64
     L.fmc_memo_keys_host.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -180,7 +183,7 @@ EXPORTED_SYMBOLS = (
     "fmc_simulate_host", "fmc_tree_predict", "fmc_tree_predict_host", "fmc_packed_slots", "fmc_sync",
     "fmc_gather_probe", "fmc_debug_errors",
     "fmc_pack_forest_host", "fmc_pack_forest_host_dyn", "fmc_set_usage", "fmc_simulate_players_host",
-    "fmc_set_memo", "fmc_memo_keys_host",
+    "fmc_set_memo", "fmc_memo_keys_host", "fmc_gather_probe_coherent", "fmc_predict_stats", "fmc_invalidate_tables",
 )
 
 
@@ -481,8 +484,23 @@ class Context:
         _check(self._L.fmc_tree_predict(self._h, int(model_id), rows_ptr, int(n), out_ptr, int(tree_begin),
                                         int(tree_end), int(coach_col), cuda_stream or None))
 
+    def predict_stats(self, reset: bool = True) -> dict:
+        """Node gathers of the tree_predict launches since the last reset (fmc_predict_stats)."""
+        out = (C.c_uint64 * 2)()
+        _check(self._L.fmc_predict_stats(self._h, out, 1 if reset else 0))
+        return dict(warp_steps=int(out[0]), visits=int(out[1]))
+
+    def invalidate_tables(self) -> None:
+        _check(self._L.fmc_invalidate_tables(self._h))
+
     def sync(self) -> None:
         _check(self._L.fmc_sync(self._h))
+
+    def gather_probe_coherent(self, table_bytes: int, window_bytes: int = 256, iters: int = 2000) -> dict:
+        """Warp-coherent gather rate (lanes of a warp inside one window, like a tree level): the walk's denominator."""
+        out = (C.c_double * 3)()
+        _check(self._L.fmc_gather_probe_coherent(self._h, int(table_bytes), int(window_bytes), int(iters), out))
+        return dict(gbs=float(out[0]), warp_gathers_per_s=float(out[1]), ms=float(out[2]))
 
     def gather_probe(self, table_bytes: int, iters: int = 2000) -> float:
         """GB/s of dependent 8-byte gathers through a cache-resident table (roofline denominator)."""

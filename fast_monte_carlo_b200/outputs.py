@@ -15,19 +15,94 @@ import pandas as pd
 HIST_BINS = 128
 
 
+def _chunks(n: int, workers: int):
+    """Even-aligned row ranges for the worker threads (numpy copies release the GIL)."""
+    step = max(2, ((n + workers - 1) // workers + 1) & ~1)
+    return [(lo, min(n, lo + step)) for lo in range(0, n, step)]
+
+
+def _pool(n: int):
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    try:
+        cpus = len(os.sched_getaffinity(0))
+    except AttributeError:          # pragma: no cover
+        cpus = os.cpu_count() or 1
+    w = max(1, min(16, cpus, n // 500_000))
+    return (ThreadPoolExecutor(max_workers=w) if w > 1 else None), w
+
+
+def _alternating_names(first: str, second: str, n: int, pool=None, workers: int = 1):
+    """Arrow large_string array `first, second, first, ...` of length n, assembled from its buffers (no Python string
+    objects: a 10 M-row column takes tens of milliseconds instead of seconds)."""
+    import pyarrow as pa
+    fb, sb = first.encode("utf-8"), second.encode("utf-8")
+    la, lb = len(fb), len(sb)
+    offsets = np.empty(n + 1, dtype=np.int64)
+    total = (n // 2) * (la + lb) + (n & 1) * la
+    data = np.empty(total, dtype=np.uint8)
+    pair = np.frombuffer(fb + sb, dtype=np.uint8)
+
+    def fill(lo, hi):          # lo is even
+        m = hi - lo
+        base = (lo // 2) * (la + lb)
+        k = np.arange(0, (m + 1) // 2 + 1, dtype=np.int64) * (la + lb) + base
+        offsets[lo:hi + 1:2] = k[: (m + 2) // 2]
+        offsets[lo + 1:hi + 1:2] = k[: (m + 1) // 2] + la
+        nb = int(offsets[hi]) - base
+        full = nb // (la + lb)
+        if full:
+            data[base:base + full * (la + lb)].reshape(full, la + lb)[:] = pair
+        if nb - full * (la + lb):
+            data[base + full * (la + lb):base + nb] = pair[: nb - full * (la + lb)]
+
+    parts = _chunks(n, workers) if n else []
+    if pool is not None and len(parts) > 1:
+        list(pool.map(lambda r: fill(*r), parts))
+    else:
+        for r in parts:
+            fill(*r)
+    if n == 0:
+        offsets[0] = 0
+    return pa.LargeStringArray.from_buffers(n, pa.py_buffer(offsets), pa.py_buffer(data))
+
+
 def sims_frame(team_a: str, team_b: str, scores: np.ndarray, first_game: int = 0) -> pd.DataFrame:
     """Per-game table with the reference's columns and row order (FMC:1501-1509): game g has the
-    opening-kickoff receiver as `team`; even games are A-first, odd games B-first."""
-    n = scores.shape[0]
-    g = np.arange(first_game, first_game + n)
-    a_first = (g & 1) == 0
-    names = np.array([team_a, team_b], dtype=object)
-    return pd.DataFrame({
-        "team": names[np.where(a_first, 0, 1)],
-        "opp": names[np.where(a_first, 1, 0)],
-        "pts": np.where(a_first, scores[:, 0], scores[:, 1]).astype(np.int64),
-        "opp_pts": np.where(a_first, scores[:, 1], scores[:, 0]).astype(np.int64),
-    })
+    opening-kickoff receiver as `team`; even games are A-first, odd games B-first.  The two name columns have
+    the dtype pandas infers for the reference's own lists of names; they are assembled from Arrow buffers and the
+    point columns by strided copies, on a few threads (10 M rows: ~0.1 s instead of 2.5 s through 20 M Python
+    string objects)."""
+    n = int(scores.shape[0])
+    p = int(first_game) & 1
+    names = (team_a, team_b) if p == 0 else (team_b, team_a)
+    pts = np.empty(n, dtype=np.int64)
+    opp = np.empty(n, dtype=np.int64)
+    pool, workers = _pool(n)
+
+    def points(lo, hi):        # rows lo, lo + 2, ... (lo even) have parity p: A first when p == 0
+        pts[lo:hi:2] = scores[lo:hi:2, p]; opp[lo:hi:2] = scores[lo:hi:2, 1 - p]
+        pts[lo + 1:hi:2] = scores[lo + 1:hi:2, 1 - p]; opp[lo + 1:hi:2] = scores[lo + 1:hi:2, p]
+
+    try:
+        parts = _chunks(n, workers) if n else []
+        if pool is not None and len(parts) > 1:
+            list(pool.map(lambda r: points(*r), parts))
+        else:
+            for r in parts:
+                points(*r)
+        dt = pd.Series(["x"]).dtype        # what `pd.DataFrame(rows)` of the reference gives its name columns
+        if dt == object:
+            nm = np.array(names, dtype=object)
+            idx = np.arange(n) & 1
+            team, other = nm[idx], nm[1 - idx]
+        else:
+            team = pd.array(_alternating_names(names[0], names[1], n, pool, workers), dtype=dt)
+            other = pd.array(_alternating_names(names[1], names[0], n, pool, workers), dtype=dt)
+    finally:
+        if pool is not None:
+            pool.shutdown()
+    return pd.DataFrame({"team": team, "opp": other, "pts": pts, "opp_pts": opp}, copy=False)
 
 
 def summary_frame(sims_df: pd.DataFrame) -> pd.DataFrame:

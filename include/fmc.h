@@ -248,6 +248,14 @@ int fmc_tree_predict_host(fmc_ctx *ctx, int32_t model_id, const double *rows_hos
 int fmc_packed_slots(fmc_ctx *ctx, int32_t m, int32_t *out);
 
 int fmc_sync(fmc_ctx *ctx);
+/* Measurement helper: drop the specialised node tables; the next fmc_simulate specialises, packs and uploads again
+ * (bench.py times the whole host path with it). */
+int fmc_invalidate_tables(fmc_ctx *ctx);
+
+/* Roofline accounting of the tree evaluator: node gathers of the fmc_tree_predict launches since the last reset.
+ * out2[0] = warp-level gathers (one per warp, tree and level: what the L1 data pipe sees), out2[1] = lane-level
+ * gathers of live rows (x 8 bytes = gathered bytes).  Synchronises the device. */
+int fmc_predict_stats(fmc_ctx *ctx, uint64_t *out2, int32_t reset);
 
 /* Diagnostics: out-of-range node gathers / feature offsets counted (and skipped) by a library built with
  * -DFMC_DEBUG_CHECKS since the last call; always 0 for the production build. */
@@ -258,6 +266,13 @@ int64_t fmc_debug_errors(void);
  * few MiB), 8 chains per lane, one 1024-lane CTA per SM -- a tree walk with nothing around it.
  * Synchronous; returns GB/s of gathered slots (8 bytes each). */
 int fmc_gather_probe(fmc_ctx *ctx, int64_t table_bytes, int32_t iters, double *gbytes_per_s);
+
+/* The same with WARP-COHERENT lanes, the access pattern of a real tree level: the 32 lanes of a warp gather inside
+ * one window of `window_bytes` (power of two; a depth-3 tree of the quantile models spans 112 bytes, a group of four
+ * under 512) and all move on to the same next window.  out3 = {GB/s of gathered slots (8 bytes x lanes), warp-level
+ * gathers per second, best time in ms}.  The walk's achieved gather rate (FMC_C_VISITS x 8 bytes / kernel time) is
+ * reported as a fraction of this in bench.py (< 1: a walk also loads a feature and compares per level). */
+int fmc_gather_probe_coherent(fmc_ctx *ctx, int64_t table_bytes, int32_t window_bytes, int32_t iters, double *out3);
 
 /* Host-only, needs no context and no GPU: runs the forest specialiser/packer and returns the node
  * table, the root stream and the constants side stream the kernels walk (layout:

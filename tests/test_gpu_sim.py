@@ -81,8 +81,9 @@ def test_injected_stream_bit_exact_16384(engine, oracle, models_s2, spa, spb):
 
 
 def test_philox_scores_equal_oracle(engine, oracle, models_s2):
-    """Same Philox key/counter scheme on both sides: identical games."""
-    n = 50000
+    """Same Philox key/counter scheme on both sides: identical games (gate G6 at 200 k games here; the recorded
+    1 M-game run of scripts/g6_full.py is under profiles/)."""
+    n = 200_000
     engine.set_matchups([MatchupSpec("A", "B", KSU, ISU, n, 0, n, 0)])
     got = engine.simulate_host(20251018, want_iters=True)
     ref = oracle.simulate(oracle.make_config(models_s2, KSU, ISU), n, seed=20251018)
@@ -168,14 +169,23 @@ def test_edge_sizes(engine):
     assert r["counters"]["games"] == 7 and int(r["hist"][0].sum()) == 0 and int(r["hist"][1].sum()) == 7
 
 
-def test_ks_against_independent_oracle_run(engine, oracle, models_s2):
-    """Gate G7: Philox-GPU distributions vs an oracle run on a DIFFERENT seed (two-sample KS,
-    alpha = 0.001) for points per team, margin and total."""
+def test_ks_against_numpy_driven_oracle(engine, oracle, models_s2):
+    """Gate G7: the GPU's Philox + u01 + AS241 draws against the oracle fed NumPy's own generator
+    (`np.random.default_rng`: PCG64 uniforms and standard normals, FMC:64, 827, 839, 851, 881-889) through the
+    injected-stream path -- two-sample KS at alpha = 0.001 on points per team, margin and total, >= 200 k games each.
+    A biased uniform mapping or inverse normal on the GPU would separate the two distributions."""
     from scipy.stats import ks_2samp
-    n = 200_000
+    n, chunk = 212_992, 16_384                       # 13 chunks of [16384][360][16] float64 draws
     engine.set_matchups([MatchupSpec("A", "B", KSU, ISU, n, 0, n, 0)])
     g = engine.simulate_host(1)["scores"]
-    o = oracle.simulate(oracle.make_config(models_s2, KSU, ISU), n, seed=2)["scores"]
+    cfg = oracle.make_config(models_s2, KSU, ISU)
+    parts = []
+    for i in range(n // chunk):
+        stream = oracle.make_stream(chunk, 1000 + i)
+        parts.append(oracle.simulate(cfg, chunk, game0=i * chunk, stream=stream)["scores"])
+        del stream
+    o = np.concatenate(parts)
+    assert len(o) == n >= 200_000
     for name, a, b in (("ptsA", g[:, 0], o[:, 0]), ("ptsB", g[:, 1], o[:, 1]),
                        ("margin", g[:, 0] - g[:, 1], o[:, 0] - o[:, 1]), ("total", g.sum(1), o.sum(1))):
         assert ks_2samp(a, b).pvalue > 0.001, name
