@@ -543,7 +543,7 @@ def run_ours(args):
             t0 = time.perf_counter()
             df, _ = api.simulate_matchup(A, B, n=total_games // 2, seed=SEED, show_progress=False, engine=eng,
                                          game_range=(rank * G, (rank + 1) * G))
-            h = torch.from_numpy(df.attrs["hist"].astype(np.int64))
+            h = torch.from_numpy(df.attrs["hist"].value.astype(np.int64))
             if world > 1:
                 hd = h.to(dev)
                 dist.all_reduce(hd)

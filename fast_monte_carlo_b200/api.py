@@ -64,6 +64,21 @@ def get_engine(device: Optional[int] = None, **kw) -> Engine:
     return _ENGINES[key]
 
 
+class _Attached:
+    """A value riding in DataFrame.attrs: compared by identity, so that pandas' own attrs comparisons (concat, astype)
+    never evaluate an array for truth."""
+    __slots__ = ("value",)
+
+    def __init__(self, value):
+        self.value = value
+
+    def __eq__(self, other):
+        return self is other
+
+    def __hash__(self):
+        return id(self)
+
+
 def _fresh_seed() -> int:
     return int.from_bytes(os.urandom(8), "little")
 
@@ -95,7 +110,7 @@ def simulate_matchup(teamA: TeamContext, teamB: TeamContext, n: int = 100, seed:
         box = res.get("players")
         sims_df = outputs.sims_frame(teamA.name, teamB.name, res["scores"], first_game=g0)
         sims_df.attrs["counters"] = dict(res["counters"])
-        sims_df.attrs["hist"] = res["hist"][0]
+        sims_df.attrs["hist"] = _Attached(res["hist"][0])
         LAST_RUN.clear()
         LAST_RUN.update(hist=res["hist"][0], counters=dict(res["counters"]), teams=(teamA.name, teamB.name),
                         scores=res["scores"], player_box=box, usage=use, game_range=(g0, g1))
@@ -131,6 +146,7 @@ def simulate_upcoming_matchup(teamA: str, teamB: str, *, year: int = 2025, week:
     # information; the histogram gives the five statistics in microseconds (tests check the two agree)
     c = sims_df.attrs.get("counters")
     h = sims_df.attrs.get("hist")
+    h = h.value if isinstance(h, _Attached) else None
     if h is not None and c and c.get("hist_overflow", 1) == 0 and min(int(h[0].sum()), int(h[1].sum())) > 1:
         summary = outputs.summary_from_hist(h, A.name, B.name)
     else:

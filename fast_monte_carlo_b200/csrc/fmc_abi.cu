@@ -1,6 +1,7 @@
 // C ABI of libfmc_b200.so (include/fmc.h): context, forest specialisation/upload, the tree-predict
 // kernel launch and the persistent simulation kernel launch.  No CPU fallback anywhere: every
 // compute entry point launches a kernel or fails.
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -66,14 +67,16 @@ __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs
             const float v = (float)x;
             const bool flag = (k == 3 || k == 12 || k == 13 || k == 14 || k == 16);
             float *col = rows + (r >> 5) * kPredChunkFloats + (r & 31);
-            if (flag || !a.zero_is_missing) {
+            if (SKL) {
                 col[k * 32] = v;
+            } else if (flag && a.zero_is_missing) {
+                col[k * 32] = (x != x) ? 0.f : v;       // a missing flag of a CSR-fed booster is an absent one
             } else {
-                // rows of the B views follow the 17 numerics in the order of the non-flag columns
-                int nb = kNumMax;
-                for (int q = 0; q < k; ++q) nb += !(q == 3 || q == 12 || q == 13 || q == 14 || q == 16);
-                col[k * 32] = v == 0.f ? -inf : v;
-                col[nb * 32] = v == 0.f ? inf : v;
+                // xgboost: NaN is missing, and so is an exact zero for the CSR-fed boosters -> A view -inf (default-left
+                // nodes), B view +inf (default-right nodes); rows of the B views follow the 17 numerics
+                const bool miss = (x != x) || (a.zero_is_missing && v == 0.f);
+                col[k * 32] = miss ? -inf : v;
+                col[(kNumMax + k) * 32] = miss ? inf : v;
             }
         }
         __syncthreads();
@@ -213,7 +216,7 @@ struct fmc_ctx {
     RankSpec *d_specs = nullptr;
     std::vector<uint8_t> memo_ok;        // [n_matchups][kMemoFams][2] the forest's ranks fit the key
     std::vector<std::string> memo_why;   // why not, for diagnostics
-    int memo_mode = 1, memo_max_trips = 8, memo_break_parked = 16, memo_break_waiting = kMemoThreads / 64;
+    int memo_mode = 1, memo_max_trips = 24, memo_break_parked = 16, memo_break_waiting = kMemoThreads / 64;
     uint64_t memo_max_bytes = 0;
     char *d_memo = nullptr;
     size_t memo_bytes = 0;
@@ -378,7 +381,7 @@ extern "C" int fmc_set_memo(fmc_ctx *c, int32_t mode, uint64_t max_bytes, int32_
     if (max_trips < 0 || max_trips > 4096 || break_parked < 0 || break_parked > 32) return fail(FMC_ERR_INVALID, "fmc_set_memo: bad scheduling knob");
     c->memo_mode = mode;
     c->memo_max_bytes = max_bytes;
-    c->memo_max_trips = max_trips > 0 ? max_trips : 8;
+    c->memo_max_trips = max_trips > 0 ? max_trips : 24;
     c->memo_break_parked = break_parked > 0 ? break_parked : 16;
     if (const char *e = std::getenv("FMC_MEMO_BREAK_WAITING")) { const int v = std::atoi(e); if (v > 0) c->memo_break_waiting = v; }
     c->memo_valid = false;
@@ -680,11 +683,13 @@ static size_t memo_layout(fmc_ctx *c, uint64_t games, MemoRegion (&R)[kMemoFams]
     uint64_t slots[kMemoFams];
     // distinct keys per game measured on configs[1] (scripts/memo_study.py): the boosters see tens of distinct rank
     // vectors per game (their second-resolution clock thresholds), the quantile families a few hundred thousand in all
-    slots[0] = clampu(pow2_at_least(games * 24), 1u << 14, 1u << 27);
-    slots[1] = clampu(pow2_at_least(games * 12), 1u << 13, 1u << 26);
-    slots[2] = slots[3] = clampu(pow2_at_least(games / 2 + 1), 1u << 12, 1u << 22);
-    slots[4] = clampu(pow2_at_least(games / 4 + 1), 1u << 12, 1u << 21);
-    slots[5] = clampu(pow2_at_least(games * 16), 1u << 13, 1u << 25);
+    // (stage 1: 4.4 M keys after 60 k games, 6.2 M after 100 k, of the order of 1.5e8 after 10 M; quantile families
+    // 3e5 after 100 k games).  The table is direct mapped, so it is sized a few times the expected key count.
+    slots[0] = clampu(pow2_at_least(games * 96), 1u << 16, 1u << 28);
+    slots[1] = clampu(pow2_at_least(games * 48), 1u << 15, 1u << 27);
+    slots[2] = slots[3] = clampu(pow2_at_least(games * 4), 1u << 16, 1u << 22);
+    slots[4] = clampu(pow2_at_least(games * 2), 1u << 15, 1u << 21);
+    slots[5] = clampu(pow2_at_least(games * 64), 1u << 16, 1u << 26);
     bool used[kMemoFams];
     for (int f = 0; f < kMemoFams; ++f) used[f] = family_needed(c, f);
     uint64_t budget = c->memo_max_bytes;
@@ -987,6 +992,9 @@ extern "C" int fmc_tree_predict_host(fmc_ctx *c, int32_t id, const double *rows_
                                      int32_t tree_begin, int32_t tree_end, int32_t coach_col) {
     if (!c || id < 0 || id >= FMC_N_MODELS || !c->forest[id].loaded) return fail(FMC_ERR_INVALID, "fmc_tree_predict_host: model not loaded");
     if (n <= 0) return FMC_OK;
+    if (c->forest[id].kind == FMC_KIND_SKL)      // Pipeline.predict raises on NaN input ("Input X contains NaN")
+        for (int64_t i = 0; i < n * kNumMax; ++i)
+            if (rows_host[i] != rows_host[i]) return fail(FMC_ERR_INVALID, "fmc_tree_predict_host: Input X contains NaN (scikit-learn model)");
     CK(cudaSetDevice(c->device));
     const int no = c->forest[id].n_outputs;
     double *d_rows = nullptr, *d_out = nullptr;
@@ -1004,6 +1012,124 @@ extern "C" int fmc_tree_predict_host(fmc_ctx *c, int32_t id, const double *rows_
     if (rc) return rc;
     if (e != cudaSuccess) return fail(FMC_ERR_CUDA, std::string("fmc_tree_predict_host: ") + cudaGetErrorString(e));
     return FMC_OK;
+}
+
+// Per-row names (FMC:744, 756, 784-809: every row of a DataFrame carries its own passer / target / rusher): rows are
+// grouped by their pair of hot one-hot columns, every distinct pair gets its own specialised table (packed by all host
+// threads, uploaded once), and one predict launch per group walks its rows.  Outputs come back in row order.
+extern "C" int fmc_tree_predict_cols_host(fmc_ctx *c, int32_t id, const double *rows_host, int64_t n, const int32_t *hot_cols_host,
+                                          double *out_host, int32_t tree_begin, int32_t tree_end) {
+    if (!c || id < 0 || id >= FMC_N_MODELS || !c->forest[id].loaded) return fail(FMC_ERR_INVALID, "fmc_tree_predict_cols_host: model not loaded");
+    if (n < 0 || (n > 0 && (!rows_host || !out_host || !hot_cols_host))) return fail(FMC_ERR_INVALID, "fmc_tree_predict_cols_host: bad buffers");
+    if (n == 0) return FMC_OK;
+    CK(cudaSetDevice(c->device));
+    HostForest &f = c->forest[id];
+    prescale(f);
+    if (f.kind == FMC_KIND_SKL)
+        for (int64_t i = 0; i < n * kNumMax; ++i)
+            if (rows_host[i] != rows_host[i]) return fail(FMC_ERR_INVALID, "fmc_tree_predict_cols_host: Input X contains NaN (scikit-learn model)");
+    for (int64_t i = 0; i < 2 * n; ++i)
+        if (hot_cols_host[i] < -1 || hot_cols_host[i] >= f.n_features || (hot_cols_host[i] >= f.num_base && hot_cols_host[i] < f.num_base + f.n_num))
+            return fail(FMC_ERR_INVALID, "fmc_tree_predict_cols_host: a hot column must be -1 or a one-hot column of the model");
+    // ---- group the rows by their column pair (first-appearance order)
+    struct Group { int32_t c0, c1; std::vector<int64_t> rows; PackedForest pf; std::string err; TablePlacement pl; int table = 0; bool multi = false; };
+    std::vector<Group> groups;
+    {
+        std::vector<std::pair<uint64_t, int>> index;     // sorted (pair -> group)
+        for (int64_t i = 0; i < n; ++i) {
+            const uint64_t k = ((uint64_t)(uint32_t)hot_cols_host[2 * i] << 32) | (uint32_t)hot_cols_host[2 * i + 1];
+            auto it = std::lower_bound(index.begin(), index.end(), std::make_pair(k, -1));
+            int g;
+            if (it != index.end() && it->first == k) g = it->second;
+            else {
+                g = (int)groups.size();
+                groups.emplace_back();
+                groups.back().c0 = hot_cols_host[2 * i]; groups.back().c1 = hot_cols_host[2 * i + 1];
+                index.insert(it, std::make_pair(k, g));
+            }
+            groups[(size_t)g].rows.push_back(i);
+        }
+    }
+    // ---- specialise + pack every pair on all host threads
+    auto run = [&](Group &g) {
+        PackSpec s;
+        preset_predict(s);
+        s.active[0] = g.c0; s.active[1] = g.c1;
+        s.tree_begin = tree_begin; s.tree_end = tree_end;
+        g.err = pack_forest(f, s, g.pf);
+    };
+    {
+        unsigned nt = std::thread::hardware_concurrency();
+        if (nt == 0) nt = 1;
+        if (nt > 32) nt = 32;
+        if (groups.size() < 4) nt = 1;
+        if (nt <= 1) for (Group &g : groups) run(g);
+        else {
+            std::atomic<size_t> next{0};
+            std::vector<std::thread> pool;
+            for (unsigned t = 0; t < nt; ++t)
+                pool.emplace_back([&]() { for (size_t k; (k = next.fetch_add(1)) < groups.size();) run(groups[k]); });
+            for (auto &th : pool) th.join();
+        }
+    }
+    TableArena A;
+    for (Group &g : groups) {
+        if (!g.err.empty()) return fail(FMC_ERR_CAPACITY, "packing model " + std::to_string(id) + ": " + g.err);
+        g.multi = g.pf.table_bytes() > kWindowBytes;
+        g.table = A.place(g.pf, g.pl);
+        std::vector<uint64_t>().swap(g.pf.slots);
+    }
+    const int no = f.n_outputs;
+    double *d_rows = nullptr, *d_out = nullptr;
+    std::vector<double> staged((size_t)n * kNumMax), outs((size_t)n * no);
+    {
+        size_t at = 0;
+        for (const Group &g : groups)
+            for (int64_t r : g.rows) { std::memcpy(&staged[at * kNumMax], rows_host + r * kNumMax, sizeof(double) * kNumMax); ++at; }
+    }
+    int rc = FMC_OK;
+    cudaError_t e = cudaSuccess;
+    do {
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+        if ((e = A.upload(nullptr, true)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_rows, staged.size() * 8)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_out, outs.size() * 8)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_rows, staged.data(), staged.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        size_t at = 0;
+        for (const Group &g : groups) {
+            const long long m = (long long)g.rows.size();
+            PredictArgs a;
+            std::memset(&a, 0, sizeof(a));
+            a.rows = d_rows + at * kNumMax; a.out = d_out + at * no; a.n = m;
+            const uint64_t w = A.window_addr(g.table);
+            a.win_lo = (uint32_t)w; a.win_hi = (uint32_t)(w >> 32);
+            a.stream = A.d_stream; a.consts = A.d_consts;
+            for (int k = 0; k < 8; ++k) { a.stream_off[k] = g.pl.stream_off[k]; a.consts_off[k] = g.pl.consts_off[k]; a.n_groups[k] = g.pl.n_groups[k]; }
+            a.n_outputs = no; a.n_num = f.n_num;
+            a.multi_window = g.multi ? 1 : 0;
+            a.zero_is_missing = (f.kind == FMC_KIND_XGB && f.zero_is_missing) ? 1 : 0;
+            for (int k = 0; k < 8; ++k) a.base[k] = f.base[k];
+            a.n_scaled = f.n_scaled;
+            for (int j = 0; j < f.n_scaled; ++j) { a.scaler_cols[j] = f.scaler_cols[j]; a.scaler_mean[j] = f.scaler_mean[j]; a.scaler_scale[j] = f.scaler_scale[j]; }
+            a.stats = c->d_pred_stats;
+            long long blocks = (m + kPredThreads - 1) / kPredThreads;
+            const long long cap = (long long)c->prop.multiProcessorCount * 8;
+            if (blocks > cap) blocks = cap;
+            if (f.kind == FMC_KIND_SKL) predict_kernel<true><<<(int)blocks, kPredThreads>>>(a);
+            else predict_kernel<false><<<(int)blocks, kPredThreads>>>(a);
+            at += (size_t)m;
+        }
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) break;
+        if ((e = cudaMemcpy(outs.data(), d_out, outs.size() * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        at = 0;
+        for (const Group &g : groups)
+            for (int64_t r : g.rows) { std::memcpy(out_host + r * no, &outs[at * no], sizeof(double) * no); ++at; }
+    } while (0);
+    cudaFree(d_rows); cudaFree(d_out);
+    A.release();
+    if (e != cudaSuccess) rc = fail(FMC_ERR_CUDA, std::string("fmc_tree_predict_cols_host: ") + cudaGetErrorString(e));
+    return rc;
 }
 
 // Diagnostics: number of out-of-range gathers / feature offsets seen by a library built with

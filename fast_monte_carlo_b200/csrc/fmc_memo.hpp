@@ -63,7 +63,7 @@ struct MemoArgs {
     MemoRegion region[kMemoFams];
     const RankSpec *specs;              // [n_matchups][kMemoFams][2]
     int enabled;
-    int max_trips;                      // plays a lane may chain per round while it keeps hitting
+    int max_trips;                      // stage steps a warp may run per round
     int break_parked;                   // a warp leaves the trip loop once this many of its lanes wait for the walk (or are idle)
     int break_waiting;                  // ... or once this many warps of the CTA have left it
 };

@@ -76,6 +76,8 @@ struct PackSpec {
     int8_t row_b[kNumMax];          // B view row, or -1
     uint8_t is_flag[kNumMax];       // 0/1 valued numeric
     int ninf_row = 0;               // feature row that always holds -inf
+    bool nan_views = false;         // predict preset: every numeric of an xgboost forest has a B view, so that a NaN (= missing
+                                    // for xgboost, whatever the booster was fed) follows the node's default branch
     int tree_begin = 0, tree_end = -1;
     // player mode: one-hot columns whose 0/1 value is a per-request feature row (the sampled passer /
     // target / rusher of the play) instead of a pack-time constant
@@ -158,8 +160,8 @@ struct PackedForest {
 // 13 fourth_and_short 14 fg_range 15 half 16 two_minute
 constexpr int kSimNinfRow = 14;   // 11 varying numerics + B views of distance, yardsToGoal, score_diff, then -inf
 constexpr int kSimRows = 15;
-constexpr int kPredNinfRow = 29;  // 17 numerics + 12 B views, then -inf
-constexpr int kPredRows = 30;
+constexpr int kPredNinfRow = 34;  // 17 numerics + their 17 B views, then -inf
+constexpr int kPredRows = 35;
 
 inline void preset_sim(PackSpec &s) {
     const int8_t row[kNumMax] = {0, 1, 2, 3, 4, 5, -1, -1, -1, -1, -1, -1, 6, 7, 8, 9, 10};
@@ -171,14 +173,14 @@ inline void preset_sim(PackSpec &s) {
 }
 inline void preset_predict(PackSpec &s) {
     const uint8_t fl[kNumMax] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 1};
-    int nb = kNumMax;
     for (int k = 0; k < kNumMax; ++k) {
         s.row[k] = (int8_t)k;
         s.is_flag[k] = fl[k];
-        s.row_b[k] = fl[k] ? -1 : (int8_t)nb++;
+        s.row_b[k] = (int8_t)(kNumMax + k);
     }
     s.fold_mask = 0;
     s.ninf_row = kPredNinfRow;
+    s.nan_views = true;
 }
 
 namespace detail {
@@ -258,7 +260,9 @@ struct Builder {
         int r = build(f.right[i]);
         if (same_leaf(nodes[l], nodes[r])) return l;
         int row = s.row[k];
-        if (zm && !f.dl[i] && s.row_b[k] >= 0) row = s.row_b[k];
+        // default-right nodes read the B view: it holds +inf where the value is missing (an exact zero of a CSR-fed
+        // booster; a NaN of any xgboost forest in the predict preset), the A view holds -inf there
+        if ((zm || (s.nan_views && f.kind == FMC_KIND_XGB)) && !f.dl[i] && s.row_b[k] >= 0) row = s.row_b[k];
         nodes.push_back({false, 0.0, row, f.thr[i], l, r});
         return (int)nodes.size() - 1;
     }

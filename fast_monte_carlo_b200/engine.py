@@ -124,9 +124,23 @@ class Engine:
         return self.ctx.simulate_host(seed=seed, **kw)
 
     def predict(self, name: str, rows: np.ndarray, tree_begin: int = 0, tree_end: int = -1,
-                coach: Optional[str] = None) -> np.ndarray:
-        """Raw margins of one model on [n,17] numerics (hot columns = this engine's `player`)."""
+                coach: Optional[str] = None, names: Optional[Sequence[Sequence[Optional[str]]]] = None,
+                hot_cols: Optional[np.ndarray] = None) -> np.ndarray:
+        """Raw margins of one model on [n,17] numerics.  Without `names` / `hot_cols` every row has this engine's
+        `player` ("Unknown") in its name columns.  `names`: per row the values of the model's categorical inputs in the
+        order of `forest.groups` (passer_name, target_name | rusher_name | coach), exactly what a DataFrame row of the
+        reference carries (FMC:744, 756, 784-809); names that are not categories light nothing.  `hot_cols` gives the
+        one-hot columns directly (int32 [n, 2], -1 = none)."""
         f = self.models[name]
+        if names is not None:
+            groups = f.groups[:2]
+            hot_cols = np.full((len(names), 2), -1, dtype=np.int32)
+            for i, row in enumerate(names):
+                for gi, g in enumerate(groups):
+                    if gi < len(row):
+                        hot_cols[i, gi] = g.column_of(row[gi])
+        if hot_cols is not None:
+            return self.ctx.tree_predict_cols_host(art.MODEL_IDS[name], rows, hot_cols, f.n_outputs, tree_begin, tree_end)
         cc = -1
         if name == "play_model" and coach is not None:
             cc = f.group("coach").column_of(coach)

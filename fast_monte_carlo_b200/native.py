@@ -26,7 +26,8 @@ MAX_ITERS = 360
 TRACE_COLS = 8
 COUNTER_NAMES = ("games", "plays", "iters", "pass", "comp", "inc", "int", "sack", "run", "td", "fga", "fg",
                  "punt", "go", "hist_overflow", "rounds", "requests", "visits", "ph_overflow", "warp_steps",
-                 "memo_probes", "memo_hits", "trips")
+                 "memo_probes", "memo_hits", "trips", "_23", "memo_hits_s1", "memo_hits_s2", "memo_hits_pq", "memo_hits_rq",
+                 "memo_hits_sq", "memo_hits_pm")
 PH_YDS_BINS, PH_YDS_OFFSET, PH_CNT_BINS = 8192, 1000, 128
 PH_BINS = PH_YDS_BINS + 5 * PH_CNT_BINS
 
@@ -169,6 +170,8 @@ def load_library():
                                        C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]
     L.fmc_gather_probe_coherent.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_double)]
     L.fmc_invalidate_tables.argtypes = [C.c_void_p]
+    L.fmc_tree_predict_cols_host.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                             C.c_int32, C.c_int32]
     L.fmc_predict_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.c_int32]
     L.fmc_memo_keys_host.restype = C.c_int64
     L.fmc_memo_keys_host.argtypes = [C.POINTER(ForestDesc), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
@@ -183,7 +186,7 @@ EXPORTED_SYMBOLS = (
     "fmc_simulate_host", "fmc_tree_predict", "fmc_tree_predict_host", "fmc_packed_slots", "fmc_sync",
     "fmc_gather_probe", "fmc_debug_errors",
     "fmc_pack_forest_host", "fmc_pack_forest_host_dyn", "fmc_set_usage", "fmc_simulate_players_host",
-    "fmc_set_memo", "fmc_memo_keys_host", "fmc_gather_probe_coherent", "fmc_predict_stats", "fmc_invalidate_tables",
+    "fmc_set_memo", "fmc_memo_keys_host", "fmc_gather_probe_coherent", "fmc_predict_stats", "fmc_invalidate_tables", "fmc_tree_predict_cols_host",
 )
 
 
@@ -477,6 +480,19 @@ class Context:
         if rows.shape[0]:
             _check(self._L.fmc_tree_predict_host(self._h, int(model_id), full.ctypes.data, rows.shape[0],
                                                  out.ctypes.data, int(tree_begin), int(tree_end), int(coach_col)))
+        return out
+
+    def tree_predict_cols_host(self, model_id: int, rows: np.ndarray, hot_cols: np.ndarray, n_outputs: int, tree_begin=0,
+                               tree_end=-1) -> np.ndarray:
+        """Raw margins of rows that carry their own names: hot_cols int32 [n, 2] = the one-hot columns of each row."""
+        rows = np.asarray(rows, dtype=np.float64)
+        full = np.zeros((rows.shape[0], 17), dtype=np.float64)
+        full[:, :rows.shape[1]] = rows
+        hc = np.ascontiguousarray(hot_cols, dtype=np.int32).reshape(rows.shape[0], 2)
+        out = np.zeros((rows.shape[0], n_outputs), dtype=np.float64)
+        if rows.shape[0]:
+            _check(self._L.fmc_tree_predict_cols_host(self._h, int(model_id), full.ctypes.data, rows.shape[0], hc.ctypes.data,
+                                                      out.ctypes.data, int(tree_begin), int(tree_end)))
         return out
 
     def tree_predict_device(self, model_id: int, rows_ptr: int, n: int, out_ptr: int, tree_begin=0, tree_end=-1,

@@ -151,7 +151,10 @@ enum {
     FMC_C_WARP_STEPS,  /* warp-level node gathers of the tree walk (tree levels walked x trees per group, per warp) */
     FMC_C_MEMO_PROBES, /* requests looked up in the exact memo (fmc_set_memo) */
     FMC_C_MEMO_HITS,   /* ... of which were answered from it (the rest were walked: FMC_C_REQUESTS) */
-    FMC_C_TRIPS        /* warp-level passes of the state machine (memo kernel) */
+    FMC_C_TRIPS,       /* warp-level passes of the state machine (memo kernel) */
+    FMC_C_MEMO_HITS_FAM0 = 24 /* ... 29: memo hits per family (model ids 0..5); probes per family follow from the event
+                                 counters: stage 1 = pass, stage 2 = pass - comp, pass yards = comp, run yards = run,
+                                 sack yards = sack, play model = plays under policy 1 */
 };
 
 #define FMC_N_SLOTS 16           /* injected-draw record per (game, loop iteration); see DESIGN.md */
@@ -213,8 +216,8 @@ int fmc_set_usage(fmc_ctx *ctx, int32_t n_matchups, const fmc_team_usage *teams,
  *   mode 1: on (default), the table is cleared at the start of every fmc_simulate;
  *   mode 2: on, the table is kept between calls for as long as the node tables stay the same.
  * max_bytes: device memory the tables may take (0 = default: up to 1/4 of the free memory, at most 16 GiB; they
- * are sized by the games of the launch).  max_trips / break_parked: scheduling knobs of the memo kernel (plays a
- * lane may chain per round; lanes of a warp that must wait before the warp stops chaining); 0 = default.
+ * are sized by the games of the launch).  max_trips / break_parked: scheduling knobs of the memo kernel (stage steps a
+ * warp may run per round; lanes of a warp that must wait for the walk before the warp ends its round); 0 = default.
  * Player mode (fmc_set_usage) and slates of more than 1024 matchups always run unmemoised. */
 int fmc_set_memo(fmc_ctx *ctx, int32_t mode, uint64_t max_bytes, int32_t max_trips, int32_t break_parked);
 
@@ -242,6 +245,13 @@ int fmc_tree_predict(fmc_ctx *ctx, int32_t model_id, const double *rows_dev, int
                      int32_t tree_begin, int32_t tree_end, int32_t coach_col, void *stream);
 int fmc_tree_predict_host(fmc_ctx *ctx, int32_t model_id, const double *rows_host, int64_t n, double *out_host,
                           int32_t tree_begin, int32_t tree_end, int32_t coach_col);
+
+/* The same for rows that carry their OWN names (a DataFrame with passer_name / target_name / rusher_name per row, FMC:744,
+ * 756, 784-809): hot_cols_host = int32 [n][2], the one-hot column each of the row's (up to) two names lights in this model
+ * (artifacts.OneHotGroup.column_of), -1 = the name is not a category (OneHotEncoder(handle_unknown='ignore') lights
+ * nothing).  Rows are grouped by column pair, every pair gets its own specialised table; outputs are in row order. */
+int fmc_tree_predict_cols_host(fmc_ctx *ctx, int32_t model_id, const double *rows_host, int64_t n, const int32_t *hot_cols_host,
+                               double *out_host, int32_t tree_begin, int32_t tree_end);
 
 /* Packed-table statistics of the last fmc_set_matchups (slots per family/orientation), for
  * DESIGN.md / roofline accounting.  out[FMC_N_MODELS][2] = 8-byte slots of matchup `m`. */

@@ -168,6 +168,7 @@ static inline double walk(const FoForest *f, int t, const FoRow *r) {
         int go_left;
         if (f->kind == FO_KIND_XGB) {
             if (f->zero_is_missing && v == 0.0f) go_left = f->dl[i] != 0;  /* absent from the CSR row */
+            else if (v != v) go_left = f->dl[i] != 0;                      /* NaN: xgboost's missing value */
             else go_left = v < f->thr[i];
         } else {
             go_left = v <= f->thr[i];

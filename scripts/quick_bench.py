@@ -40,5 +40,7 @@ c = cnt.cpu().numpy()
 print(f"rounds/CTA {c[15]/148:.0f} requests {c[16]:.4g} visits/request {c[17]/max(c[16],1):.0f} us/round {best*1e3/(c[15]/148):.1f}")
 print(f"memo {eng.memo}: probes {c[20]:.4g} hits {c[21]:.4g} ({c[21]/max(c[20],1):.4f}) walked {c[16]:.4g} trips/warp {c[22]/(148*32):.0f} "
       f"plays/trip/lane {c[1]/max(c[22]*32,1):.3f}")
+pr = {"s1": c[3], "s2": c[3] - c[4], "pq": c[4], "rq": c[8], "sq": c[7]}
+print("memo hit rate per family: " + "  ".join(f"{k} {c[24 + i] / max(pr[k], 1):.4f}" for i, k in enumerate(pr)) + f"  warp_steps {c[19]:.4g}")
 if players: print("player mode: slots per team", eng.n_slots, "packed slots", eng.ctx.packed_slots(0)[:6].tolist())
 print(f"{os.environ.get('FMC_LIB_PATH','default')}: {games} games {best:.1f} ms -> {games/best*1e3:.3e} games/s {c[1]/best*1e3:.3e} plays/s  checksum {int(hist.to(torch.int64).mul(torch.arange(128*128*2, device='cuda').view(1,2,128,128)).sum())}")

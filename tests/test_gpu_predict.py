@@ -48,6 +48,35 @@ def test_sklearn_golden_through_gpu(engine, models_s2):
         assert np.array_equal(got, g[f"{fam}/pred"][sel])
 
 
+def test_per_row_names_all_golden_rows(engine, oracle, models_s2):
+    """Every row of the golden file with ITS OWN passer / target / rusher columns (FMC:744, 756, 784-809 predict rows
+    with arbitrary names): fmc_tree_predict_cols_host against the live sklearn pipelines' predictions, bit for bit,
+    and against the oracle for the boosters."""
+    g = np.load(os.path.join(GOLDEN, "sklearn_quantiles.npz"))
+    for fam in ("pass_yards", "run_yards", "sack_yards"):
+        act = g[f"{fam}/active"].astype(np.int32)
+        assert len(np.unique(act, axis=0)) > 5                     # many different name pairs in one call
+        got = engine.predict(fam, g["num"], hot_cols=act)
+        assert np.array_equal(got, g[f"{fam}/pred"]), fam
+    rng = np.random.default_rng(8)
+    for name in ("pass_stage1", "pass_stage2", "run_fumble"):
+        f = models_s2[name]
+        rows = _rows(3000, 17)
+        cols = np.full((rows.shape[0], 2), -1, dtype=np.int32)
+        for gi, grp in enumerate(f.groups[:2]):
+            pick = rng.integers(-1, len(grp.categories), rows.shape[0])
+            cols[:, gi] = np.where(pick < 0, -1, grp.base + pick)
+        ref = oracle.predict(name, rows, cols, f.n_outputs)
+        got = engine.predict(name, rows[:, :f.n_num], hot_cols=cols)
+        assert np.array_equal(got, ref), name
+    # by name, through the category lists
+    f = models_s2["pass_stage1"]
+    rows = _rows(64, 3)
+    names = [("Caleb Williams", "Unknown") if i % 2 else ("nobody at all", None) for i in range(64)]
+    cols = np.array([[f.groups[0].column_of(a), f.groups[1].column_of(b)] for a, b in names], dtype=np.int32)
+    assert np.array_equal(engine.predict("pass_stage1", rows, names=names), oracle.predict("pass_stage1", rows, cols, 1))
+
+
 def test_named_players_and_tree_ranges(engine, oracle, models_s2):
     """Real one-hot columns (fmc_set_active_columns) and iteration_range (sim_helpers.py:22-23)."""
     p = json.load(open(os.path.join(GOLDEN, "xgb_provisional.json")))
