@@ -323,9 +323,16 @@ __device__ __forceinline__ double sample_yards(const SimKernelArgs &a, Draws<TES
     return (m > hi) ? hi : m;
 }
 
+// matchups a slate works on at a time (see the matchup selection of the kernels)
+#ifndef FMC_SLATE_WAVE
+#define FMC_SLATE_WAVE 8
+#endif
+constexpr int kSlateWave = FMC_SLATE_WAVE;
+
 struct SimShared {
     MatchupDev M;
     int cur_matchup;
+    int scan_from;                    // no matchup below this index has games left
     unsigned int cnt[2][kNumKeys];    // requests per key, double-buffered by round parity
     unsigned int off[kNumKeys];       // first position of each key's list
     unsigned int evalc[kNumKeys];     // requests of the key that are evaluated this round (the rest wait one round)
@@ -818,7 +825,7 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
         feats[(size_t)(i >> 5) * kChunkFloats + kSimNinfRow * 32 + (i & 31)] = __int_as_float(0xff800000);
     if (tid < FMC_N_COUNTERS) sh.stat[tid] = 0ULL;
     if (tid < kNumKeys) { sh.cnt[0][tid] = 0; sh.cnt[1][tid] = 0; sh.aged[tid] = 0; }
-    if (tid == 0) sh.cur_matchup = -1;
+    if (tid == 0) { sh.cur_matchup = -1; sh.scan_from = 0; }
     __syncthreads();
 
     PackedLane P;
@@ -839,12 +846,20 @@ __global__ void __launch_bounds__(kSimThreads, kSimCtasPerSm) sim_kernel(const S
         // ---- pick the next matchup that still has games; CTAs start at different matchups so that a
         // slate is spread over the SMs and each CTA drains only when its matchup runs dry
         if (tid == 0) {
-            int found = -1;
-            const int start = (sh.cur_matchup < 0) ? (int)(blockIdx.x % (unsigned)a.n_matchups) : sh.cur_matchup;
-            for (int j = 0; j < a.n_matchups; ++j) {
-                const int m = (start + j) % a.n_matchups;
-                if (*((volatile unsigned long long *)&a.next_game[m]) < a.matchups[m].game_end) { found = m; break; }
+            // Waves: the CTAs of the grid share the kSlateWave lowest-numbered matchups that still have games (CTA b takes
+            // the (b mod kSlateWave)-th of them), and move up as matchups drain -- so a slate keeps a handful of node
+            // tables (and their memo entries) live at a time instead of one per CTA (720 x 0.6 MB for a season).
+            int found = -1, last = -1, seen = 0;
+            const int want = (int)(blockIdx.x % (unsigned)kSlateWave);
+            for (int m = sh.scan_from; m < a.n_matchups; ++m) {
+                if (*((volatile unsigned long long *)&a.next_game[m]) < a.matchups[m].game_end) {
+                    if (seen == 0) sh.scan_from = m;          // everything below is finished for good
+                    last = m;
+                    if (seen == want) { found = m; break; }
+                    if (++seen >= kSlateWave) break;
+                }
             }
+            if (found < 0) found = last;                      // fewer unfinished matchups than the wave is wide
             sh.cur_matchup = found;
         }
         __syncthreads();

@@ -74,23 +74,24 @@ __device__ __forceinline__ void memo_insert(unsigned long long addr, unsigned lo
         if (u < units) memo_st(addr + 16ull * u, key | (unsigned long long)u, r[u]);
 }
 
-// per-lane event tally: 8-bit fields, four per word (flushed to the warp's totals every few scheduler steps)
-enum { EV_GO = 0, EV_FGA, EV_FG, EV_PUNT, EV_RUN, EV_PASS, EV_COMP, EV_INC, EV_INT, EV_SACK, EV_TD, EV_GAMES, EV_PROBE,
+// warp-level event tally of one trip: four words of five 6-bit fields each (a lane adds at most one per field and
+// trip, a field's warp sum is at most 32) -- except the probe count, which has a word of its own
+enum { EV_GO = 0, EV_FGA, EV_FG, EV_PUNT, EV_RUN, EV_PASS, EV_COMP, EV_INC, EV_INT, EV_SACK, EV_TD, EV_GAMES,
        EV_HIT0, EV_HIT1, EV_HIT2, EV_HIT3, EV_HIT4, EV_HIT5, EV_N };
 __device__ __constant__ int kEvCounter[EV_N] = {FMC_C_GO, FMC_C_FGA, FMC_C_FG, FMC_C_PUNT, FMC_C_RUN, FMC_C_PASS, FMC_C_COMP,
-                                                FMC_C_INC, FMC_C_INT, FMC_C_SACK, FMC_C_TD, FMC_C_GAMES, FMC_C_MEMO_PROBES,
+                                                FMC_C_INC, FMC_C_INT, FMC_C_SACK, FMC_C_TD, FMC_C_GAMES,
                                                 FMC_C_MEMO_HITS_FAM0, FMC_C_MEMO_HITS_FAM0 + 1, FMC_C_MEMO_HITS_FAM0 + 2,
                                                 FMC_C_MEMO_HITS_FAM0 + 3, FMC_C_MEMO_HITS_FAM0 + 4, FMC_C_MEMO_HITS_FAM0 + 5};
-constexpr int kEvWords = (EV_N + 3) / 4;
-constexpr int kWstat = 24;             // EV_N event totals, then plays, iters
-static_assert(EV_N + 2 <= kWstat && EV_N + 2 <= 32, "one lane per tally");
+constexpr int kEvWords = (EV_N + 4) / 5;
+constexpr int kWstat = 24;             // EV_N event totals, then plays, iters, probes
+static_assert(EV_N + 3 <= kWstat && EV_N + 3 <= 32, "one lane per tally");
 struct EvTally {
     uint32_t w[kEvWords];
     __device__ __forceinline__ EvTally() {
 #pragma unroll
         for (int i = 0; i < kEvWords; ++i) w[i] = 0u;
     }
-    __device__ __forceinline__ void hit(int ev) { w[ev >> 2] += 1u << (8 * (ev & 3)); }
+    __device__ __forceinline__ void hit(int ev) { w[ev / 5] += 1u << (6 * (ev % 5)); }
 };
 
 // CTA shape of the memo kernel (independent of sim_kernel's): with most requests answered by the memo the walk no
@@ -101,12 +102,6 @@ struct EvTally {
 #ifndef FMC_MEMO_CTAS_PER_SM
 #define FMC_MEMO_CTAS_PER_SM 1
 #endif
-// every stage of a trip is entered by the whole warp together (no lane leaves the trip loop on its own)
-#ifndef FMC_MEMO_NO_SYNCWARP
-#define FMC_MEMO_CONVERGE() __syncwarp()
-#else
-#define FMC_MEMO_CONVERGE() ((void)0)
-#endif
 constexpr int kMemoThreads = FMC_MEMO_THREADS;
 constexpr int kMemoCtasPerSm = FMC_MEMO_CTAS_PER_SM;
 constexpr int kMemoChunks = kMemoThreads / 32 + kNumKeys;        // every key's list starts on a chunk boundary
@@ -116,6 +111,7 @@ constexpr size_t kMemoResultBytes = (size_t)kMemoChunks * 32 * 3 * 8;
 struct MemoShared {
     MatchupDev M;
     int cur_matchup;
+    int scan_from;                       // no matchup below this index has games left
     unsigned int cnt[2][kNumKeys];
     unsigned int off[kNumKeys], evalc[kNumKeys], aged[kNumKeys];
     unsigned int item_prefix[kNumKeys + 1];
@@ -123,20 +119,17 @@ struct MemoShared {
     unsigned int alive[2];
     unsigned long long stat[FMC_N_COUNTERS];
     unsigned int waiting[2];             // warps that have left the trip loop this round (by round parity)
-    unsigned long long wstat[kMemoThreads / 32][kWstat];  // per-warp event totals (EV_*, then plays, iters), no atomics
+    unsigned long long wstat[kMemoThreads / 32][kWstat];  // per-warp event totals (EV_*, then plays, iters, probes), no atomics
 };
 constexpr size_t kMemoSharedBytes = ((sizeof(MemoShared) + 15) / 16) * 16;
 constexpr size_t kMemoKeyBytes = (size_t)kMemoThreads * 8;
 inline size_t sim_memo_smem_bytes() { return kMemoSharedBytes + kMemoFeatBytes + kMemoResultBytes + kMemoKeyBytes; }
 
-// Launch bounds: always those of a full 1024-thread CTA (64 registers per thread), also when the CTA is smaller --
-// builds with __launch_bounds__(512 | 768, ...) of this kernel die on the B200 with "an illegal instruction was
-// encountered" at the first launch (ptxas 12.9; the same source with bounds 1024 launched with 512 threads is fine).
-#ifndef FMC_MEMO_LB
-#define FMC_MEMO_LB 1024
-#endif
+// (bounds of a full CTA whatever kMemoThreads: builds of this kernel with __launch_bounds__(512 | 768, ...) die on the B200
+// with "an illegal instruction was encountered" at the first launch; the same source with bounds 1024 and a 512-thread
+// launch is fine -- ptxas 12.9)
 template <bool TEST>
-__global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKernelArgs a, const MemoArgs mm) {
+__global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a, const MemoArgs mm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kChunkFloats = chunk_floats(false);
     constexpr size_t kFeatBytes_ = kMemoFeatBytes;
@@ -153,7 +146,7 @@ __global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKerne
     if (tid < FMC_N_COUNTERS) sh.stat[tid] = 0ULL;
     for (int i = tid; i < (kMemoThreads / 32) * kWstat; i += kMemoThreads) (&sh.wstat[0][0])[i] = 0ULL;
     if (tid < kNumKeys) { sh.cnt[0][tid] = 0; sh.cnt[1][tid] = 0; sh.aged[tid] = 0; }
-    if (tid == 0) { sh.cur_matchup = -1; sh.alive[0] = 0; sh.alive[1] = 0; sh.waiting[0] = 0; sh.waiting[1] = 0; }
+    if (tid == 0) { sh.cur_matchup = -1; sh.scan_from = 0; sh.alive[0] = 0; sh.alive[1] = 0; sh.waiting[0] = 0; sh.waiting[1] = 0; }
     __syncthreads();
 
     PackedLane P;
@@ -169,12 +162,20 @@ __global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKerne
 
     for (;;) {
         if (tid == 0) {
-            int found = -1;
-            const int start = (sh.cur_matchup < 0) ? (int)(blockIdx.x % (unsigned)a.n_matchups) : sh.cur_matchup;
-            for (int j = 0; j < a.n_matchups; ++j) {
-                const int m = (start + j) % a.n_matchups;
-                if (*((volatile unsigned long long *)&a.next_game[m]) < a.matchups[m].game_end) { found = m; break; }
+            // Waves: the CTAs of the grid share the kSlateWave lowest-numbered matchups that still have games (CTA b takes
+            // the (b mod kSlateWave)-th of them), and move up as matchups drain -- so a slate keeps a handful of node
+            // tables (and their memo entries) live at a time instead of one per CTA (720 x 0.6 MB for a season).
+            int found = -1, last = -1, seen = 0;
+            const int want = (int)(blockIdx.x % (unsigned)kSlateWave);
+            for (int m = sh.scan_from; m < a.n_matchups; ++m) {
+                if (*((volatile unsigned long long *)&a.next_game[m]) < a.matchups[m].game_end) {
+                    if (seen == 0) sh.scan_from = m;          // everything below is finished for good
+                    last = m;
+                    if (seen == want) { found = m; break; }
+                    if (++seen >= kSlateWave) break;
+                }
             }
+            if (found < 0) found = last;                      // fewer unfinished matchups than the wave is wide
             sh.cur_matchup = found;
         }
         __syncthreads();
@@ -198,7 +199,6 @@ __global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKerne
             Lane L = unpack_lane(P);
             unsigned long long r[3] = {0ULL, 0ULL, 0ULL};
             bool have = false;         // r[] holds the outputs the lane's stage waits for
-            bool unmemoised = false;   // ... and they came from a walk of a request that has no memo entry
             // ---- D: walked requests come back; they also enter the memo
             if (parked && pos >= 0) {
                 const unsigned long long *src = reinterpret_cast<const unsigned long long *>(results) + (size_t)pos * 3;
@@ -206,91 +206,39 @@ __global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKerne
                 const int fam = stage_family(L.stage);
                 const unsigned long long key = mkey[tid];
                 if (key != 0ULL) memo_insert(memo_slot_addr(mm.region[fam], key), key, memo_units(fam), r);
-                unmemoised = key == 0ULL;
                 have = true;
                 parked = false;
             }
             pos = -1;
-            // ---- A: stage scheduler.  Every lane is at some stage of its play; each step the warp executes the ONE
-            // stage that most of its lanes wait at (warp match + max), for those lanes only, so that a stage's code --
-            // Philox, the inverse normal, the float64 divisions of the outcome logic -- runs for many lanes at a time
-            // instead of once per lane path (rare stages: punts, interceptions, sacks simply wait until enough lanes
-            // have gathered or nothing else can run).  A lane whose probe misses parks until the walk of phase C.
-            Lane Lv = L;
-            Lv.iter = (L.stage == ST_ITER || L.stage == ST_NEED_GAME) ? L.iter : L.iter - 1;
-            Draws<TEST> D(a, M, m, Lv);
-            EvTally ev;
-            uint32_t fin_plays = 0, fin_iters = 0;
-            for (int step = 0;; ++step) {
-                const bool runnable = !parked && L.stage != ST_IDLE;
-                // scheduling class: NEED_GAME joins ITER, the run and pass yardage stages share their code
-                const int cls = L.stage == ST_NEED_GAME ? (int)ST_ITER : (L.stage == ST_WAIT_RQ ? (int)ST_WAIT_PQ : L.stage);
-                const unsigned int peers = __match_any_sync(FULL, runnable ? cls : 31);
-                // an output that is not in the memo (its family is not memoised) must be used before the round ends: it
-                // cannot be looked up again -- its class goes first.  Every other output a lane still holds when the round
-                // stops is simply looked up again next round.
-                const unsigned int keep_mask = __ballot_sync(FULL, runnable && have && unmemoised);
-                const unsigned int score = runnable ? (((unsigned int)__popc(peers) + ((peers & keep_mask) ? 32u : 0u)) << 5) | (unsigned int)(31 - cls)
-                                                    : 0u;
-                const unsigned int best = __reduce_max_sync(FULL, score);
-                const unsigned int n_run = (unsigned int)__popc(__ballot_sync(FULL, runnable));
-                // every round runs at least one stage (progress), then stops when few lanes can still run
-                bool stop = best == 0u || (step > 0 && keep_mask == 0u && (step >= mm.max_trips || (int)n_run <= 32 - mm.break_parked));
-#ifndef FMC_MEMO_NO_WAITING
-                if (!stop && (step & 3) == 3) {
-                    unsigned int wv = 0;
-                    if (lane == 0) wv = *((volatile unsigned int *)&sh.waiting[parity]);
-                    wv = __shfl_sync(FULL, wv, 0);
-                    stop = wv >= (unsigned int)mm.break_waiting;
-                }
-#endif
-                if (stop || (step & 3) == 3) {
-                    // warp tallies: a lane adds at most one per field and step, so at most 4 x 32 = 128 per 8-bit field
-                    // since the last flush -- the warp sum of a whole word never carries between fields
-#pragma unroll
-                    for (int i = 0; i < kEvWords; ++i) {
-                        const uint32_t t = __reduce_add_sync(FULL, ev.w[i]);
-                        if (lane < EV_N && (lane >> 2) == i) {
-                            const uint32_t c = (t >> (8 * (lane & 3))) & 0xFFu;
-                            if (c) sh.wstat[warp][lane] += (unsigned long long)c;
-                        }
-                        ev.w[i] = 0u;
-                    }
-                    const uint32_t tp = __reduce_add_sync(FULL, fin_plays), ti = __reduce_add_sync(FULL, fin_iters);
-                    if (lane == EV_N) { if (tp) sh.wstat[warp][EV_N] += (unsigned long long)tp; }
-                    else if (lane == EV_N + 1) { if (ti) sh.wstat[warp][EV_N + 1] += (unsigned long long)ti; }
-                    fin_plays = 0; fin_iters = 0;
-                }
-                if (stop) break;
+            // ---- A: trips
+            for (int trip = 0; trip < mm.max_trips; ++trip) {
                 trips += 1;
-                const int kb = 31 - (int)(best & 31u);
-                const bool mine = runnable && cls == kb;
-                const int team = L.offense;
-                const int sd = L.score[team] - L.score[team ^ 1];
-                if (kb == ST_ITER) {
-                    // -- game over (FMC:1456-1464, 1501-1503)
-                    const bool over = mine && L.stage == ST_ITER && L.sec <= 0;
-                    const unsigned int over_mask = __ballot_sync(FULL, over);
-                    if (over) {
-                        const size_t oi = (size_t)(M.out_offset + (L.game - M.game_begin));
-                        if (a.scores) a.scores[oi] = (uint32_t)L.score[0] | ((uint32_t)L.score[1] << 16);
-                        if (a.iters) a.iters[oi] = (uint16_t)L.iter;
-                        if (a.hist) {
-                            const int ha = L.score[0] < FMC_HIST_BINS ? L.score[0] : FMC_HIST_BINS - 1;
-                            const int hb = L.score[1] < FMC_HIST_BINS ? L.score[1] : FMC_HIST_BINS - 1;
-                            if (L.score[0] >= FMC_HIST_BINS || L.score[1] >= FMC_HIST_BINS) atomicAdd(&sh.stat[FMC_C_HIST_OVERFLOW], 1ULL);
-                            const unsigned int bin = (unsigned int)(((L.game & 1ULL) * FMC_HIST_BINS + ha) * FMC_HIST_BINS + hb);
-                            // warp-level reduce: lanes finishing in the same bin add once
-                            const unsigned int same = __match_any_sync(over_mask, bin);
-                            if (lane == __ffs(same) - 1)
-                                atomicAdd(&a.hist[(size_t)m * 2 * FMC_HIST_BINS * FMC_HIST_BINS + bin], (unsigned int)__popc(same));
-                        }
-                        ev.hit(EV_GAMES);
-                        fin_plays += (uint32_t)L.plays; fin_iters += (uint32_t)L.iter;
-                        L.stage = ST_NEED_GAME;
+                EvTally ev;
+                uint32_t fin_plays = 0, fin_iters = 0, n_probes = 0;
+                // -- game over (FMC:1456-1464, 1501-1503)
+                const bool over = !parked && L.stage == ST_ITER && L.sec <= 0;
+                const unsigned int over_mask = __ballot_sync(FULL, over);
+                if (over) {
+                    const size_t oi = (size_t)(M.out_offset + (L.game - M.game_begin));
+                    if (a.scores) a.scores[oi] = (uint32_t)L.score[0] | ((uint32_t)L.score[1] << 16);
+                    if (a.iters) a.iters[oi] = (uint16_t)L.iter;
+                    if (a.hist) {
+                        const int ha = L.score[0] < FMC_HIST_BINS ? L.score[0] : FMC_HIST_BINS - 1;
+                        const int hb = L.score[1] < FMC_HIST_BINS ? L.score[1] : FMC_HIST_BINS - 1;
+                        if (L.score[0] >= FMC_HIST_BINS || L.score[1] >= FMC_HIST_BINS) atomicAdd(&sh.stat[FMC_C_HIST_OVERFLOW], 1ULL);
+                        const unsigned int bin = (unsigned int)(((L.game & 1ULL) * FMC_HIST_BINS + ha) * FMC_HIST_BINS + hb);
+                        // warp-level reduce: lanes finishing in the same bin add once
+                        const unsigned int peers = __match_any_sync(over_mask, bin);
+                        if (lane == __ffs(peers) - 1)
+                            atomicAdd(&a.hist[(size_t)m * 2 * FMC_HIST_BINS * FMC_HIST_BINS + bin], (unsigned int)__popc(peers));
                     }
-                    // -- next game: one global atomic per warp
-                    const bool need = mine && L.stage == ST_NEED_GAME;
+                    ev.hit(EV_GAMES);
+                    fin_plays = (uint32_t)L.plays; fin_iters = (uint32_t)L.iter;
+                    L.stage = ST_NEED_GAME;
+                }
+                // -- next game: one global atomic per warp
+                {
+                    const bool need = !parked && L.stage == ST_NEED_GAME;
                     const unsigned int nm = __ballot_sync(FULL, need);
                     if (nm) {
                         unsigned long long base = 0ULL;
@@ -309,70 +257,61 @@ __global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKerne
                             }
                         }
                     }
-                    // -- iteration start
-                    if (mine && L.stage == ST_ITER) {
-                        if (TEST && a.trace && L.iter < FMC_MAX_ITERS) {
-                            const int first = (int)(L.game & 1ULL);
-                            double *t = a.trace + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_TRACE_COLS;
-                            t[0] = (L.offense == first) ? 1.0 : 0.0; t[1] = (double)L.down; t[2] = (double)L.sec;
-                            t[3] = (double)L.score[first]; t[4] = (double)L.score[first ^ 1]; t[5] = L.dist; t[6] = L.ytg;
-                            t[7] = (double)L.going;
-                        }
-                        D.restart(a, M, L);                   // the draw record of iteration L.iter
-                        L.iter += 1;
-                        L.stage = L.down == 4 ? ST_FOURTH : ST_CALL;
-                    }
                 }
-                if (kb == ST_FOURTH) {
-                    // -- handle_fourth FMC:1382-1421: go for it, field goal, or punt
-                    if (mine) {
-                        const int tm = L.offense;
-                        const int sdd = L.score[tm] - L.score[tm ^ 1];
+                // draws of the iteration this trip works on: a lane that enters at ST_ITER starts iteration L.iter,
+                // one that resumes a parked play is inside iteration L.iter - 1
+                Lane Lv = L;
+                Lv.iter = (L.stage == ST_ITER) ? L.iter : L.iter - 1;
+                Draws<TEST> D(a, M, m, Lv);
+                const int team = L.offense;
+                const int sd = L.score[team] - L.score[team ^ 1];
+                const double ytg0 = L.ytg;
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
+                // -- iteration start: fourth down (handle_fourth FMC:1382-1421) and the play call
+                if (!parked && L.stage == ST_ITER) {
+                    if (TEST && a.trace && L.iter < FMC_MAX_ITERS) {
+                        const int first = (int)(L.game & 1ULL);
+                        double *t = a.trace + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_TRACE_COLS;
+                        t[0] = (L.offense == first) ? 1.0 : 0.0; t[1] = (double)L.down; t[2] = (double)L.sec;
+                        t[3] = (double)L.score[first]; t[4] = (double)L.score[first ^ 1]; t[5] = L.dist; t[6] = L.ytg;
+                        t[7] = (double)L.going;
+                    }
+                    L.iter += 1;
+                    bool play = true;
+                    if (L.down == 4) {
                         const double ytg = L.ytg, dist = L.dist;
-                        const double p_go = pymin(1.0, go_for_it_prob(ytg, dist, sdd, L.sec) * 1.15);
+                        const double p_go = pymin(1.0, go_for_it_prob(ytg, dist, sd, L.sec) * 1.15);
                         if (D.u(S_U_GO) < p_go) {
                             L.going = 1;
                             ev.hit(EV_GO);
-                            L.stage = ST_CALL;
                         } else if (ytg <= 38.0) {
                             ev.hit(EV_FGA);
                             const bool good = D.u(S_U_FG) < field_goal_prob(ytg + 17.0);
                             tick_clock(L, 12);
-                            if (good) { ev.hit(EV_FG); L.score[tm] += 3; change_possession(L, true, 75.0); }
+                            if (good) { ev.hit(EV_FG); L.score[team] += 3; change_possession(L, true, 75.0); }
                             else change_possession(L, true, 100.0 - ytg);
-                            L.stage = ST_ITER;
+                            play = false;
                         } else {
                             ev.hit(EV_PUNT);
-                            L.stage = ST_PUNT;
+                            const double gross = pymax(30.0, 43.0 + 6.0 * D.z(S_Z_GROSS));      // attempt_punt FMC:876-896
+                            const double ret = pymax(0.0, 6.0 + 3.0 * D.z(S_Z_RET));
+                            double net = gross - ret;
+                            if (ytg <= 60.0) {
+                                const double tb = softclip((60.0 - ytg) / 60.0, 0.10, 0.55);
+                                if (D.u(S_U_TB) < tb) net = ytg - 25.0;
+                            }
+                            net = softclip(net, 15.0, ytg - 1.0);
+                            const int inet = (int)net;
+                            tick_clock(L, 16);
+                            change_possession(L, true, softclip(100.0 - (ytg - (double)inet), 1.0, 99.0));
+                            play = false;
                         }
                     }
-                }
-                if (kb == ST_PUNT) {
-                    if (mine) {                                  // attempt_punt FMC:876-896
-                        const double ytg = L.ytg;
-                        const double gross = pymax(30.0, 43.0 + 6.0 * D.z(S_Z_GROSS));
-                        const double ret = pymax(0.0, 6.0 + 3.0 * D.z(S_Z_RET));
-                        double net = gross - ret;
-                        if (ytg <= 60.0) {
-                            const double tb = softclip((60.0 - ytg) / 60.0, 0.10, 0.55);
-                            if (D.u(S_U_TB) < tb) net = ytg - 25.0;
-                        }
-                        net = softclip(net, 15.0, ytg - 1.0);
-                        const int inet = (int)net;
-                        tick_clock(L, 16);
-                        change_possession(L, true, softclip(100.0 - (ytg - (double)inet), 1.0, 99.0));
-                        L.stage = ST_ITER;
-                    }
-                }
-                // the play call follows the iteration start at once for the lanes that need no fourth-down decision
-                if (kb == ST_CALL || kb == ST_ITER) {
-                    if (runnable && L.stage == ST_CALL) {          // simulate_play FMC:1026-...: the play call
-                        const int tm = L.offense;
-                        const int sdd = L.score[tm] - L.score[tm ^ 1];
+                    if (play) {                                   // simulate_play FMC:1026-...: the play call
                         L.plays += 1;
                         if (a.policy == 1) L.stage = ST_WAIT_PM;
                         else {
-                            const double p_pass = pass_prob_v1(L.down, L.dist, L.ytg, L.sec, sdd);
+                            const double p_pass = pass_prob_v1(L.down, L.dist, L.ytg, L.sec, sd);
                             double a0 = 1.0 - p_pass, a1 = p_pass;
                             const double s = a0 + a1;
                             a0 = a0 / s; a1 = a1 / s;
@@ -382,20 +321,21 @@ __global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKerne
                         }
                     }
                 }
-                if (kb == ST_WAIT_PM) {
-                    // -- play model (policy 1): probe, then FMC:420-425
-                    if (mine && !have) {
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
+                // -- play model (policy 1): probe, then FMC:420-425
+                if (a.policy == 1) {
+                    if (!parked && !have && L.stage == ST_WAIT_PM) {
                         const RankSpec *rs = specs + 5 * 2 + team;
                         unsigned long long key = 0ULL;
                         bool hit = false;
                         if (mm.enabled && __ldg(&rs->enabled)) {
                             key = lane_memo_key<true>(rs, 5, team, m, L, a);
                             hit = memo_probe<3>(memo_slot_addr(mm.region[5], key), key, r);
-                            ev.hit(EV_PROBE); if (hit) ev.hit(EV_HIT5);
+                            n_probes += 1; if (hit) ev.hit(EV_HIT5);
                         }
                         if (hit) have = true; else { parked = true; mkey[tid] = key; }
                     }
-                    if (mine && have) {
+                    if (have && L.stage == ST_WAIT_PM) {
                         float mg[6];
                         mg[0] = __uint_as_float((uint32_t)r[0]); mg[1] = __uint_as_float((uint32_t)(r[0] >> 32));
                         mg[2] = __uint_as_float((uint32_t)r[1]); mg[3] = __uint_as_float((uint32_t)(r[1] >> 32));
@@ -412,76 +352,72 @@ __global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKerne
                         have = false;
                     }
                 }
-                if (kb == ST_WAIT_S1) {
-                    // -- stage 1: probe, then FMC:1086-1087
-                    if (mine && !have) {
-                        const RankSpec *rs = specs + 0 * 2 + team;
-                        unsigned long long key = 0ULL;
-                        bool hit = false;
-                        if (mm.enabled && __ldg(&rs->enabled)) {
-                            key = lane_memo_key<true>(rs, 0, team, m, L, a);
-                            hit = memo_probe<1>(memo_slot_addr(mm.region[0], key), key, r);
-                            ev.hit(EV_PROBE); if (hit) ev.hit(EV_HIT0);
-                        }
-                        if (hit) have = true; else { parked = true; mkey[tid] = key; }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
+                // -- stage 1: probe, then FMC:1086-1087
+                if (!parked && !have && L.stage == ST_WAIT_S1) {
+                    const RankSpec *rs = specs + 0 * 2 + team;
+                    unsigned long long key = 0ULL;
+                    bool hit = false;
+                    if (mm.enabled && __ldg(&rs->enabled)) {
+                        key = lane_memo_key<true>(rs, 0, team, m, L, a);
+                        hit = memo_probe<1>(memo_slot_addr(mm.region[0], key), key, r);
+                        n_probes += 1; if (hit) ev.hit(EV_HIT0);
                     }
-                    if (mine && have) {
-                        const float m1 = __uint_as_float((uint32_t)r[0]);
-                        const double p1 = (double)(1.0f / (expf_cr(-m1) + 1.0f));                 // xgboost sigmoid, float32
-                        const double p_complete = softclip(p1 + M.bias[team], 0.02, 0.98);
-                        have = false;
-                        if (D.u(S_U_COMP) < p_complete) { ev.hit(EV_COMP); L.stage = ST_WAIT_PQ; }
-                        else L.stage = ST_WAIT_S2;        // with the stand-in the stage-2 block needs no model output
-                    }
+                    if (hit) have = true; else { parked = true; mkey[tid] = key; }
                 }
-                if (kb == ST_WAIT_S2) {
-                    // -- stage 2: probe, then the not-complete outcome FMC:751-770, 1157-1199
-                    const bool standin = a.stage2_mode != 1;
-                    if (mine && !have && !standin) {
-                        const RankSpec *rs = specs + 1 * 2 + team;
-                        unsigned long long key = 0ULL;
-                        bool hit = false;
-                        if (mm.enabled && __ldg(&rs->enabled)) {
-                            key = lane_memo_key<true>(rs, 1, team, m, L, a);
-                            hit = memo_probe<2>(memo_slot_addr(mm.region[1], key), key, r);
-                            ev.hit(EV_PROBE); if (hit) ev.hit(EV_HIT1);
-                        }
-                        if (hit) have = true; else { parked = true; mkey[tid] = key; }
-                    }
-                    if (mine && (have || standin)) {
-                        double raw[3];
-                        if (!standin) {
-                            float mg[3];
-                            mg[0] = __uint_as_float((uint32_t)r[0]); mg[1] = __uint_as_float((uint32_t)(r[0] >> 32)); mg[2] = __uint_as_float((uint32_t)r[1]);
-                            float wmax = mg[0];
-                            wmax = fmaxf(mg[1], wmax); wmax = fmaxf(mg[2], wmax);
-                            float e[3];
-                            double wsum = 0.0;
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) { e[k] = expf_cr(mg[k] - wmax); wsum += (double)e[k]; }
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) raw[k] = (double)(e[k] / (float)wsum);
-                        } else {
-                            raw[0] = a.standin[0]; raw[1] = a.standin[1]; raw[2] = a.standin[2];
-                        }
-                        have = false;
-                        const int outcome = stage2_outcome(raw, D.u(S_U_S2));
-                        if (outcome == 0) {                                   // incomplete FMC:1160-1168
-                            ev.hit(EV_INC);
-                            L.down += 1; L.going = 0;
-                            tick_clock(L, 10);
-                            L.stage = ST_ITER;
-                        } else if (outcome == 2) {
-                            ev.hit(EV_SACK);
-                            L.stage = ST_WAIT_SQ;
-                        } else {
-                            ev.hit(EV_INT);
-                            L.stage = ST_INT;
-                        }
-                    }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
+                bool s2_standin = false;
+                if (have && L.stage == ST_WAIT_S1) {
+                    const float m1 = __uint_as_float((uint32_t)r[0]);
+                    const double p1 = (double)(1.0f / (expf_cr(-m1) + 1.0f));                 // xgboost sigmoid, float32
+                    const double p_complete = softclip(p1 + M.bias[team], 0.02, 0.98);
+                    have = false;
+                    if (D.u(S_U_COMP) < p_complete) { ev.hit(EV_COMP); L.stage = ST_WAIT_PQ; }
+                    else if (a.stage2_mode == 1) L.stage = ST_WAIT_S2;
+                    else s2_standin = true;
                 }
-                if (kb == ST_INT) {
-                    if (mine) {                                               // intercepted FMC:1186-1199
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
+                // -- stage 2: probe, then the not-complete outcome FMC:751-770, 1157-1199
+                if (!parked && !have && L.stage == ST_WAIT_S2) {
+                    const RankSpec *rs = specs + 1 * 2 + team;
+                    unsigned long long key = 0ULL;
+                    bool hit = false;
+                    if (mm.enabled && __ldg(&rs->enabled)) {
+                        key = lane_memo_key<true>(rs, 1, team, m, L, a);
+                        hit = memo_probe<2>(memo_slot_addr(mm.region[1], key), key, r);
+                        n_probes += 1; if (hit) ev.hit(EV_HIT1);
+                    }
+                    if (hit) have = true; else { parked = true; mkey[tid] = key; }
+                }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
+                if ((have && L.stage == ST_WAIT_S2) || s2_standin) {
+                    double raw[3];
+                    if (!s2_standin) {
+                        float mg[3];
+                        mg[0] = __uint_as_float((uint32_t)r[0]); mg[1] = __uint_as_float((uint32_t)(r[0] >> 32)); mg[2] = __uint_as_float((uint32_t)r[1]);
+                        float wmax = mg[0];
+                        wmax = fmaxf(mg[1], wmax); wmax = fmaxf(mg[2], wmax);
+                        float e[3];
+                        double wsum = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) { e[k] = expf_cr(mg[k] - wmax); wsum += (double)e[k]; }
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) raw[k] = (double)(e[k] / (float)wsum);
+                    } else {
+                        raw[0] = a.standin[0]; raw[1] = a.standin[1]; raw[2] = a.standin[2];
+                    }
+                    have = false;
+                    const int outcome = stage2_outcome(raw, D.u(S_U_S2));
+                    if (outcome == 0) {                                   // incomplete FMC:1160-1168
+                        ev.hit(EV_INC);
+                        L.down += 1; L.going = 0;
+                        tick_clock(L, 10);
+                        L.stage = ST_ITER;
+                    } else if (outcome == 2) {
+                        ev.hit(EV_SACK);
+                        L.stage = ST_WAIT_SQ;
+                    } else {                                              // intercepted FMC:1186-1199
+                        ev.hit(EV_INT);
                         const double ret = softclip(6.0 + 5.0 * D.z(S_Z_INT), 0.0, L.ytg);
                         const double spot = 100.0 - (L.ytg - ret);
                         L.going = 0;
@@ -490,66 +426,80 @@ __global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKerne
                         L.stage = ST_ITER;
                     }
                 }
-                if (kb == ST_WAIT_PQ || kb == ST_WAIT_SQ) {
-                    // -- yardage families: probe, then the outcome
-                    if (mine && !have) {
-                        const int fam = stage_family(L.stage);
-                        const RankSpec *rs = specs + fam * 2 + team;
-                        unsigned long long key = 0ULL;
-                        bool hit = false;
-                        if (mm.enabled && __ldg(&rs->enabled)) {
-                            key = lane_memo_key<false>(rs, fam, team, m, L, a);
-                            hit = memo_probe<3>(memo_slot_addr(mm.region[fam], key), key, r);
-                            ev.hit(EV_PROBE); if (hit) ev.w[(EV_HIT0 + fam) >> 2] += 1u << (8 * ((EV_HIT0 + fam) & 3));
-                        }
-                        if (hit) have = true; else { parked = true; mkey[tid] = key; }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
+                // -- yardage families: probe, then the outcome
+                if (!parked && !have && L.stage >= ST_WAIT_PQ && L.stage <= ST_WAIT_SQ) {
+                    const int fam = stage_family(L.stage);
+                    const RankSpec *rs = specs + fam * 2 + team;
+                    unsigned long long key = 0ULL;
+                    bool hit = false;
+                    if (mm.enabled && __ldg(&rs->enabled)) {
+                        key = lane_memo_key<false>(rs, fam, team, m, L, a);
+                        hit = memo_probe<3>(memo_slot_addr(mm.region[fam], key), key, r);
+                        n_probes += 1; if (hit) ev.w[(EV_HIT0 + fam) / 5] += 1u << (6 * ((EV_HIT0 + fam) % 5));
                     }
-                    if (mine && have) {
-                        const double q[3] = {__longlong_as_double((long long)r[0]), __longlong_as_double((long long)r[1]),
-                                             __longlong_as_double((long long)r[2])};
-                        const double mz = M.mz[team];
-                        const double ytg0 = L.ytg;
-                        have = false;
-                        if (kb == ST_WAIT_SQ) {                          // sack FMC:1170-1184
-                            double loss = -sample_yards(a, D, q, 0.25, -20.0, 0.0);
-                            loss = pymax(0.0, loss);
-                            loss = pymin(loss, 100.0 - (100.0 - L.ytg));
-                            L.ytg += loss; L.dist += loss; L.down += 1; L.going = 0;
-                            tick_clock(L, 24);
-                        } else {
-                            // completed pass FMC:1089-1152 / run FMC:1201-1257: the same steps with different constants
-                            const bool pass = L.stage == ST_WAIT_PQ;
-                            double yards = sample_yards(a, D, q, pass ? 0.4 : 0.35, pass ? 0.0 : -4.0, L.ytg) * M.ymul[team];
-                            if (ytg0 > 25.0 && D.u(S_U_EX) < (pass ? 0.60 : 0.5) * explosive_prob(mz, ytg0)) {
-                                const double ub = pass ? 0.35 + (0.95 - 0.35) * D.u(S_U_BOOST) : 0.2 + (0.5 - 0.2) * D.u(S_U_BOOST);
-                                yards *= 1.0 + ub * (1.0 + (pass ? 0.7 : 0.6) * mz);
-                                yards = pymin(yards, ytg0);
-                            }
-                            if (ytg0 <= (pass ? 12.0 : 9.0) && L.down <= 3) {
-                                if (D.u(S_U_FIN) < rz_finish_prob(ytg0, M.tanh35[team], L.down, pass)) yards = ytg0;
-                            }
-                            if (yards + 1e-9 >= ytg0) {
-                                ev.hit(EV_TD);
-                                L.score[team] += 7; L.going = 0;
-                                tick_clock(L, pass ? 20 : 28);
-                                change_possession(L, true, 75.0);
-                            } else {
-                                L.going = 0;
-                                advance_down(L, yards);
-                                tick_clock(L, pass ? 26 : 28);
-                                L.going = 0;
-                            }
-                        }
-                        L.stage = ST_ITER;
-                    }
+                    if (hit) have = true; else { parked = true; mkey[tid] = key; }
                 }
-                (void)sd;
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
+                if (have && L.stage >= ST_WAIT_PQ && L.stage <= ST_WAIT_SQ) {
+                    const double q[3] = {__longlong_as_double((long long)r[0]), __longlong_as_double((long long)r[1]),
+                                         __longlong_as_double((long long)r[2])};
+                    const double mz = M.mz[team];
+                    have = false;
+                    if (L.stage == ST_WAIT_SQ) {                          // sack FMC:1170-1184
+                        double loss = -sample_yards(a, D, q, 0.25, -20.0, 0.0);
+                        loss = pymax(0.0, loss);
+                        loss = pymin(loss, 100.0 - (100.0 - L.ytg));
+                        L.ytg += loss; L.dist += loss; L.down += 1; L.going = 0;
+                        tick_clock(L, 24);
+                    } else {
+                        // completed pass FMC:1089-1152 / run FMC:1201-1257: the same steps with different constants
+                        const bool pass = L.stage == ST_WAIT_PQ;
+                        double yards = sample_yards(a, D, q, pass ? 0.4 : 0.35, pass ? 0.0 : -4.0, L.ytg) * M.ymul[team];
+                        if (ytg0 > 25.0 && D.u(S_U_EX) < (pass ? 0.60 : 0.5) * explosive_prob(mz, ytg0)) {
+                            const double ub = pass ? 0.35 + (0.95 - 0.35) * D.u(S_U_BOOST) : 0.2 + (0.5 - 0.2) * D.u(S_U_BOOST);
+                            yards *= 1.0 + ub * (1.0 + (pass ? 0.7 : 0.6) * mz);
+                            yards = pymin(yards, ytg0);
+                        }
+                        if (ytg0 <= (pass ? 12.0 : 9.0) && L.down <= 3) {
+                            if (D.u(S_U_FIN) < rz_finish_prob(ytg0, M.tanh35[team], L.down, pass)) yards = ytg0;
+                        }
+                        if (yards + 1e-9 >= ytg0) {
+                            ev.hit(EV_TD);
+                            L.score[team] += 7; L.going = 0;
+                            tick_clock(L, pass ? 20 : 28);
+                            change_possession(L, true, 75.0);
+                        } else {
+                            L.going = 0;
+                            advance_down(L, yards);
+                            tick_clock(L, pass ? 26 : 28);
+                            L.going = 0;
+                        }
+                    }
+                    L.stage = ST_ITER;
+                }
+                __syncwarp();      // every stage of the trip is entered by the whole warp together
+                // -- warp tallies of this trip
+                {
+                    const uint32_t t0 = __reduce_add_sync(FULL, ev.w[0]), t1 = __reduce_add_sync(FULL, ev.w[1]),
+                                   t2 = __reduce_add_sync(FULL, ev.w[2]), t3 = __reduce_add_sync(FULL, ev.w[3]);
+                    const uint32_t tp = __reduce_add_sync(FULL, fin_plays), ti = __reduce_add_sync(FULL, fin_iters),
+                                   tq = __reduce_add_sync(FULL, n_probes);
+                    if (lane < EV_N) {
+                        const uint32_t wv = lane < 5 ? t0 : (lane < 10 ? t1 : (lane < 15 ? t2 : t3));
+                        const uint32_t c = (wv >> (6 * (lane % 5))) & 63u;
+                        if (c) sh.wstat[warp][lane] += (unsigned long long)c;
+                    } else if (lane == EV_N) { if (tp) sh.wstat[warp][EV_N] += (unsigned long long)tp; }
+                    else if (lane == EV_N + 1) { if (ti) sh.wstat[warp][EV_N + 1] += (unsigned long long)ti; }
+                    else if (lane == EV_N + 2) { if (tq) sh.wstat[warp][EV_N + 2] += (unsigned long long)tq; }
+                }
+                // -- stop when the warp has little left to do this round
+                const unsigned int busy = __ballot_sync(FULL, !parked && L.stage != ST_IDLE);
+                if (__popc(busy) <= 32 - mm.break_parked) break;
+                // ... or when enough of the other warps already wait at the barrier for this one
+                if (*((volatile unsigned int *)&sh.waiting[parity]) >= (unsigned int)mm.break_waiting) break;
             }
-            // a lane that holds an output it could not use before the round ended looks it up again next round (it is in
-            // the memo by now); only parked lanes go to the walk
-#ifndef FMC_MEMO_NO_WAITING
             if (lane == 0) atomicAdd(&sh.waiting[parity], 1u);
-#endif
             // ---- B: compact the requests that missed
             const int key = parked ? stage_family(L.stage) * 2 + L.offense : -1;
             unsigned int rank = 0;
@@ -642,10 +592,10 @@ __global__ void __launch_bounds__(FMC_MEMO_LB, 1) sim_memo_kernel(const SimKerne
     if (lane == 0) atomicAdd(&sh.stat[FMC_C_TRIPS], (unsigned long long)trips);
     if (tid == 0) sh.stat[FMC_C_ROUNDS] = (unsigned long long)rounds;
     __syncthreads();
-    if (tid < EV_N + 2) {
+    if (tid < EV_N + 3) {
         unsigned long long s = 0ULL;
         for (int w = 0; w < kMemoThreads / 32; ++w) s += sh.wstat[w][tid];
-        const int ci = tid < EV_N ? kEvCounter[tid] : (tid == EV_N ? FMC_C_PLAYS : FMC_C_ITERS);
+        const int ci = tid < EV_N ? kEvCounter[tid] : (tid == EV_N ? FMC_C_PLAYS : (tid == EV_N + 1 ? FMC_C_ITERS : FMC_C_MEMO_PROBES));
         sh.stat[ci] += s;
     }
     __syncthreads();

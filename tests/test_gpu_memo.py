@@ -36,6 +36,8 @@ def test_memo_modes_bit_identical(models_s2, oracle):
     total_requests = c["pass"] + (c["pass"] - c["comp"]) + c["comp"] + c["run"] + c["sack"]
     assert c["memo_probes"] == total_requests
     assert c["memo_hits"] + c["requests"] == total_requests
+    assert c["memo_hits"] == sum(c[k] for k in ("memo_hits_s1", "memo_hits_s2", "memo_hits_pq", "memo_hits_rq", "memo_hits_sq", "memo_hits_pm"))
+    assert c["memo_hits_pq"] > 0.9 * c["comp"] and c["memo_hits_pm"] == 0
     assert off["counters"]["requests"] == total_requests
     ref = oracle.simulate(oracle.make_config(models_s2, KSU, ISU, stage2="booster"), 20_000, seed=20251018)
     assert np.array_equal(on["scores"][:20_000], ref["scores"])
