@@ -69,14 +69,18 @@ __global__ void __launch_bounds__(kPredThreads) predict_kernel(const PredictArgs
             float *col = rows + (r >> 5) * kPredChunkFloats + (r & 31);
             if (SKL) {
                 col[k * 32] = v;
-            } else if (flag && a.zero_is_missing) {
-                col[k * 32] = (x != x) ? 0.f : v;       // a missing flag of a CSR-fed booster is an absent one
+            } else if (flag) {
+                // 0/1 flags have no B view: a missing flag of a CSR-fed booster is an absent one (the host entry points
+                // reject NaN flags for the dense-fed boosters)
+                col[k * 32] = (x != x) ? 0.f : v;
             } else {
                 // xgboost: NaN is missing, and so is an exact zero for the CSR-fed boosters -> A view -inf (default-left
-                // nodes), B view +inf (default-right nodes); rows of the B views follow the 17 numerics
+                // nodes), B view +inf (default-right nodes); the B views follow the 17 numerics in the order of the non-flags
+                int nb = kNumMax;
+                for (int q = 0; q < k; ++q) nb += !(q == 3 || q == 12 || q == 13 || q == 14 || q == 16);
                 const bool miss = (x != x) || (a.zero_is_missing && v == 0.f);
                 col[k * 32] = miss ? -inf : v;
-                col[(kNumMax + k) * 32] = miss ? inf : v;
+                col[nb * 32] = miss ? inf : v;
             }
         }
         __syncthreads();
@@ -992,13 +996,27 @@ extern "C" int fmc_tree_predict(fmc_ctx *c, int32_t id, const double *rows_dev, 
     return FMC_OK;
 }
 
+// NaN inputs: xgboost treats them as missing (the node's default branch), which the predict kernel honours for every
+// numeric that has a B view; scikit-learn's Pipeline.predict raises on them.
+static int check_nan_rows(const HostForest &f, const double *rows, int64_t n, const char *who) {
+    const bool skl = f.kind == FMC_KIND_SKL, dense_xgb = !skl && !f.zero_is_missing;
+    if (!skl && !dense_xgb) return FMC_OK;
+    for (int64_t i = 0; i < n; ++i)
+        for (int k = 0; k < f.n_num && k < kNumMax; ++k) {
+            const double x = rows[i * kNumMax + k];
+            if (x == x) continue;
+            if (skl) return fail(FMC_ERR_INVALID, std::string(who) + ": Input X contains NaN (scikit-learn model)");
+            if (k == 3 || k == 12 || k == 13 || k == 14 || k == 16)
+                return fail(FMC_ERR_INVALID, std::string(who) + ": NaN in a 0/1 flag column of a dense-fed booster is not supported");
+        }
+    return FMC_OK;
+}
+
 extern "C" int fmc_tree_predict_host(fmc_ctx *c, int32_t id, const double *rows_host, int64_t n, double *out_host,
                                      int32_t tree_begin, int32_t tree_end, int32_t coach_col) {
     if (!c || id < 0 || id >= FMC_N_MODELS || !c->forest[id].loaded) return fail(FMC_ERR_INVALID, "fmc_tree_predict_host: model not loaded");
     if (n <= 0) return FMC_OK;
-    if (c->forest[id].kind == FMC_KIND_SKL)      // Pipeline.predict raises on NaN input ("Input X contains NaN")
-        for (int64_t i = 0; i < n * kNumMax; ++i)
-            if (rows_host[i] != rows_host[i]) return fail(FMC_ERR_INVALID, "fmc_tree_predict_host: Input X contains NaN (scikit-learn model)");
+    if (int rc_nan = check_nan_rows(c->forest[id], rows_host, n, "fmc_tree_predict_host")) return rc_nan;
     CK(cudaSetDevice(c->device));
     const int no = c->forest[id].n_outputs;
     double *d_rows = nullptr, *d_out = nullptr;
@@ -1029,9 +1047,7 @@ extern "C" int fmc_tree_predict_cols_host(fmc_ctx *c, int32_t id, const double *
     CK(cudaSetDevice(c->device));
     HostForest &f = c->forest[id];
     prescale(f);
-    if (f.kind == FMC_KIND_SKL)
-        for (int64_t i = 0; i < n * kNumMax; ++i)
-            if (rows_host[i] != rows_host[i]) return fail(FMC_ERR_INVALID, "fmc_tree_predict_cols_host: Input X contains NaN (scikit-learn model)");
+    if (int rc_nan = check_nan_rows(f, rows_host, n, "fmc_tree_predict_cols_host")) return rc_nan;
     for (int64_t i = 0; i < 2 * n; ++i)
         if (hot_cols_host[i] < -1 || hot_cols_host[i] >= f.n_features || (hot_cols_host[i] >= f.num_base && hot_cols_host[i] < f.num_base + f.n_num))
             return fail(FMC_ERR_INVALID, "fmc_tree_predict_cols_host: a hot column must be -1 or a one-hot column of the model");

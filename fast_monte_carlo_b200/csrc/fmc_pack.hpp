@@ -160,8 +160,8 @@ struct PackedForest {
 // 13 fourth_and_short 14 fg_range 15 half 16 two_minute
 constexpr int kSimNinfRow = 14;   // 11 varying numerics + B views of distance, yardsToGoal, score_diff, then -inf
 constexpr int kSimRows = 15;
-constexpr int kPredNinfRow = 34;  // 17 numerics + their 17 B views, then -inf
-constexpr int kPredRows = 35;
+constexpr int kPredNinfRow = 29;  // 17 numerics + the B views of the 12 that are not flags, then -inf (the slot format
+constexpr int kPredRows = 30;     // addresses at most 32 feature rows)
 
 inline void preset_sim(PackSpec &s) {
     const int8_t row[kNumMax] = {0, 1, 2, 3, 4, 5, -1, -1, -1, -1, -1, -1, 6, 7, 8, 9, 10};
@@ -173,10 +173,11 @@ inline void preset_sim(PackSpec &s) {
 }
 inline void preset_predict(PackSpec &s) {
     const uint8_t fl[kNumMax] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 0, 1};
+    int nb = kNumMax;
     for (int k = 0; k < kNumMax; ++k) {
         s.row[k] = (int8_t)k;
         s.is_flag[k] = fl[k];
-        s.row_b[k] = (int8_t)(kNumMax + k);
+        s.row_b[k] = fl[k] ? -1 : (int8_t)nb++;
     }
     s.fold_mask = 0;
     s.ninf_row = kPredNinfRow;

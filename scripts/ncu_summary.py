@@ -1,6 +1,9 @@
 """Summarise an .ncu-rep (raw + source pages) -> JSON + text.
 
-    python scripts/ncu_summary.py rep out_prefix [games_in_profiled_launch] [launch_index]
+    python scripts/ncu_summary.py rep out_prefix [games_in_profiled_launch] [launch_index] [warp_steps]
+
+`warp_steps`: FMC_C_WARP_STEPS / fmc_predict_stats of the same launch run without ncu (scripts/quick_bench.py prints
+it): warp-level node gathers of the tree walk; with it the summary carries the kernel's L1 wavefronts per gather level.
 
 bench.py reads the JSON: `dram_bytes_per_launch` / `games_in_profiled_launch` scale `roofline.traffic`, and
 `derived.lgds_wavefronts_per_global_ld_request` (L1 data-pipe wavefronts one warp-level node gather costs) turns the
@@ -50,6 +53,11 @@ if wf_lgds and req:
     derived["lgds_wavefronts_per_global_ld_request"] = wf_lgds / req
 if sec and req:
     derived["sectors_per_global_ld_request"] = sec / req
+if wf is not None and len(sys.argv) > 5 and float(sys.argv[5]) > 0:
+    derived["warp_steps_in_profiled_launch"] = float(sys.argv[5])
+    # every L1 data-pipe wavefront of the kernel (feature LDS + node gather of the walk, root / constant streams, and the
+    # state machine's own shared-memory traffic) per warp-level gather level of the walk
+    derived["l1_wavefronts_per_warp_step"] = wf / float(sys.argv[5])
 if wf is not None:
     derived["l1_data_pipe_wavefronts"] = wf
     derived["l1_data_pipe_wavefronts_mem_lgds"] = wf_lgds

@@ -70,6 +70,10 @@ __device__ __forceinline__ void step4(uint32_t &n, uint32_t fcol, uint32_t wl, u
     asm("{.reg .u64 ad; mov.b64 ad, {%1, %2}; ld.global.nc.u32 %0, [ad];}" : "=r"(n) : "r"(a), "r"(wh));
 }
 // trees: depth D complete trees; tree t occupies nodes [t*(2^(D+1)) ...]; children of node i (heap order within tree, BFS) adjacent
+// COHERENCE experiment (round 2): production lanes of a warp are not random -- requests of one (family, orientation)
+// share most of their feature values (down 1..4, flags, similar clocks), so the lanes of a warp sit on the same few
+// nodes of a tree level.  g_coh = percentage of lanes whose feature values are the warp's common ones.
+__device__ int g_coh = 0;
 template <int MODE>
 __global__ void __launch_bounds__(1024, 1) k(const void *tbl, int n_trees, int depth, int iters, unsigned *sink, int tree_stride) {
     extern __shared__ __align__(4096) uint32_t rows[];   // 32 warps x 16 rows x 32 lanes
@@ -77,6 +81,11 @@ __global__ void __launch_bounds__(1024, 1) k(const void *tbl, int n_trees, int d
     for (int r = 0; r < kRows; ++r) {
         uint32_t h = (tid * 2654435761u) ^ (r * 40503u) ^ (blockIdx.x * 97u);
         h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+        uint32_t hw = ((uint32_t)(warp + 1) * 2654435761u) ^ (r * 40503u) ^ (blockIdx.x * 97u);     // the warp's common value
+        hw ^= hw >> 15; hw *= 2246822519u; hw ^= hw >> 13;
+        uint32_t hs = (tid * 374761393u) ^ (blockIdx.x * 668265263u);                               // does this lane follow it?
+        hs ^= hs >> 13; hs *= 1274126177u; hs ^= hs >> 16;
+        if ((int)(hs % 100u) < g_coh) h = hw;
         if (MODE == 8) rows[(warp * kRows + r) * 32 + lane] = __float_as_uint((float)(h & 1023));
         else rows[(warp * kRows + r) * 32 + lane] = ((uint32_t)r << 28) | ((h & 1023) << 16);
     }
@@ -141,6 +150,21 @@ int main() {
     cudaMemcpy(a4, t4.data(), t4.size() * 4, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(k<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536); cudaFuncSetAttribute(k<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int coh : {0, 75, 95, 100}) {
+        cudaMemcpyToSymbol(g_coh, &coh, sizeof(int));
+        for (int depth : {3, 6})
+            for (int mode : {8, 4, 8, 4}) {
+                const int iters = 2000;
+                cudaEventRecord(e0);
+                if (mode == 8) k<8><<<148, 1024, 65536>>>(a8, n_trees, depth, iters, sink, stride);
+                else k<4><<<148, 1024, 65536>>>(a4, n4, depth, iters, sink, stride);
+                cudaEventRecord(e1); cudaEventSynchronize(e1);
+                float ms; cudaEventElapsedTime(&ms, e0, e1);
+                printf("coherent lanes %3d%% depth %d mode %dB: %.2f ms  %.3e lane-steps/s  err=%s\n", coh, depth, mode, ms,
+                       148.0 * 1024 * iters * 8.0 * depth / ms * 1e3, cudaGetErrorString(cudaGetLastError()));
+            }
+    }
+    { const int zero = 0; cudaMemcpyToSymbol(g_coh, &zero, sizeof(int)); }
     for (int depth : {3, 6}) {
         for (int mode : {8, 4, 8, 4}) {
             const int iters = 2000;

@@ -29,9 +29,9 @@ def sim_rows(num17, zero_missing, scaler=None):
 
 
 def predict_rows(num17, zero_missing, scaler=None, xgb=True):
-    """[n,35] float32 feature rows of the predict preset: 17 numerics (A views), their 17 B views, row 34 = -inf.
-    xgboost forests: a NaN (and, for the CSR-fed boosters, an exact zero) is missing -> A view -inf, B view +inf;
-    a missing flag of a CSR-fed booster is an absent one (0)."""
+    """[n,30] float32 feature rows of the predict preset: 17 numerics (A views), the B views of the 12 non-flags,
+    row 29 = -inf.  xgboost forests: a NaN (and, for the CSR-fed boosters, an exact zero) is missing -> A view -inf,
+    B view +inf; a missing flag is an absent one (0)."""
     n = num17.shape[0]
     x = np.array(num17, dtype=np.float64, copy=True)
     if scaler is not None:
@@ -40,17 +40,19 @@ def predict_rows(num17, zero_missing, scaler=None, xgb=True):
             x[:, k] = (x[:, k] - mean[j]) / scale[j]
     v = np.zeros((n, 17), dtype=np.float32)
     v[:, :x.shape[1]] = x.astype(np.float32)
-    rows = np.zeros((n, 35), dtype=np.float32)
+    rows = np.zeros((n, 30), dtype=np.float32)
     rows[:, :17] = v
     if xgb:
+        nb = 17
         for k in range(17):
-            if k in FLAGS and zero_missing:
+            if k in FLAGS:
                 rows[:, k] = np.where(np.isnan(v[:, k]), 0.0, v[:, k])
                 continue
             z = np.isnan(v[:, k]) | ((v[:, k] == 0) if zero_missing else False)
             rows[:, k] = np.where(z, -np.inf, v[:, k])
-            rows[:, 17 + k] = np.where(z, np.inf, v[:, k])
-    rows[:, 34] = -np.inf
+            rows[:, nb] = np.where(z, np.inf, v[:, k])
+            nb += 1
+    rows[:, 29] = -np.inf
     return rows
 
 

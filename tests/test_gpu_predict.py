@@ -77,6 +77,35 @@ def test_per_row_names_all_golden_rows(engine, oracle, models_s2):
     assert np.array_equal(engine.predict("pass_stage1", rows, names=names), oracle.predict("pass_stage1", rows, cols, 1))
 
 
+def test_nan_is_missing_for_xgboost(engine, oracle, models_s2):
+    """Booster.predict on a DataFrame row treats NaN as missing (the node's default branch): honoured for every numeric
+    that is not a 0/1 flag; scikit-learn pipelines raise on NaN."""
+    from fast_monte_carlo_b200.native import FmcError
+    rng = np.random.default_rng(4)
+    for name in ("pass_stage1", "pass_stage2", "run_fumble", "play_model"):
+        f = models_s2[name]
+        rows = _rows(4000, 31)
+        nonflag = [k for k in range(f.n_num) if k not in (3, 12, 13, 14, 16)]
+        mask = rng.random((rows.shape[0], len(nonflag))) < 0.15
+        sub = rows[:, nonflag]
+        sub[mask] = np.nan
+        rows[:, nonflag] = sub
+        cols = ([g.column_of("Unknown") for g in f.groups if g.name != "coach"] + [-1, -1])[:2]
+        ref = _oracle_margins(oracle, f, name, rows, cols)
+        got = engine.predict(name, rows[:, :f.n_num])
+        assert np.array_equal(got, ref), name
+        clean = _oracle_margins(oracle, f, name, np.nan_to_num(rows, nan=1.0), cols)
+        assert not np.array_equal(ref, clean)                  # the NaNs did take other branches
+    bad = _rows(8, 1)
+    bad[3, 2] = np.nan
+    with pytest.raises(FmcError, match="NaN"):
+        engine.predict("pass_yards", bad)
+    bad = _rows(8, 1)
+    bad[2, 3] = np.nan                                         # is_red_zone of the dense-fed play model
+    with pytest.raises(FmcError, match="flag"):
+        engine.predict("play_model", bad[:, :12])
+
+
 def test_named_players_and_tree_ranges(engine, oracle, models_s2):
     """Real one-hot columns (fmc_set_active_columns) and iteration_range (sim_helpers.py:22-23)."""
     p = json.load(open(os.path.join(GOLDEN, "xgb_provisional.json")))

@@ -44,7 +44,7 @@ def test_predict_preset(models_s2, native_lib, name):
     f, cols, skl, zm, scaler = _setup(models_s2, name)
     num = _rows(96, 1)[:, :f.n_num]
     slots, stream, consts, meta = native.pack_forest_host(f, mode=1, cols=cols)
-    got = pw.walk(slots, stream, consts, meta, pw.predict_rows(num, zm, scaler), skl, f.base_margin)
+    got = pw.walk(slots, stream, consts, meta, pw.predict_rows(num, zm, scaler, xgb=not skl), skl, f.base_margin)
     x = to.play_model_features(f, num) if scaler else num
     ref = to.raw_margin(f, x, np.tile(np.array(cols), (num.shape[0], 1)))
     assert np.array_equal(got, ref)
@@ -76,7 +76,7 @@ def test_tree_range_and_named_player(models_s2, native_lib):
     num = _rows(40, 3)
     slots, stream, consts, meta = native.pack_forest_host(f, mode=1, cols=(col, -1), tree_begin=0, tree_end=68)
     assert meta["rounds"] == 68
-    got = pw.walk(slots, stream, consts, meta, pw.predict_rows(num, zm, None), skl, f.base_margin)
+    got = pw.walk(slots, stream, consts, meta, pw.predict_rows(num, zm, None, xgb=not skl), skl, f.base_margin)
     ref = to.raw_margin(f, num, np.tile(np.array([col, -1]), (40, 1)), 0, 68)
     assert np.array_equal(got, ref)
 

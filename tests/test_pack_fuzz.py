@@ -63,7 +63,7 @@ def _check(f, mode, rows, cols, fold=None, tb=0, te=-1):
     skl = f.kind == art.KIND_SKL
     zm = bool(f.zero_is_missing) and not skl
     slots, stream, consts, meta = native.pack_forest_host(f, mode=mode, cols=cols, fold_values=fold, tree_begin=tb, tree_end=te)
-    feats = pw.sim_rows(rows, zm) if mode == 0 else pw.predict_rows(rows, zm)
+    feats = pw.sim_rows(rows, zm) if mode == 0 else pw.predict_rows(rows, zm, xgb=not skl)
     got = pw.walk(slots, stream, consts, meta, feats, skl, f.base_margin)
     act = np.tile(np.array([cols[0]]), (rows.shape[0], 1))
     ref = to.raw_margin(f, rows, act, tb, f.n_trees if te < 0 else te)
