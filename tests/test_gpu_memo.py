@@ -65,21 +65,21 @@ def test_persistent_memo_and_table_change(models_s2, oracle):
         b = e.simulate_host(11, want_iters=True)
         assert np.array_equal(a["scores"], b["scores"]) and np.array_equal(a["iters"], b["iters"])
         assert b["counters"]["memo_hits"] > a["counters"]["memo_hits"]
-        assert b["counters"]["memo_hits"] > 0.97 * b["counters"]["memo_probes"]      # direct mapped: a few conflicts
+        assert b["counters"]["memo_hits"] > 0.85 * b["counters"]["memo_probes"]      # direct mapped: later inserts overwrite a fifth of the entries
         c = e.simulate_host(12)                      # another seed on the warm table
         ref = oracle.simulate(oracle.make_config(models_s2, KSU, ISU, stage2="booster"), 4000, seed=12)
         assert np.array_equal(c["scores"][:4000], ref["scores"])
         # the same ranges again through set_matchups: tables (and the memo) are kept
         e.set_matchups([MatchupSpec("A", "B", KSU, ISU, n, 0, n, 0)])
         d = e.simulate_host(11)
-        assert np.array_equal(d["scores"], a["scores"]) and d["counters"]["memo_hits"] > 0.97 * d["counters"]["memo_probes"]
+        assert np.array_equal(d["scores"], a["scores"]) and d["counters"]["memo_hits"] > 0.85 * d["counters"]["memo_probes"]
         # another pair: new tables, the old entries must not be served
         other = ((0.0, 28.0, 27.5), (31.7, 41.9, 10.1))
         e.set_matchups([MatchupSpec("C", "D", other[0], other[1], n, 0, n, 0)])
         g = e.simulate_host(11)
         ref = oracle.simulate(oracle.make_config(models_s2, other[0], other[1], stage2="booster"), 4000, seed=11)
         assert np.array_equal(g["scores"][:4000], ref["scores"])
-        assert g["counters"]["memo_hits"] < 0.9 * g["counters"]["memo_probes"]
+        assert g["counters"]["memo_hits"] < 0.8 * g["counters"]["memo_probes"]
     finally:
         e.close()
 
