@@ -50,6 +50,9 @@ def parse():
                          "--slate-games games each, sharded over the GPUs by contiguous game-id ranges (strong scaling); "
                          "season = configs[4]: 12 weekly slates of 60 matchups from seeded shuffles of the 136 teams")
     ap.add_argument("--slate-games", type=int, default=1_000_000, help="games per matchup of the slate workload")
+    ap.add_argument("--shard", default="matchups", choices=["games", "matchups"],
+                    help="slate / season under several GPUs: whole matchups per rank (default; keeps a matchup's memo on one "
+                         "GPU) or a game-id slice of every matchup per rank")
     ap.add_argument("--stage2", default="synthetic", choices=["synthetic", "standin"])
     ap.add_argument("--players", action="store_true",
                     help="matchup workload in player mode: usage tables from the synthetic focus sheet "
@@ -92,8 +95,8 @@ def workload(args, n_gpus):
     if args.workload == "season":
         return {
             "workload": "configs[4]: season slate, 12 weeks x 60 matchups (seeded shuffles of the 136 teams of "
-                        f"PregameSPPlus2025_1) x {args.slate_games:,} simulated games each, contiguous game-id shards "
-                        f"over {n_gpus} GPU(s), Philox seed {SEED}",
+                        f"PregameSPPlus2025_1) x {args.slate_games:,} simulated games each, sharded over {n_gpus} GPU(s) by "
+                        f"{args.shard}, Philox seed {SEED}",
             "total_games_per_step": 720 * args.slate_games,
             "play_call": "pass_prob_v1 heuristic (reference behaviour when play_model.json is absent)",
             "stage2": ("synthetic booster of the trained shape (1086 trees, depth<=7)" if args.stage2 == "synthetic"
@@ -106,7 +109,7 @@ def workload(args, n_gpus):
     if args.workload == "slate":
         return {
             "workload": "configs[3]: full-slate run, 60 matchups (first 120 teams of PregameSPPlus2025_1 paired) x "
-                        f"{args.slate_games:,} simulated games each, contiguous game-id shards over {n_gpus} GPU(s), "
+                        f"{args.slate_games:,} simulated games each, sharded over {n_gpus} GPU(s) by {args.shard}, "
                         f"Philox seed {SEED}",
             "total_games_per_step": 60 * args.slate_games,
             "play_call": "pass_prob_v1 heuristic (reference behaviour when play_model.json is absent)",
@@ -447,7 +450,7 @@ def run_ours(args):
     eng = Engine(ms, device=local, stage2="booster" if args.stage2 == "synthetic" else "standin", memo=args.memo)
     if args.workload in ("slate", "season"):
         pairs, sp_df = slate_pairs() if args.workload == "slate" else season_pairs()
-        spec = api.slate_specs(pairs, args.slate_games, sp_df, rank, world)
+        spec = api.slate_specs(pairs, args.slate_games, sp_df, rank, world, shard=args.shard)
         G = sum(m.game_end - m.game_begin for m in spec)          # this rank's games per step
         total_games = len(pairs) * args.slate_games
     else:

@@ -194,14 +194,24 @@ def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
 
 
 def slate_specs(pairs: Sequence[Tuple[str, str]], games_per_matchup: int, sp_df: pd.DataFrame,
-                rank: int = 0, world: int = 1) -> List[MatchupSpec]:
-    """Every rank simulates its contiguous game-id slice of every matchup.  Results do not depend
-    on `world`: the Philox key is (seed, matchup, game id)."""
+                rank: int = 0, world: int = 1, shard: str = "games") -> List[MatchupSpec]:
+    """The matchup list of one rank.  Results do not depend on `world` or `shard`: the Philox key is (seed, matchup,
+    game id) and the ranks' integer histograms add up (`merge_histograms`).
+      shard="games":    every rank simulates its contiguous game-id slice of every matchup (FMC:1321-1328 treats a pair
+                        of games as the unit of work);
+      shard="matchups": rank r simulates all games of matchups r, r + world, ... and none of the others (their ranges are
+                        empty) -- a matchup's node tables and its memo entries then live on one GPU only, which keeps the
+                        memo's hit rate at that of an unsharded matchup."""
+    if shard not in ("games", "matchups"):
+        raise ValueError("shard must be 'games' or 'matchups'")
     specs = []
     off = 0
-    for a, b in pairs:
+    for i, (a, b) in enumerate(pairs):
         spa, spb = lookup_sp_flex(a, sp_df), lookup_sp_flex(b, sp_df)
-        g0, g1 = shard_range(int(games_per_matchup), rank, world)
+        if shard == "games":
+            g0, g1 = shard_range(int(games_per_matchup), rank, world)
+        else:
+            g0, g1 = (0, int(games_per_matchup)) if i % world == rank else (0, 0)
         specs.append(MatchupSpec(a, b, spa, spb, int(games_per_matchup), g0, g1, off))
         off += g1 - g0
     return specs

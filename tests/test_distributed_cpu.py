@@ -31,7 +31,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, games, q):
+def _worker(rank, world, port, games, q, shard="games"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -40,11 +40,13 @@ def _worker(rank, world, port, games, q):
     ms = art.load_default_models()
     co.load_models(ms)
     sp = priors.load_sp_flex(priors.packaged_priors_path())
-    pairs = [("Kansas State", "Iowa State"), ("UTSA", "Ohio State")]
-    specs = api.slate_specs(pairs, games, sp, rank, world)
+    pairs = [("Kansas State", "Iowa State"), ("UTSA", "Ohio State"), ("Iowa State", "UTSA")]
+    specs = api.slate_specs(pairs, games, sp, rank, world, shard=shard)
     hist = torch.zeros((len(pairs), 2, outputs.HIST_BINS, outputs.HIST_BINS), dtype=torch.int64)
     counters = torch.zeros(4, dtype=torch.int64)
     for m, s in enumerate(specs):
+        if s.game_end == s.game_begin:
+            continue                     # shard="matchups": this rank does not own the matchup
         cfg = co.make_config(ms, s.sp_a, s.sp_b)
         r = co.simulate(cfg, s.game_end - s.game_begin, game0=s.game_begin, matchup=m, seed=99, threads=1)
         hist[m] += torch.from_numpy(outputs.histogram_from_scores(r["scores"], s.game_begin))
@@ -62,10 +64,11 @@ def test_two_rank_histogram_merge_equals_single_process():
     games = 300
     ctx = mp.get_context("spawn")
     results = {}
-    for world in (1, 2):
+    for world, shard in ((1, "games"), (2, "games"), ("2m", "matchups")):
+        n = 2 if world == "2m" else world
         q = ctx.SimpleQueue()
         port = _free_port()
-        procs = [ctx.Process(target=_worker, args=(r, world, port, games, q)) for r in range(world)]
+        procs = [ctx.Process(target=_worker, args=(r, n, port, games, q, shard)) for r in range(n)]
         for p in procs:
             p.start()
         results[world] = q.get()
@@ -74,8 +77,10 @@ def test_two_rank_histogram_merge_equals_single_process():
             assert p.exitcode == 0
     h1, c1 = results[1]
     h2, c2 = results[2]
+    h3, c3 = results["2m"]               # whole matchups per rank instead of game slices
     assert np.array_equal(h1, h2) and np.array_equal(c1, c2)
-    assert h1.sum() == 2 * games and c1[0] == 2 * games
+    assert np.array_equal(h1, h3) and np.array_equal(c1, c3)
+    assert h1.sum() == 3 * games and c1[0] == 3 * games
 
 
 def _players_worker(rank, world, port, games, q):
