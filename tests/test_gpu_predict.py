@@ -70,11 +70,12 @@ def test_per_row_names_all_golden_rows(engine, oracle, models_s2):
         got = engine.predict(name, rows[:, :f.n_num], hot_cols=cols)
         assert np.array_equal(got, ref), name
     # by name, through the category lists
-    f = models_s2["pass_stage1"]
+    f = models_s2["pass_yards"]                                    # passer_name + target_name
     rows = _rows(64, 3)
-    names = [("Caleb Williams", "Unknown") if i % 2 else ("nobody at all", None) for i in range(64)]
+    names = [("Adrian Martinez", "Aaron Anderson") if i % 2 else ("nobody at all", None) for i in range(64)]
     cols = np.array([[f.groups[0].column_of(a), f.groups[1].column_of(b)] for a, b in names], dtype=np.int32)
-    assert np.array_equal(engine.predict("pass_stage1", rows, names=names), oracle.predict("pass_stage1", rows, cols, 1))
+    assert cols.max() > 0 and cols.min() == -1
+    assert np.array_equal(engine.predict("pass_yards", rows, names=names), oracle.predict("pass_yards", rows, cols, 3))
 
 
 def test_nan_is_missing_for_xgboost(engine, oracle, models_s2):
