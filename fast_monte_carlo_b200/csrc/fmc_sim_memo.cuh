@@ -37,6 +37,36 @@ __device__ __forceinline__ int stage_family(int stage) {      // ST_WAIT_* -> mo
 static_assert(ST_WAIT_S2 == ST_WAIT_S1 + 1 && ST_WAIT_PQ == ST_WAIT_S1 + 2 && ST_WAIT_RQ == ST_WAIT_S1 + 3 && ST_WAIT_SQ == ST_WAIT_S1 + 4,
               "stage_family assumes consecutive wait stages");
 
+// Out-of-line copies of the pure scalar helpers for the trip loop: its code is several times the instruction cache that
+// 32 warps at different stages share (ncu: `stall_no_instruction` is the top stall of this kernel, 7.4 per issue), so the
+// helpers that are called from one or two places each are kept out of the loop body (FMC_MEMO_OUTLINE=1; measured 14 % SLOWER than inlining them -- 447 vs 393 ms at 4 M games: the calls cost more than the cache misses they save -- so the default keeps them inline).
+#ifndef FMC_MEMO_OUTLINE
+#define FMC_MEMO_OUTLINE 0
+#endif
+#if FMC_MEMO_OUTLINE
+#define FMC_MEMO_HELPER __device__ __noinline__
+#else
+#define FMC_MEMO_HELPER __device__ __forceinline__
+#endif
+FMC_MEMO_HELPER double m_pass_prob_v1(int down, double distance, double ytg, int sec, int sd) { return pass_prob_v1(down, distance, ytg, sec, sd); }
+FMC_MEMO_HELPER double m_go_for_it_prob(double ytg, double dist, int sd, int sec) { return go_for_it_prob(ytg, dist, sd, sec); }
+FMC_MEMO_HELPER int m_stage2_outcome(double r0, double r1, double r2, double u2) { const double raw[3] = {r0, r1, r2}; return stage2_outcome(raw, u2); }
+FMC_MEMO_HELPER double m_rz_finish_prob(double ytg, double tanh35, int down, bool pass) { return rz_finish_prob(ytg, tanh35, down, pass); }
+FMC_MEMO_HELPER double m_call_cut(double p_pass) {       // FMC:1064-1066: P(run) after the two normalisations of the play call
+    double a0 = 1.0 - p_pass, a1 = p_pass;
+    const double s = a0 + a1;
+    a0 = a0 / s; a1 = a1 / s;
+    return a0 / (a0 + a1);
+}
+FMC_MEMO_HELPER unsigned long long m_memo_key_xgb(const RankSpec *rs, int fam, int team, int matchup, int down, double dist, double ytg,
+                                                  int sd, int sec, float v1, float v2) {
+    return memo_key<true>(rs, fam, team, matchup, down, dist, ytg, sd, sec, v1, v2);
+}
+FMC_MEMO_HELPER unsigned long long m_memo_key_skl(const RankSpec *rs, int fam, int team, int matchup, int down, double dist, double ytg,
+                                                  int sd, int sec, float v1, float v2) {
+    return memo_key<false>(rs, fam, team, matchup, down, dist, ytg, sd, sec, v1, v2);
+}
+
 // Key of the request (family, team on offense) a lane is about to post.  The feature values are formed exactly as
 // write_features forms them (same float conversions, same play-model standardisation).
 template <bool XGB>
@@ -48,7 +78,8 @@ __device__ __forceinline__ unsigned long long lane_memo_key(const RankSpec *rs, 
         if (a.pm_scaled[1]) v1 = (float)((L.dist - a.pm_mean[1]) / a.pm_scale[1]);
         if (a.pm_scaled[2]) v2 = (float)((L.ytg - a.pm_mean[2]) / a.pm_scale[2]);
     }
-    return memo_key<XGB>(rs, fam, team, matchup, L.down, L.dist, L.ytg, sd, L.sec, v1, v2);
+    return XGB ? m_memo_key_xgb(rs, fam, team, matchup, L.down, L.dist, L.ytg, sd, L.sec, v1, v2)
+               : m_memo_key_skl(rs, fam, team, matchup, L.down, L.dist, L.ytg, sd, L.sec, v1, v2);
 }
 
 __device__ __forceinline__ unsigned long long memo_slot_addr(const MemoRegion &R, unsigned long long key) {
@@ -280,7 +311,7 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                     bool play = true;
                     if (L.down == 4) {
                         const double ytg = L.ytg, dist = L.dist;
-                        const double p_go = pymin(1.0, go_for_it_prob(ytg, dist, sd, L.sec) * 1.15);
+                        const double p_go = pymin(1.0, m_go_for_it_prob(ytg, dist, sd, L.sec) * 1.15);
                         if (D.u(S_U_GO) < p_go) {
                             L.going = 1;
                             ev.hit(EV_GO);
@@ -311,11 +342,7 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                         L.plays += 1;
                         if (a.policy == 1) L.stage = ST_WAIT_PM;
                         else {
-                            const double p_pass = pass_prob_v1(L.down, L.dist, L.ytg, L.sec, sd);
-                            double a0 = 1.0 - p_pass, a1 = p_pass;
-                            const double s = a0 + a1;
-                            a0 = a0 / s; a1 = a1 / s;
-                            const double c0 = a0 / (a0 + a1);
+                            const double c0 = m_call_cut(m_pass_prob_v1(L.down, L.dist, L.ytg, L.sec, sd));
                             if (D.u(S_U_CALL) < c0) { ev.hit(EV_RUN); L.stage = ST_WAIT_RQ; }
                             else { ev.hit(EV_PASS); L.stage = ST_WAIT_S1; }
                         }
@@ -342,11 +369,7 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                         mg[4] = __uint_as_float((uint32_t)r[2]); mg[5] = 0.f;
                         float e1, sum;
                         play_softmax(mg, M.tbl[5][team].n_outputs, a.pass_class, a.play_temp, e1, sum);
-                        const double p_pass = softclip((double)(e1 / sum), 0.02, 0.98);
-                        double a0 = 1.0 - p_pass, a1 = p_pass;
-                        const double s = a0 + a1;
-                        a0 = a0 / s; a1 = a1 / s;
-                        const double c0 = a0 / (a0 + a1);
+                        const double c0 = m_call_cut(softclip((double)(e1 / sum), 0.02, 0.98));
                         if (D.u(S_U_CALL) < c0) { ev.hit(EV_RUN); L.stage = ST_WAIT_RQ; }
                         else { ev.hit(EV_PASS); L.stage = ST_WAIT_S1; }
                         have = false;
@@ -407,7 +430,7 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                         raw[0] = a.standin[0]; raw[1] = a.standin[1]; raw[2] = a.standin[2];
                     }
                     have = false;
-                    const int outcome = stage2_outcome(raw, D.u(S_U_S2));
+                    const int outcome = m_stage2_outcome(raw[0], raw[1], raw[2], D.u(S_U_S2));
                     if (outcome == 0) {                                   // incomplete FMC:1160-1168
                         ev.hit(EV_INC);
                         L.down += 1; L.going = 0;
@@ -462,7 +485,7 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                             yards = pymin(yards, ytg0);
                         }
                         if (ytg0 <= (pass ? 12.0 : 9.0) && L.down <= 3) {
-                            if (D.u(S_U_FIN) < rz_finish_prob(ytg0, M.tanh35[team], L.down, pass)) yards = ytg0;
+                            if (D.u(S_U_FIN) < m_rz_finish_prob(ytg0, M.tanh35[team], L.down, pass)) yards = ytg0;
                         }
                         if (yards + 1e-9 >= ytg0) {
                             ev.hit(EV_TD);
