@@ -12,11 +12,7 @@
 #include <vector>
 
 #include "fmc_sim.cuh"
-#ifdef FMC_MEMO_DEFERRED      // experiment: rare stages deferred; not the shipped kernel
-#include "fmc_sim_memo_deferred.cuh"
-#else
 #include "fmc_sim_memo.cuh"
-#endif
 
 using namespace fmc;
 
