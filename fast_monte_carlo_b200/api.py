@@ -101,14 +101,19 @@ def simulate_matchup(teamA: TeamContext, teamB: TeamContext, n: int = 100, seed:
     if g1 - g0 <= 0:
         sims_df = pd.DataFrame(columns=["team", "opp", "pts", "opp_pts"])
     else:
-        with _ENGINE_LOCK:
-            # the sampled names feed the models whether or not the box is collected (FMC:1058-1081, 1203-1216)
-            eng.set_matchups([MatchupSpec(teamA.name, teamB.name, teamA.sp, teamB.sp, games, g0, g1, 0, usage=use)])
-            want_box = bool(collect_players) and eng.n_slots > 0
-            res = eng.simulate_host(_fresh_seed() if seed is None else int(seed), want_scores=True, want_hist=True,
-                                    want_players=want_box)
+        # the name columns of the result depend on the names and the game parity only: built while the GPU plays
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=1) as side:
+            names_f = side.submit(outputs.name_columns, teamA.name, teamB.name, g1 - g0, g0)
+            with _ENGINE_LOCK:
+                # the sampled names feed the models whether or not the box is collected (FMC:1058-1081, 1203-1216)
+                eng.set_matchups([MatchupSpec(teamA.name, teamB.name, teamA.sp, teamB.sp, games, g0, g1, 0, usage=use)])
+                want_box = bool(collect_players) and eng.n_slots > 0
+                res = eng.simulate_host(_fresh_seed() if seed is None else int(seed), want_scores=True, want_hist=True,
+                                        want_players=want_box)
+            names = names_f.result()
         box = res.get("players")
-        sims_df = outputs.sims_frame(teamA.name, teamB.name, res["scores"], first_game=g0)
+        sims_df = outputs.sims_frame(teamA.name, teamB.name, res["scores"], first_game=g0, names=names)
         sims_df.attrs["counters"] = dict(res["counters"])
         sims_df.attrs["hist"] = _Attached(res["hist"][0])
         LAST_RUN.clear()

@@ -67,15 +67,35 @@ def _alternating_names(first: str, second: str, n: int, pool=None, workers: int 
     return pa.LargeStringArray.from_buffers(n, pa.py_buffer(offsets), pa.py_buffer(data))
 
 
-def sims_frame(team_a: str, team_b: str, scores: np.ndarray, first_game: int = 0) -> pd.DataFrame:
+def name_columns(team_a: str, team_b: str, n: int, first_game: int = 0):
+    """The `team` / `opp` columns of `sims_frame` for games [first_game, first_game + n): they depend on the names and
+    the game parity only, so `api.simulate_matchup` builds them on a worker thread WHILE the kernel runs."""
+    n = int(n)
+    p = int(first_game) & 1
+    names = (team_a, team_b) if p == 0 else (team_b, team_a)
+    dt = pd.Series(["x"]).dtype        # what `pd.DataFrame(rows)` of the reference gives its name columns
+    if dt == object:
+        nm = np.array(names, dtype=object)
+        idx = np.arange(n) & 1
+        return nm[idx], nm[1 - idx]
+    pool, workers = _pool(n)
+    try:
+        team = pd.array(_alternating_names(names[0], names[1], n, pool, workers), dtype=dt)
+        other = pd.array(_alternating_names(names[1], names[0], n, pool, workers), dtype=dt)
+    finally:
+        if pool is not None:
+            pool.shutdown()
+    return team, other
+
+
+def sims_frame(team_a: str, team_b: str, scores: np.ndarray, first_game: int = 0, names=None) -> pd.DataFrame:
     """Per-game table with the reference's columns and row order (FMC:1501-1509): game g has the
     opening-kickoff receiver as `team`; even games are A-first, odd games B-first.  The two name columns have
     the dtype pandas infers for the reference's own lists of names; they are assembled from Arrow buffers and the
     point columns by strided copies, on a few threads (10 M rows: ~0.1 s instead of 2.5 s through 20 M Python
-    string objects)."""
+    string objects).  `names` = a `name_columns(...)` result computed ahead of time."""
     n = int(scores.shape[0])
     p = int(first_game) & 1
-    names = (team_a, team_b) if p == 0 else (team_b, team_a)
     pts = np.empty(n, dtype=np.int64)
     opp = np.empty(n, dtype=np.int64)
     pool, workers = _pool(n)
@@ -91,17 +111,10 @@ def sims_frame(team_a: str, team_b: str, scores: np.ndarray, first_game: int = 0
         else:
             for r in parts:
                 points(*r)
-        dt = pd.Series(["x"]).dtype        # what `pd.DataFrame(rows)` of the reference gives its name columns
-        if dt == object:
-            nm = np.array(names, dtype=object)
-            idx = np.arange(n) & 1
-            team, other = nm[idx], nm[1 - idx]
-        else:
-            team = pd.array(_alternating_names(names[0], names[1], n, pool, workers), dtype=dt)
-            other = pd.array(_alternating_names(names[1], names[0], n, pool, workers), dtype=dt)
     finally:
         if pool is not None:
             pool.shutdown()
+    team, other = names if names is not None else name_columns(team_a, team_b, n, first_game)
     return pd.DataFrame({"team": team, "opp": other, "pts": pts, "opp_pts": opp}, copy=False)
 
 
