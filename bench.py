@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: simulated plays/s (and games/s) of the play-by-play Monte Carlo engine.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--games G]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--games G] [--memo on|off]
 
 Workload (BASELINE.json configs[1]): Kansas State vs Iowa State from the 2025 week-1 SP+ priors,
 10,000,000 simulated games per GPU per step (weak scaling: rank r plays game ids
@@ -10,11 +10,17 @@ step).  Shipped model artifacts; the stage-2 booster the reference snapshot lack
 synthetic booster of the trained shape (fast_monte_carlo_b200/synth.py) so that the stage-2 tree
 work is NOT skipped.  One step = one launch of the persistent simulation kernel over the batch.
 
-Prints ONE JSON line (rank 0).  `value` = plays/s with everything resident in HBM (CUDA events on
-the launch stream); `e2e` = the same metric through the C-ABI host-buffer call
-(fmc_simulate_host: forest specialisation + upload, kernel, per-game score table + histogram copied
-back) timed with the host clock; `cpu_baseline` = the C oracle (a port of the reference's
-algorithm) on this box's host cores; `--impl reference` times that CPU port as its own arm.
+Prints ONE JSON line (rank 0):
+  value         plays/s with everything resident in HBM (CUDA events on the launch stream), the engine as shipped:
+                exact memo in front of the tree walk ON (`memo`: hit rate, requests still walked);
+  e2e           the same metric through the reference's Python entry point api.simulate_matchup (FMC:1467-1521) with
+                HOST buffers: kernel, per-game score words + histogram copied back, the 2n-row sims_df; host clock;
+  roofline      the tree walk, measured in the same run with the memo OFF (no tree work hidden): fraction of the L1
+                data-pipe peak (the bound of a gather over cache-resident node tables), with the SURVEY 8(d)
+                algorithmic-bytes figure, the gathered bytes against a warp-coherent gather probe, and DRAM traffic;
+  tree_eval     BASELINE configs[2]: predict_kernel on 2^26 synthetic states, same accounting;
+  cpu_baseline  the C oracle (a port of the reference's algorithm) on all host cores of this box, at every N.
+`--impl reference` times that CPU port as its own arm.  `--workload slate | season` = configs[3] / configs[4].
 """
 from __future__ import annotations
 
