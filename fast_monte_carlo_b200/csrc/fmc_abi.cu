@@ -220,7 +220,7 @@ struct fmc_ctx {
     RankSpec *d_specs = nullptr;
     std::vector<uint8_t> memo_ok;        // [n_matchups][kMemoFams][2] the forest's ranks fit the key
     std::vector<std::string> memo_why;   // why not, for diagnostics
-    int memo_mode = 1, memo_max_trips = 8, memo_break_parked = 16, memo_min_rare = 1, memo_min_s2 = 1, memo_break_waiting = kMemoThreads / 64;
+    int memo_mode = 1, memo_max_trips = 8, memo_break_parked = 16, memo_break_waiting = kMemoThreads / 64;
     uint64_t memo_max_bytes = 0;
     char *d_memo = nullptr;
     size_t memo_bytes = 0;
@@ -388,8 +388,6 @@ extern "C" int fmc_set_memo(fmc_ctx *c, int32_t mode, uint64_t max_bytes, int32_
     c->memo_max_trips = max_trips > 0 ? max_trips : 8;
     c->memo_break_parked = break_parked > 0 ? break_parked : 16;
     if (const char *e = std::getenv("FMC_MEMO_BREAK_WAITING")) { const int v = std::atoi(e); if (v > 0) c->memo_break_waiting = v; }
-    if (const char *e = std::getenv("FMC_MEMO_MIN_RARE")) { const int v = std::atoi(e); if (v > 0) c->memo_min_rare = v; }
-    if (const char *e = std::getenv("FMC_MEMO_MIN_S2")) { const int v = std::atoi(e); if (v > 0) c->memo_min_s2 = v; }
     c->memo_valid = false;
     return FMC_OK;
 }
@@ -814,8 +812,6 @@ extern "C" int fmc_simulate(fmc_ctx *c, const fmc_sim_args *g) {
         mm.max_trips = c->memo_max_trips;
         mm.break_parked = c->memo_break_parked;
         mm.break_waiting = c->memo_break_waiting;
-        mm.min_rare = c->memo_min_rare;
-        mm.min_s2 = c->memo_min_s2;
         c->memo_valid = bytes != 0;
         const int mgrid = c->prop.multiProcessorCount * kMemoCtasPerSm;
         if (test) sim_memo_kernel<true><<<mgrid, kMemoThreads, sim_memo_smem_bytes(), st>>>(a, mm);

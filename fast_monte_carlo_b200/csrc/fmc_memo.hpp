@@ -66,8 +66,6 @@ struct MemoArgs {
     int max_trips;                      // stage steps a warp may run per round
     int break_parked;                   // a warp leaves the trip loop once this many of its lanes wait for the walk (or are idle)
     int break_waiting;                  // ... or once this many warps of the CTA have left it
-    int min_rare, min_s2;               // lanes that must wait at a rare stage (fourth down, punt, interception, sack / stage 2)
-                                        // before the warp runs it (every fourth trip runs them all)
 };
 
 __host__ __device__ inline int memo_units(int fam) { return fam == 0 ? 1 : (fam == 1 ? 2 : 3); }

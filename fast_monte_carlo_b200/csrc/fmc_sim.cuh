@@ -101,9 +101,7 @@ struct SimKernelArgs {
 };
 
 enum Stage : int {
-    ST_NEED_GAME = 0, ST_ITER, ST_WAIT_PM, ST_WAIT_S1, ST_WAIT_S2, ST_WAIT_PQ, ST_WAIT_RQ, ST_WAIT_SQ, ST_IDLE,
-    // finer stages of the memo kernel's scheduler (fmc_sim_memo.cuh); all inside the iteration L.iter - 1
-    ST_FOURTH, ST_PUNT, ST_CALL, ST_INT
+    ST_NEED_GAME = 0, ST_ITER, ST_WAIT_PM, ST_WAIT_S1, ST_WAIT_S2, ST_WAIT_PQ, ST_WAIT_RQ, ST_WAIT_SQ, ST_IDLE
 };
 
 // slot ids of the 16-slot draw record
@@ -186,13 +184,6 @@ struct Draws {
         rec = (TEST && a.stream) ? a.stream + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_N_SLOTS
                                  : nullptr;
         ctr = make_uint4((uint32_t)L.game, (uint32_t)(L.game >> 32), (uint32_t)matchup, (uint32_t)L.iter << 2);
-        cur = -1;
-    }
-    // start over on the draw record of the iteration L.iter of L's game
-    __device__ __forceinline__ void restart(const SimKernelArgs &a_, const MatchupDev &M, const Lane &L) {
-        rec = (TEST && a_.stream) ? a_.stream + ((size_t)(M.out_offset + (L.game - M.game_begin)) * FMC_MAX_ITERS + (size_t)L.iter) * FMC_N_SLOTS
-                                  : nullptr;
-        ctr.x = (uint32_t)L.game; ctr.y = (uint32_t)(L.game >> 32); ctr.w = (uint32_t)L.iter << 2;
         cur = -1;
     }
     __device__ __forceinline__ uint32_t word(int slot) {
