@@ -402,7 +402,9 @@ extern "C" int fmc_set_matchups(fmc_ctx *c, int32_t n, const fmc_matchup *m) {
     bool same = !c->tables_dirty && (int)c->matchups.size() == n && c->d_matchups != nullptr;
     for (int i = 0; same && i < n; ++i)
         same = std::memcmp(c->matchups[i].sp, m[i].sp, sizeof(m[i].sp)) == 0 &&
-               c->matchups[i].coach_col[0] == m[i].coach_col[0] && c->matchups[i].coach_col[1] == m[i].coach_col[1];
+               c->matchups[i].coach_col[0] == m[i].coach_col[0] && c->matchups[i].coach_col[1] == m[i].coach_col[1] &&
+               // a matchup that had no games has no tables (build_tables skips it)
+               (c->matchups[i].game_end > c->matchups[i].game_begin || m[i].game_end == m[i].game_begin);
     if (same) {
         CK(cudaSetDevice(c->device));
         CK(cudaDeviceSynchronize());           // a launch in flight reads the ranges
@@ -516,10 +518,14 @@ static int build_tables(fmc_ctx *c) {
     // of hundreds of matchups is packed by all host threads
     struct Job { int matchup, off, fam; PackedForest pf; std::string err, memo_why; RankSpec spec; };
     std::vector<Job> jobs;
-    for (int i = 0; i < n; ++i)
+    for (int i = 0; i < n; ++i) {
+        // a matchup without games on this context (another rank owns it: api.slate_specs(shard="matchups")) is never
+        // selected by the kernels, so it needs no tables: a rank specialises only the forests it will walk
+        if (c->matchups[i].game_end == c->matchups[i].game_begin) continue;
         for (int off = 0; off < 2; ++off)
             for (int fam = 0; fam < kNumFam; ++fam)
                 if (family_needed(c, fam)) { jobs.emplace_back(); jobs.back().matchup = i; jobs.back().off = off; jobs.back().fam = fam; }
+    }
     auto run_job = [&](Job &j) {
         const fmc_matchup &mu = c->matchups[j.matchup];
         const int off = j.off, de = off ^ 1, fam = j.fam;
