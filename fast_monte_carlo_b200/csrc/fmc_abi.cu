@@ -232,6 +232,11 @@ struct fmc_ctx {
     // fmc_simulate_host: device scratch + pinned staging, kept between calls
     struct Scratch { void *dev = nullptr; size_t dev_bytes = 0; };
     Scratch scr[8];
+    // pinned staging of the large device -> host copies of fmc_simulate_host (two buffers: the DMA of one chunk overlaps
+    // the host copy of the previous one into the caller's pageable buffer)
+    void *pin[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev[2] = {nullptr, nullptr};
     // fmc_tree_predict: packed + uploaded tables are kept per (model, tree range, hot columns) until the model
     // or its columns change -- a stream of predict calls on the same model re-uses them
     struct PredEntry {
@@ -309,6 +314,8 @@ extern "C" void fmc_destroy(fmc_ctx *c) {
     cudaFree(c->d_matchups); cudaFree(c->d_next); cudaFree(c->d_box_scratch);
     cudaFree(c->d_specs); cudaFree(c->d_memo); cudaFree(c->d_pred_stats);
     for (auto &q : c->scr) cudaFree(q.dev);
+    for (int b = 0; b < 2; ++b) { if (c->pin[b]) cudaFreeHost(c->pin[b]); if (c->copy_ev[b]) cudaEventDestroy(c->copy_ev[b]); }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_done) cudaEventDestroy(c->ev_done);
     delete c;
 }
@@ -846,6 +853,36 @@ static cudaError_t scratch(fmc_ctx *c, int slot, size_t bytes, void **out) {
     return cudaSuccess;
 }
 
+// Device -> pageable host copy through the context's pinned staging buffers (large results only: the per-game score words,
+// the per-game player box); the device is idle when this runs (fmc_simulate_host synchronises first).
+static cudaError_t d2h_staged(fmc_ctx *c, void *dst, const void *src, size_t bytes) {
+    constexpr size_t kChunk = 8u << 20;
+    if (bytes <= kChunk) return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+    cudaError_t e;
+    for (int b = 0; b < 2; ++b) {
+        if (!c->pin[b] && (e = cudaHostAlloc(&c->pin[b], kChunk, cudaHostAllocDefault)) != cudaSuccess) { c->pin[b] = nullptr; cudaGetLastError(); return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost); }
+        if (!c->copy_ev[b] && (e = cudaEventCreateWithFlags(&c->copy_ev[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    if (!c->copy_stream && (e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    const size_t n = (bytes + kChunk - 1) / kChunk;
+    auto len = [&](size_t i) { return i + 1 < n ? kChunk : bytes - i * kChunk; };
+    auto issue = [&](size_t i) -> cudaError_t {
+        cudaError_t r = cudaMemcpyAsync(c->pin[i & 1], (const char *)src + i * kChunk, len(i), cudaMemcpyDeviceToHost, c->copy_stream);
+        return r != cudaSuccess ? r : cudaEventRecord(c->copy_ev[i & 1], c->copy_stream);
+    };
+    auto drain = [&](size_t i) -> cudaError_t {
+        cudaError_t r = cudaEventSynchronize(c->copy_ev[i & 1]);
+        if (r == cudaSuccess) std::memcpy((char *)dst + i * kChunk, c->pin[i & 1], len(i));
+        return r;
+    };
+    if ((e = issue(0)) != cudaSuccess) return e;
+    for (size_t i = 1; i < n; ++i) {
+        if ((e = issue(i)) != cudaSuccess) return e;          // buffer i & 1 was drained as chunk i - 2 in the previous turn
+        if ((e = drain(i - 1)) != cudaSuccess) return e;
+    }
+    return drain(n - 1);
+}
+
 static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, uint32_t *hist_host,
                               uint64_t *counters_host, const double *stream_host, double *trace_host,
                               uint16_t *iters_host, fmc_player_rec *players_host, uint32_t *player_hist_host) {
@@ -909,12 +946,12 @@ static int simulate_host_impl(fmc_ctx *c, uint64_t seed, uint32_t *scores_host, 
         rc = fmc_simulate(c, &g);
         if (rc) break;
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) { bail(e, "sim_kernel"); break; }
-        if (scores_host && games && (e = cudaMemcpy(scores_host, d_scores, games * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H scores"); break; }
+        if (scores_host && games && (e = d2h_staged(c, scores_host, d_scores, games * 4)) != cudaSuccess) { bail(e, "D2H scores"); break; }
         if (hist_host && (e = cudaMemcpy(hist_host, d_hist, hist_n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H hist"); break; }
         if (counters_host && (e = cudaMemcpy(counters_host, d_cnt, FMC_N_COUNTERS * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H counters"); break; }
         if (trace_host && games && (e = cudaMemcpy(trace_host, d_trace, games * FMC_MAX_ITERS * FMC_TRACE_COLS * 8, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H trace"); break; }
         if (iters_host && games && (e = cudaMemcpy(iters_host, d_iters, games * 2, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H iters"); break; }
-        if (d_players && (e = cudaMemcpy(players_host, d_players, players_n * sizeof(fmc_player_rec), cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H players"); break; }
+        if (d_players && (e = d2h_staged(c, players_host, d_players, players_n * sizeof(fmc_player_rec))) != cudaSuccess) { bail(e, "D2H players"); break; }
         if (d_phist && (e = cudaMemcpy(player_hist_host, d_phist, phist_n * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) { bail(e, "D2H player hist"); break; }
     } while (0);
     // big test-mode buffers (injected draws, traces: 46 KB per game) are not worth keeping
