@@ -607,7 +607,7 @@ def run_ours(args):
                 continue
             samples.append(float(tt[0]))
             plays_e2e += int(pp[0])
-        e2e = {"value": plays_e2e / sum(samples) if samples else None, "unit": UNIT, "h2d_bytes_per_step": 200 + 8 * n_m,
+        e2e = {"value": plays_e2e / sum(samples) if samples else None, "unit": UNIT, "h2d_bytes_per_step": table_bytes + 200 + 8 * n_m,
                "d2h_bytes_per_step": G * 4 + int(np.prod(hist.shape)) * 4 + native.N_COUNTERS * 8 + (box.numel() * 8 if box is not None else 0),
                "step_seconds": samples, "clocks": sampler2.stop(), "tables_h2d_bytes_first_call": table_bytes,
                "how": "fmc_simulate_host through ctypes: kernel, per-game scores + histogram + counters (+ player box) copied "

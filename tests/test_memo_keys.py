@@ -108,3 +108,49 @@ def test_keys_separate_what_the_forest_separates(native_lib, oracle, models_s2):
     out = oracle.predict("pass_yards", rows, np.tile(np.asarray(cols, np.int32), (len(rows), 1)), 3)
     n_out = len(np.unique(out.view(np.uint64), axis=0))
     assert len(np.unique(keys)) >= n_out
+
+
+@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("kind,zm", [(art.KIND_XGB, True), (art.KIND_XGB, False), (art.KIND_SKL, False)])
+def test_random_forests_equal_keys_equal_margins(native_lib, seed, kind, zm):
+    """The same property on random forests (both tree kinds, with and without "zero is missing", thresholds on either
+    side of the 0/1 flags, splits on the folded numerics and on one-hot columns): whatever the specialiser keeps,
+    the key must determine the margins."""
+    from oracle import tree_oracle as to
+    from test_pack_fuzz import random_forest
+    rng = np.random.default_rng(7000 + 100 * kind + 10 * seed + int(zm))
+    f = random_forest(rng, kind, n_trees=int(rng.integers(10, 80)), n_outputs=int(rng.integers(1, 4)),
+                      max_depth=int(rng.integers(2, 7)), zero_is_missing=zm, const_fraction=float(rng.choice([0, 0.2])))
+    fold = np.zeros(17)
+    fold[6] = fold[7] = 3.0
+    fold[8:12] = [15.6, 35.7, 20.6, 0.0]          # an SP+ rating of exactly 0 folds as "missing" for CSR-fed boosters
+    hot = int(rng.integers(-1, 6))
+    st = _states(rng, 3000)
+    keys, meta = native.memo_keys_host(f, 0 if kind == art.KIND_XGB else 2, st, cols=(hot, -1), fold_values=fold)
+    assert keys is not None, meta
+    rows = _rows17(st, (fold[8], fold[9], 0.0), (fold[11], 0.0, fold[10]))
+    out = to.raw_margin(f, rows, np.tile(np.array([hot]), (rows.shape[0], 1)))
+    order = np.argsort(keys, kind="stable")
+    k, o = keys[order], np.ascontiguousarray(out[order]).view(np.uint64)
+    same = k[1:] == k[:-1]
+    assert same.sum() > 500
+    assert np.array_equal(o[1:][same], o[:-1][same])
+
+
+def test_forest_that_does_not_fit_a_key_is_reported(native_lib):
+    """More thresholds on a tabulated feature than a code byte holds: the family is reported as not memoisable (its
+    requests are then always walked) instead of being keyed wrongly."""
+    n = 300                                           # 300 distinct thresholds on seconds_remaining
+    feat, thr, left, right, val, roots = [], [], [], [], [], []
+    for t in range(n):
+        roots.append(len(feat))
+        feat += [6 + 5, -1, -1]; thr += [float(10 * t + 0.5), 0.0, 0.0]
+        left += [len(left) + 1, -1, -1]; right += [len(right) + 2, -1, -1]; val += [0.0, 1.0, -1.0]
+    f = art.Forest(
+        name="wide", kind=art.KIND_XGB, link=art.LINK_SIGMOID, n_outputs=1, n_features=23, num_base=6, n_num=17,
+        zero_is_missing=False, base_margin=np.zeros(1), scale=1.0, groups=[art.OneHotGroup("player", 0, list("abcdeU"))],
+        feat=np.asarray(feat, np.int32), thr=np.asarray(thr, np.float32), left=np.asarray(left, np.int32),
+        right=np.asarray(right, np.int32), default_left=np.zeros(len(feat), np.uint8), value=np.asarray(val, np.float64),
+        tree_root=np.asarray(roots, np.int32), tree_out=np.zeros(n, np.int32))
+    keys, meta = native.memo_keys_host(f, 0, np.array([[1, 10.0, 75.0, 0, 3600]], float), cols=(-1, -1), fold_values=np.zeros(17))
+    assert keys is None and not meta["memoisable"] and "threshold" in meta["why"]
