@@ -8,7 +8,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "fmc_abi.cu")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("fmc_abi.cu", "fmc_sim.cuh", "fmc_device.cuh", "fmc_pack.hpp")] + \
+DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))
+              if f.endswith((".cu", ".cuh", ".hpp", ".h"))) + \
        [os.path.join(os.path.dirname(HERE), "include", "fmc.h")]
 OUT = os.path.join(HERE, "libfmc_b200.so")
 
