@@ -1469,18 +1469,8 @@ extern "C" int64_t fmc_memo_keys_host(const fmc_forest_desc *d, int32_t family, 
             if (in.pm_scaled[1]) v1 = (float)((x[1] - in.pm_mean[1]) / in.pm_scale[1]);
             if (in.pm_scaled[2]) v2 = (float)((x[2] - in.pm_mean[2]) / in.pm_scale[2]);
         }
-        // every form of the key code (binary search / bucket tables, comparison fixed at compile time / chosen at run
-        // time) must give the same key: the kernel is built with one of them (FMC_MEMO_KEY_BUCKET, FMC_MEMO_SPEC)
-        const int md = in.xgb ? 1 : 0;
-        const unsigned long long k00 = md ? memo_key_impl<1, false>(&rs, true, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2)
-                                          : memo_key_impl<0, false>(&rs, false, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2);
-        const unsigned long long k01 = md ? memo_key_impl<1, true>(&rs, true, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2)
-                                          : memo_key_impl<0, true>(&rs, false, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2);
-        const unsigned long long k20 = memo_key_impl<2, false>(&rs, in.xgb, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2);
-        const unsigned long long k21 = memo_key_impl<2, true>(&rs, in.xgb, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2);
-        if (k00 != k01 || k00 != k20 || k00 != k21)
-            return fail(FMC_ERR_CAPACITY, "fmc_memo_keys_host: the forms of the key code disagree");
-        keys_out[i] = k00;
+        keys_out[i] = in.xgb ? memo_key<true>(&rs, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2)
+                             : memo_key<false>(&rs, family, 0, 0, down, x[1], x[2], sd, sec, v1, v2);
     }
     return 1;
 }

@@ -39,26 +39,19 @@ constexpr int kMemoSdOffset = 256, kMemoSdLut = 512, kMemoSecLut = 3604, kMemoDo
 
 // What the kernel needs to turn a request of one (family, orientation) into its key.  Lives in global memory
 // (read through L1); one per (matchup, family, orientation).
-constexpr int kMemoBuckets = 512;       // buckets of a searched feature's bucket table
-struct alignas(16) RankSpec {
-    // -- what the key code reads: two 16-byte loads for all the per-forest scalars
-    uint32_t hdr[4];                    // [0] shift0 | shift1 << 8 | shift_sd << 16 | shift_sec << 24, [1] n_thr0 | n_thr1 << 16, [2] zm
-    float bparm[4];                     // lo0, scale0, lo1, scale1: bucket of x = clamp(int((x - lo) * scale), 0, kMemoBuckets - 1)
+struct RankSpec {
     uint32_t enabled;                   // 0: this forest's ranks do not fit the key -> its requests are always walked
     uint32_t xgb;                       // compare: 1 -> right iff x >= t (xgboost), 0 -> right iff x > t (sklearn)
     uint32_t zm;                        // exact zero == missing (rows 1, 2, 4 get the extra "zero" code)
     uint32_t n_thr[2];                  // searched features: 0 distance (row 1), 1 yardsToGoal (row 2)
     uint32_t shift[2];
     uint32_t shift_sd, shift_sec;
-    uint32_t pad_[3];
-    float thr[2][kMemoThrMax + 5];      // ascending, padded with +inf (thr[n .. n + 4] are readable)
-    uint16_t b_lut[2][kMemoBuckets];    // bucket -> index of its first threshold | thresholds in it << 8 | (more than two) << 15
+    float thr[2][kMemoThrMax + 1];      // ascending, padded with +inf
     uint64_t lut_down[kMemoDownLut];    // min(down, 15) -> code << shift
     uint64_t lut_flags[64];             // rz | gtg << 1 | f&s << 2 | fg << 3 | two_minute << 4 | (half == 2) << 5 -> codes << shifts
     uint8_t lut_sd[kMemoSdLut];         // clamp(score_diff + 256, 0, 511) -> code
     uint8_t lut_sec[kMemoSecLut];       // seconds 0..3600 -> code
 };
-static_assert(sizeof(RankSpec) % 16 == 0, "RankSpec arrays must keep 16-byte alignment");
 
 struct MemoRegion {
     unsigned long long base;            // device address of the region, 0 = family not memoised
@@ -84,8 +77,7 @@ __host__ __device__ inline int memo_slot_shift(int fam) { return fam == 0 ? 4 : 
 #define FMC_MEMO_LD(p) (*(p))
 #endif
 
-// Reference form of the rank: #{t : x goes right of t} by binary search over the ascending thresholds (padded with
-// +inf).  The kernel uses memo_rank_bucket below; build_rank_spec and fmc_memo_keys_host check the two equal.
+// Rank of x among the ascending thresholds (padded with +inf to 128): #{t : x goes right of t}.
 template <bool XGB>
 __host__ __device__ __forceinline__ uint32_t memo_rank(const float *thr, float x) {
     uint32_t pos = 0;
@@ -98,64 +90,13 @@ __host__ __device__ __forceinline__ uint32_t memo_rank(const float *thr, float x
     return pos;
 }
 
-// Bucket of a value.  Non-decreasing in x (an IEEE subtraction, a multiplication by a power of two, two clamps and a
-// truncation are all monotonic), and evaluated by the same expression for the thresholds (host) and the values
-// (kernel): a threshold in a lower bucket than x is < x, one in a higher bucket is > x -- only the thresholds of x's
-// own bucket need a comparison.  NaN goes to bucket 0 (never produced by the simulation).  Branch-free.
-__host__ __device__ __forceinline__ uint32_t memo_bucket(float x, float lo, float scale) {
-    float fb = (x - lo) * scale;
-    fb = fb >= 0.f ? fb : 0.f;                                    // also NaN -> 0
-    fb = fb < (float)(kMemoBuckets - 1) ? fb : (float)(kMemoBuckets - 1);
-    return (uint32_t)(int)fb;
-}
-// MODE 0: sklearn (right iff x > t), 1: xgboost (x >= t), 2: chosen at run time by `xgb`
-template <int MODE>
-__host__ __device__ __forceinline__ bool memo_goes_right(bool xgb, float x, float t) {
-    return MODE == 0 ? (x > t) : (MODE == 1 ? (x >= t) : ((x > t) || (xgb && x == t)));
-}
-
-// The same rank in three loads instead of seven dependent ones: the bucket table gives the index of the first threshold
-// of x's bucket (everything before it lies to the left of x); the two thresholds from there on are compared directly
-// (comparing one that belongs to a later bucket adds nothing, it is > x), the rare bucket with more than two loops.
-template <int MODE>
-__host__ __device__ __forceinline__ uint32_t memo_rank_bucket(const RankSpec *rs, int j, float x, float lo, float scale, bool xgb) {
-    const uint32_t e = FMC_MEMO_LD(&rs->b_lut[j][memo_bucket(x, lo, scale)]);
-    const uint32_t base = e & 0xffu;
-    const float *t = rs->thr[j] + base;
-    const float t0 = FMC_MEMO_LD(t), t1 = FMC_MEMO_LD(t + 1);
-    uint32_t c = base + (memo_goes_right<MODE>(xgb, x, t0) ? 1u : 0u) + (memo_goes_right<MODE>(xgb, x, t1) ? 1u : 0u);
-    if (e & 0x8000u) {
-        const uint32_t n = (e >> 8) & 0x7fu;
-#pragma unroll 1
-        for (uint32_t i = 2; i < n; ++i) c += memo_goes_right<MODE>(xgb, x, FMC_MEMO_LD(t + i)) ? 1u : 0u;
-    }
-    return c;
-}
-template <int MODE>
-__host__ __device__ __forceinline__ uint32_t memo_rank_search(const float *thr, float x, bool xgb) {
-    uint32_t pos = 0;
-#pragma unroll
-    for (int s = 64; s >= 1; s >>= 1) {
-        const float t = FMC_MEMO_LD(thr + pos + s - 1);
-        pos += memo_goes_right<MODE>(xgb, x, t) ? (uint32_t)s : 0u;
-    }
-    return pos;
-}
-
-// Which form the kernel uses (measured): 0 = binary search, 1 = bucket tables.  Both give the same ranks.
-#ifndef FMC_MEMO_KEY_BUCKET
-#define FMC_MEMO_KEY_BUCKET 0
-#endif
-
 // Key of a request of (family, team on offense) in the state (down, distance, yardsToGoal, score_diff, seconds).
 // v1 / v2 are the distance / yardsToGoal FEATURE values as write_features forms them (float conversion, play-model
 // standardisation); the flags are derived exactly as `_fill_row` derives them (FMC:996-1021).  One implementation
-// for the kernel and for the host-side check (fmc_memo_keys_host).  MODE selects the comparison (memo_goes_right): a
-// compile-time constant through memo_key<>, the run-time `xgb` through memo_key_rt, where one copy of the code serves
-// requests of both kinds (the speculative keys of fmc_sim_memo.cuh).
-template <int MODE, bool BUCKET>
-__host__ __device__ __forceinline__ unsigned long long memo_key_impl(const RankSpec *rs, bool xgb, int fam, int team, int matchup, int down,
-                                                                     double dist, double ytg, int sd, int sec, float v1, float v2) {
+// for the kernel and for the host-side check (fmc_memo_keys_host).
+template <bool XGB>
+__host__ __device__ __forceinline__ unsigned long long memo_key(const RankSpec *rs, int fam, int team, int matchup, int down,
+                                                                double dist, double ytg, int sd, int sec, float v1, float v2) {
     const uint32_t fl = (ytg <= 20.0 ? 1u : 0u) | (dist >= (ytg - 0.5) ? 2u : 0u) | ((down == 4 && dist <= 2.0) ? 4u : 0u) |
                         (ytg <= 33.0 ? 8u : 0u) | (((sec % 1800) <= 120) ? 16u : 0u) | (sec > 1800 ? 0u : 32u);
     int sdi = sd + kMemoSdOffset;
@@ -163,45 +104,16 @@ __host__ __device__ __forceinline__ unsigned long long memo_key_impl(const RankS
     const int dn = down < 0 ? 0 : (down < kMemoDownLut - 1 ? down : kMemoDownLut - 1);
     const int si = sec < 0 ? 0 : (sec > 3600 ? 3600 : sec);
     unsigned long long k = FMC_MEMO_LD(rs->lut_down + dn) | FMC_MEMO_LD(rs->lut_flags + fl);
-    if (BUCKET) {
-        // all per-forest scalars in two 16-byte loads
-#ifdef __CUDA_ARCH__
-        const uint4 h = __ldg(reinterpret_cast<const uint4 *>(rs->hdr));
-        const float4 bp = __ldg(reinterpret_cast<const float4 *>(rs->bparm));
-        const uint32_t h0 = h.x, h1 = h.y, h2 = h.z;
-        const float lo0 = bp.x, sc0 = bp.y, lo1 = bp.z, sc1 = bp.w;
-#else
-        const uint32_t h0 = rs->hdr[0], h1 = rs->hdr[1], h2 = rs->hdr[2];
-        const float lo0 = rs->bparm[0], sc0 = rs->bparm[1], lo1 = rs->bparm[2], sc1 = rs->bparm[3];
-#endif
-        k |= (unsigned long long)FMC_MEMO_LD(rs->lut_sd + sdi) << ((h0 >> 16) & 0xffu);
-        k |= (unsigned long long)FMC_MEMO_LD(rs->lut_sec + si) << (h0 >> 24);
-        uint32_t c1 = memo_rank_bucket<MODE>(rs, 0, v1, lo0, sc0, xgb), c2 = memo_rank_bucket<MODE>(rs, 1, v2, lo1, sc1, xgb);
-        if (h2 != 0u && v1 == 0.f) c1 = (h1 & 0xffffu) + 1u;
-        if (h2 != 0u && v2 == 0.f) c2 = (h1 >> 16) + 1u;
-        k |= (unsigned long long)c1 << (h0 & 0xffu);
-        k |= (unsigned long long)c2 << ((h0 >> 8) & 0xffu);
-    } else {
-        k |= (unsigned long long)FMC_MEMO_LD(rs->lut_sd + sdi) << FMC_MEMO_LD(&rs->shift_sd);
-        k |= (unsigned long long)FMC_MEMO_LD(rs->lut_sec + si) << FMC_MEMO_LD(&rs->shift_sec);
-        const uint32_t n1 = FMC_MEMO_LD(&rs->n_thr[0]), n2 = FMC_MEMO_LD(&rs->n_thr[1]);
-        const bool zm = FMC_MEMO_LD(&rs->zm) != 0u;
-        uint32_t c1 = memo_rank_search<MODE>(rs->thr[0], v1, xgb), c2 = memo_rank_search<MODE>(rs->thr[1], v2, xgb);
-        if (zm && v1 == 0.f) c1 = n1 + 1u;
-        if (zm && v2 == 0.f) c2 = n2 + 1u;
-        k |= (unsigned long long)c1 << FMC_MEMO_LD(&rs->shift[0]);
-        k |= (unsigned long long)c2 << FMC_MEMO_LD(&rs->shift[1]);
-    }
+    k |= (unsigned long long)FMC_MEMO_LD(rs->lut_sd + sdi) << FMC_MEMO_LD(&rs->shift_sd);
+    k |= (unsigned long long)FMC_MEMO_LD(rs->lut_sec + si) << FMC_MEMO_LD(&rs->shift_sec);
+    const uint32_t n1 = FMC_MEMO_LD(&rs->n_thr[0]), n2 = FMC_MEMO_LD(&rs->n_thr[1]);
+    const bool zm = FMC_MEMO_LD(&rs->zm) != 0u;
+    uint32_t c1 = memo_rank<XGB>(rs->thr[0], v1), c2 = memo_rank<XGB>(rs->thr[1], v2);
+    if (zm && v1 == 0.f) c1 = n1 + 1u;
+    if (zm && v2 == 0.f) c2 = n2 + 1u;
+    k |= (unsigned long long)c1 << FMC_MEMO_LD(&rs->shift[0]);
+    k |= (unsigned long long)c2 << FMC_MEMO_LD(&rs->shift[1]);
     return (1ULL << 63) | (k << 16) | ((unsigned long long)matchup << 6) | ((unsigned long long)fam << 3) | ((unsigned long long)team << 2);
-}
-template <bool XGB>
-__host__ __device__ __forceinline__ unsigned long long memo_key(const RankSpec *rs, int fam, int team, int matchup, int down,
-                                                                double dist, double ytg, int sd, int sec, float v1, float v2) {
-    return memo_key_impl<XGB ? 1 : 0, FMC_MEMO_KEY_BUCKET != 0>(rs, XGB, fam, team, matchup, down, dist, ytg, sd, sec, v1, v2);
-}
-__host__ __device__ __forceinline__ unsigned long long memo_key_rt(const RankSpec *rs, bool xgb, int fam, int team, int matchup, int down,
-                                                                   double dist, double ytg, int sd, int sec, float v1, float v2) {
-    return memo_key_impl<2, FMC_MEMO_KEY_BUCKET != 0>(rs, xgb, fam, team, matchup, down, dist, ytg, sd, sec, v1, v2);
 }
 
 // ---- host: build the rank spec of one specialised forest ---------------------------------------------
@@ -257,30 +169,10 @@ inline std::string build_rank_spec(const std::vector<std::vector<float>> &row_th
     // searched features
     for (int j = 0; j < 2; ++j) {
         const int row = 1 + j;
-        const std::vector<float> &tv = T[row];
-        if (tv.size() > (size_t)kMemoThrMax) return "too many thresholds on a searched feature";
-        rs.n_thr[j] = (uint32_t)tv.size();
+        if (T[row].size() > (size_t)kMemoThrMax) return "too many thresholds on a searched feature";
+        rs.n_thr[j] = (uint32_t)T[row].size();
         rs.shift[j] = shift[row];
-        for (int i = 0; i < kMemoThrMax + 5; ++i) rs.thr[j][i] = i < (int)tv.size() ? tv[i] : INFINITY;
-        // bucket table: buckets of width 1 / scale from lo = floor(smallest threshold), scale the largest power of two
-        // that keeps the largest threshold inside the table (fewest thresholds per bucket)
-        float lo = 0.f, scale = 1.f;
-        if (!tv.empty()) {
-            lo = std::floor(tv.front());
-            const float span = tv.back() - lo;
-            int e = 20;
-            while (e > -60 && !(span * std::ldexp(1.0f, e) < (float)(kMemoBuckets - 1))) --e;
-            scale = std::ldexp(1.0f, e);
-        }
-        rs.bparm[2 * j] = lo; rs.bparm[2 * j + 1] = scale;
-        std::vector<uint32_t> first(kMemoBuckets + 1, 0), count(kMemoBuckets, 0);
-        for (float t : tv) count[memo_bucket(t, lo, scale)] += 1;
-        for (int b = 0; b < kMemoBuckets; ++b) first[b + 1] = first[b] + count[b];
-        for (int b = 0; b < kMemoBuckets; ++b)
-            rs.b_lut[j][b] = (uint16_t)(first[b] | (count[b] << 8) | (count[b] > 2 ? 0x8000u : 0u));
-        // the thresholds must fall into non-decreasing buckets (memo_bucket is monotonic)
-        for (size_t i = 1; i < tv.size(); ++i)
-            if (memo_bucket(tv[i - 1], lo, scale) > memo_bucket(tv[i], lo, scale)) return "bucket table: thresholds out of order";
+        for (int i = 0; i <= kMemoThrMax; ++i) rs.thr[j][i] = i < (int)T[row].size() ? T[row][i] : INFINITY;
     }
     // table features; the clamps of the kernel must not change a code
     for (int r : {0, 4, 5}) if (max_code(r) > 255u) return "too many thresholds on a tabulated feature";
@@ -304,28 +196,6 @@ inline std::string build_rank_spec(const std::vector<std::vector<float>> &row_th
         k |= (uint64_t)code(9, half) << shift[9];
         k |= (uint64_t)code(10, tm) << shift[10];
         rs.lut_flags[f] = k;
-    }
-    rs.hdr[0] = shift[1] | (shift[2] << 8) | (shift[4] << 16) | (shift[5] << 24);
-    rs.hdr[1] = rs.n_thr[0] | (rs.n_thr[1] << 16);
-    rs.hdr[2] = rs.zm;
-    // the bucket tables must reproduce the binary-search rank: at every threshold, its two neighbours and every bucket
-    // edge (the rank is a step function that moves only at thresholds; the bucket form can only go wrong at an edge)
-    for (int j = 0; j < 2; ++j) {
-        const float lo = rs.bparm[2 * j], scale = rs.bparm[2 * j + 1];
-        auto same = [&](float x) {
-            const uint32_t want = in.xgb ? memo_rank<true>(rs.thr[j], x) : memo_rank<false>(rs.thr[j], x);
-            return memo_rank_bucket<2>(&rs, j, x, lo, scale, in.xgb) == want && memo_rank_search<2>(rs.thr[j], x, in.xgb) == want &&
-                   (in.xgb ? memo_rank_bucket<1>(&rs, j, x, lo, scale, true) : memo_rank_bucket<0>(&rs, j, x, lo, scale, false)) == want;
-        };
-        for (uint32_t i = 0; i < rs.n_thr[j]; ++i) {
-            const float t = rs.thr[j][i];
-            if (!same(t) || !same(std::nextafter(t, -INFINITY)) || !same(std::nextafter(t, INFINITY))) return "bucket table disagrees with the search";
-        }
-        for (int b = -1; b <= kMemoBuckets + 1; ++b) {
-            const float edge = lo + (float)b / scale;
-            if (!same(edge) || !same(std::nextafter(edge, -INFINITY)) || !same(std::nextafter(edge, INFINITY))) return "bucket table disagrees with the search";
-        }
-        if (!same(0.f) || !same(-0.f) || !same(-1e30f) || !same(1e30f)) return "bucket table disagrees with the search";
     }
     rs.enabled = 1;
     return "";

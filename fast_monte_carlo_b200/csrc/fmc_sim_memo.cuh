@@ -67,35 +67,12 @@ FMC_MEMO_HELPER unsigned long long m_memo_key_skl(const RankSpec *rs, int fam, i
     return memo_key<false>(rs, fam, team, matchup, down, dist, ytg, sd, sec, v1, v2);
 }
 
-// The two scores are addressed by the team on offense.  A run-time index into Lane::score puts the array (and with it
-// every access) into local memory; the select forms below keep both scores in registers (FMC_MEMO_NOLOCAL=0: the
-// indexed form).  Same for the trip's event tally, whose only run-time index was the hit counter of the yardage family.
-#ifndef FMC_MEMO_NOLOCAL
-#define FMC_MEMO_NOLOCAL 0
-#endif
-__device__ __forceinline__ int lane_score_diff(const Lane &L, int team) {
-#if FMC_MEMO_NOLOCAL
-    const int d = L.score[0] - L.score[1];
-    return team ? -d : d;
-#else
-    return L.score[team] - L.score[team ^ 1];
-#endif
-}
-__device__ __forceinline__ void lane_add_score(Lane &L, int team, int pts) {
-#if FMC_MEMO_NOLOCAL
-    L.score[0] += team ? 0 : pts;
-    L.score[1] += team ? pts : 0;
-#else
-    L.score[team] += pts;
-#endif
-}
-
 // Key of the request (family, team on offense) a lane is about to post.  The feature values are formed exactly as
 // write_features forms them (same float conversions, same play-model standardisation).
 template <bool XGB>
 __device__ __forceinline__ unsigned long long lane_memo_key(const RankSpec *rs, int fam, int team, int matchup, const Lane &L,
                                                             const SimKernelArgs &a) {
-    const int sd = lane_score_diff(L, team);
+    const int sd = L.score[team] - L.score[team ^ 1];
     float v1 = (float)L.dist, v2 = (float)L.ytg;
     if (fam == 5) {
         if (a.pm_scaled[1]) v1 = (float)((L.dist - a.pm_mean[1]) / a.pm_scale[1]);
@@ -109,32 +86,6 @@ __device__ __forceinline__ unsigned long long memo_slot_addr(const MemoRegion &R
     unsigned long long h = (key ^ (key >> 31)) * 0x9E3779B97F4A7C15ULL;
     h ^= h >> 29;
     return R.base + ((unsigned long long)((uint32_t)(h >> 20) & R.slot_mask) << R.slot_shift);
-}
-
-// Speculative keys (FMC_MEMO_SPEC): a play's later requests are made in the SAME state as its first one (stage 1 -> pass
-// yards or stage 2: nothing moves between them), so their keys can be computed, and their slots fetched into L2, while
-// the first probe is in flight -- the later probes then find their line in L2 instead of paying a second and third DRAM
-// round trip, and read their key from shared memory instead of recomputing it.  Pure scheduling: keys, probes, hits and
-// results are the same.   0 = off, 1 = the requests behind stage 1, 2 = also the run-yards key at the play call.
-#ifndef FMC_MEMO_SPEC
-#define FMC_MEMO_SPEC 0
-#endif
-#ifndef FMC_MEMO_PF_KIND
-#define FMC_MEMO_PF_KIND 0           // how a slot is fetched ahead: 0 prefetch.global.L2, 1 cp.async.bulk.prefetch.L2, 2 not at all, 3 a load nobody waits for
-#endif
-__device__ __forceinline__ void memo_prefetch(unsigned long long addr, uint32_t slot_shift) {
-#if FMC_MEMO_PF_KIND == 1
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(addr), "r"(1u << slot_shift) : "memory");
-#elif FMC_MEMO_PF_KIND == 0
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(addr));
-    if (slot_shift > 5u) asm volatile("prefetch.global.L2 [%0];" :: "l"(addr + 32ull));
-#elif FMC_MEMO_PF_KIND == 3
-    unsigned int d0, d1;
-    asm volatile("ld.volatile.global.b32 %0, [%1];" : "=r"(d0) : "l"(addr) : "memory");
-    if (slot_shift > 5u) asm volatile("ld.volatile.global.b32 %0, [%1];" : "=r"(d1) : "l"(addr + 32ull) : "memory");
-#else
-    (void)addr; (void)slot_shift;
-#endif
 }
 
 // Probe: true and r[] = payloads when every unit of the entry carries the key.
@@ -202,7 +153,7 @@ struct MemoShared {
     unsigned long long wstat[kMemoThreads / 32][kWstat];  // per-warp event totals (EV_*, then plays, iters, probes), no atomics
 };
 constexpr size_t kMemoSharedBytes = ((sizeof(MemoShared) + 15) / 16) * 16;
-constexpr size_t kMemoKeyBytes = (size_t)kMemoThreads * 8 * (FMC_MEMO_SPEC ? 3 : 1);   // + the two speculative keys per lane
+constexpr size_t kMemoKeyBytes = (size_t)kMemoThreads * 8;
 inline size_t sim_memo_smem_bytes() { return kMemoSharedBytes + kMemoFeatBytes + kMemoResultBytes + kMemoKeyBytes; }
 
 // (bounds of a full CTA whatever kMemoThreads: builds of this kernel with __launch_bounds__(512 | 768, ...) die on the B200
@@ -217,10 +168,6 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
     float *feats = reinterpret_cast<float *>(smem_raw + kMemoSharedBytes);
     double *results = reinterpret_cast<double *>(smem_raw + kMemoSharedBytes + kFeatBytes_);
     unsigned long long *mkey = reinterpret_cast<unsigned long long *>(smem_raw + kMemoSharedBytes + kFeatBytes_ + kMemoResultBytes);
-#if FMC_MEMO_SPEC
-    unsigned long long *pky = mkey + kMemoThreads;      // key of the lane's yardage request (pass yards after stage 1 / run yards)
-    unsigned long long *pks2 = pky + kMemoThreads;      // key of its stage-2 request
-#endif
     const unsigned int FULL = 0xFFFFFFFFu;
 
     const uint32_t feats_saddr = (uint32_t)__cvta_generic_to_shared(feats);
@@ -348,7 +295,7 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                 Lv.iter = (L.stage == ST_ITER) ? L.iter : L.iter - 1;
                 Draws<TEST> D(a, M, m, Lv);
                 const int team = L.offense;
-                const int sd = lane_score_diff(L, team);
+                const int sd = L.score[team] - L.score[team ^ 1];
                 const double ytg0 = L.ytg;
                 __syncwarp();      // every stage of the trip is entered by the whole warp together
                 // -- iteration start: fourth down (handle_fourth FMC:1382-1421) and the play call
@@ -372,7 +319,7 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                             ev.hit(EV_FGA);
                             const bool good = D.u(S_U_FG) < field_goal_prob(ytg + 17.0);
                             tick_clock(L, 12);
-                            if (good) { ev.hit(EV_FG); lane_add_score(L, team, 3); change_possession(L, true, 75.0); }
+                            if (good) { ev.hit(EV_FG); L.score[team] += 3; change_possession(L, true, 75.0); }
                             else change_possession(L, true, 100.0 - ytg);
                             play = false;
                         } else {
@@ -430,43 +377,6 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                 }
                 __syncwarp();      // every stage of the trip is entered by the whole warp together
                 // -- stage 1: probe, then FMC:1086-1087
-#if FMC_MEMO_SPEC
-                {
-                    // first request of the play: stage 1 of a pass (probed here) / run yards (FMC_MEMO_SPEC >= 2: key + prefetch
-                    // only, probed at the yardage stage).  One copy of the key code, looped: iteration 0 is the first request,
-                    // iterations 1, 2 (pass only) the pass-yards and stage-2 keys of the same state, prefetched while the
-                    // stage-1 load is in flight.
-                    const bool first_pass = !parked && !have && L.stage == ST_WAIT_S1;
-                    const bool first_run = FMC_MEMO_SPEC >= 2 && !parked && !have && L.stage == ST_WAIT_RQ;
-                    unsigned long long key0 = 0ULL, k0 = 0ULL;
-                    if (first_pass || first_run) {
-                        const int nreq = first_pass ? (a.stage2_mode == 1 ? 3 : 2) : 1;
-                        const int sdl = lane_score_diff(L, team);
-                        const float v1 = (float)L.dist, v2 = (float)L.ytg;
-#pragma unroll 1
-                        for (int j = 0; j < nreq; ++j) {
-                            const int fam = first_pass ? (j == 0 ? 0 : (j == 1 ? 2 : 1)) : 3;
-                            const RankSpec *rs = specs + fam * 2 + team;
-                            unsigned long long key = 0ULL;
-                            if (mm.enabled && mm.region[fam].base != 0ULL && __ldg(&rs->enabled))
-                                key = memo_key_rt(rs, fam < 2, fam, team, m, L.down, L.dist, L.ytg, sdl, L.sec, v1, v2);
-                            const unsigned long long addr = memo_slot_addr(mm.region[fam], key);
-                            if (fam == 0) {
-                                key0 = key;
-                                if (key != 0ULL) memo_ld(addr, k0, r[0]);
-                            } else {
-                                if (key != 0ULL) memo_prefetch(addr, mm.region[fam].slot_shift);
-                                if (fam == 1) pks2[tid] = key; else pky[tid] = key;
-                            }
-                        }
-                    }
-                    if (first_pass) {
-                        const bool hit = key0 != 0ULL && k0 == key0;
-                        if (key0 != 0ULL) { n_probes += 1; if (hit) ev.hit(EV_HIT0); }
-                        if (hit) have = true; else { parked = true; mkey[tid] = key0; }
-                    }
-                }
-#else
                 if (!parked && !have && L.stage == ST_WAIT_S1) {
                     const RankSpec *rs = specs + 0 * 2 + team;
                     unsigned long long key = 0ULL;
@@ -478,7 +388,6 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                     }
                     if (hit) have = true; else { parked = true; mkey[tid] = key; }
                 }
-#endif
                 __syncwarp();      // every stage of the trip is entered by the whole warp together
                 bool s2_standin = false;
                 if (have && L.stage == ST_WAIT_S1) {
@@ -493,16 +402,11 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                 __syncwarp();      // every stage of the trip is entered by the whole warp together
                 // -- stage 2: probe, then the not-complete outcome FMC:751-770, 1157-1199
                 if (!parked && !have && L.stage == ST_WAIT_S2) {
+                    const RankSpec *rs = specs + 1 * 2 + team;
                     unsigned long long key = 0ULL;
                     bool hit = false;
-#if FMC_MEMO_SPEC
-                    key = pks2[tid];              // formed at the stage-1 probe of this play, in this state
-                    if (key != 0ULL) {
-#else
-                    const RankSpec *rs = specs + 1 * 2 + team;
                     if (mm.enabled && __ldg(&rs->enabled)) {
                         key = lane_memo_key<true>(rs, 1, team, m, L, a);
-#endif
                         hit = memo_probe<2>(memo_slot_addr(mm.region[1], key), key, r);
                         n_probes += 1; if (hit) ev.hit(EV_HIT1);
                     }
@@ -552,23 +456,10 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                     const RankSpec *rs = specs + fam * 2 + team;
                     unsigned long long key = 0ULL;
                     bool hit = false;
-#if FMC_MEMO_SPEC
-                    // pass yards (and run yards with FMC_MEMO_SPEC >= 2): the key formed at the first request of this play
-                    const bool kept = fam == 2 || (FMC_MEMO_SPEC >= 2 && fam == 3);
-                    if (kept) key = pky[tid];
-                    else if (mm.enabled && __ldg(&rs->enabled)) key = lane_memo_key<false>(rs, fam, team, m, L, a);
-                    if (key != 0ULL) {
-#else
                     if (mm.enabled && __ldg(&rs->enabled)) {
                         key = lane_memo_key<false>(rs, fam, team, m, L, a);
-#endif
                         hit = memo_probe<3>(memo_slot_addr(mm.region[fam], key), key, r);
-                        n_probes += 1;
-#if FMC_MEMO_NOLOCAL
-                        if (hit) { if (fam == 2) ev.hit(EV_HIT2); else if (fam == 3) ev.hit(EV_HIT3); else ev.hit(EV_HIT4); }
-#else
-                        if (hit) ev.w[(EV_HIT0 + fam) / 5] += 1u << (6 * ((EV_HIT0 + fam) % 5));
-#endif
+                        n_probes += 1; if (hit) ev.w[(EV_HIT0 + fam) / 5] += 1u << (6 * ((EV_HIT0 + fam) % 5));
                     }
                     if (hit) have = true; else { parked = true; mkey[tid] = key; }
                 }
@@ -598,7 +489,7 @@ __global__ void __launch_bounds__(1024, 1) sim_memo_kernel(const SimKernelArgs a
                         }
                         if (yards + 1e-9 >= ytg0) {
                             ev.hit(EV_TD);
-                            lane_add_score(L, team, 7); L.going = 0;
+                            L.score[team] += 7; L.going = 0;
                             tick_clock(L, pass ? 20 : 28);
                             change_possession(L, true, 75.0);
                         } else {

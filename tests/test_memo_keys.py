@@ -137,57 +137,6 @@ def test_random_forests_equal_keys_equal_margins(native_lib, seed, kind, zm):
     assert np.array_equal(o[1:][same], o[:-1][same])
 
 
-@pytest.mark.parametrize("kind", [art.KIND_XGB, art.KIND_SKL])
-@pytest.mark.parametrize("layout", ["cluster", "outliers", "single", "negative"])
-def test_bucket_tables_with_clustered_thresholds(native_lib, kind, layout):
-    """The kernel finds a feature's rank through a bucket table (memo_rank_bucket: first threshold of the value's bucket,
-    two direct comparisons, a loop for buckets that hold more).  Thresholds that crowd one bucket, lie far apart, are a
-    single value or negative must give the ranks of the plain binary search: fmc_memo_keys_host compares the two forms on
-    every state and fails on a difference; and equal keys must still mean equal margins."""
-    from oracle import tree_oracle as to
-    from test_pack_fuzz import random_forest
-    rng = np.random.default_rng(99 + kind + len(layout))
-    f = random_forest(rng, kind, n_trees=60, n_outputs=1, max_depth=5, zero_is_missing=False)
-    internal = f.left >= 0
-    for row, centre in ((1, 7.0), (2, 40.0)):
-        sel = np.flatnonzero(internal & (f.feat == f.num_base + row))
-        if layout == "cluster":          # ~60 thresholds inside a hundredth of a yard, next to two far ones
-            t = centre + rng.integers(0, 60, len(sel)) * 1.5e-4
-            t[:2] = [0.25, 95.0][: len(t[:2])]
-        elif layout == "outliers":       # a span of 1e6: the buckets are thousands of yards wide
-            t = np.where(rng.random(len(sel)) < 0.1, 1e6, centre + rng.integers(-5, 6, len(sel)) + 0.5)
-        elif layout == "single":
-            t = np.full(len(sel), centre + 0.5)
-        else:
-            t = -centre + rng.integers(-5, 6, len(sel)) + 0.5
-        f.thr[sel] = t.astype(np.float32)
-    st = _states(rng, 1500)
-    m = st.shape[0]
-    thr1 = f.thr[internal & (f.feat == f.num_base + 1)].astype(np.float64)
-    thr2 = f.thr[internal & (f.feat == f.num_base + 2)].astype(np.float64)
-    # half of the states sit on / one float32 step off a threshold
-    pick = rng.random(m) < 0.5
-    step = rng.choice([-1, 0, 1], size=m)
-    on1 = rng.choice(thr1, size=m).astype(np.float32)
-    on2 = rng.choice(thr2, size=m).astype(np.float32)
-    on1 = np.where(step < 0, np.nextafter(on1, np.float32(-np.inf)), np.where(step > 0, np.nextafter(on1, np.float32(np.inf)), on1))
-    on2 = np.where(step < 0, np.nextafter(on2, np.float32(-np.inf)), np.where(step > 0, np.nextafter(on2, np.float32(np.inf)), on2))
-    st[:, 1] = np.where(pick, on1.astype(np.float64), st[:, 1])
-    st[:, 2] = np.where(pick, on2.astype(np.float64), st[:, 2])
-    fold = np.zeros(17)
-    fold[6] = fold[7] = 3.0
-    fold[8:12] = [15.6, 35.7, 20.6, 11.0]
-    keys, meta = native.memo_keys_host(f, 0 if kind == art.KIND_XGB else 2, st, cols=(-1, -1), fold_values=fold)
-    assert keys is not None, meta
-    rows = _rows17(st, (fold[8], fold[9], 0.0), (fold[11], 0.0, fold[10]))
-    out = to.raw_margin(f, rows, np.full((rows.shape[0], 1), -1))
-    order = np.argsort(keys, kind="stable")
-    k, o = keys[order], np.ascontiguousarray(out[order]).view(np.uint64)
-    same = k[1:] == k[:-1]
-    assert same.sum() > 200
-    assert np.array_equal(o[1:][same], o[:-1][same])
-
-
 def test_forest_that_does_not_fit_a_key_is_reported(native_lib):
     """More thresholds on a tabulated feature than a code byte holds: the family is reported as not memoisable (its
     requests are then always walked) instead of being keyed wrongly."""
