@@ -321,7 +321,13 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
     out.rounds = (int)rounds;
 
     Builder b(f, s);
-    struct Entry { std::vector<PNode> nodes; int root = -1; int depth = 0; std::vector<uint64_t> pre; };   // root < 0: padding tree
+    b.nodes.reserve(f.left.size() / (size_t)(f.n_outputs > 0 ? f.n_outputs : 1) + 64);
+    out.slots.reserve(f.left.size() + 1024);
+    out.slot_is_node.reserve(f.left.size() + 1024);
+    out.stream.reserve((size_t)(te - tb) + 64);
+    out.stream_is_node.reserve((size_t)(te - tb) + 64);
+    // a tree of the output being laid out: its nodes live in the builder's pool (one allocation per output, not per tree)
+    struct Entry { int root = -1; int depth = 0; std::vector<uint64_t> pre; };   // root < 0: padding tree
     std::vector<int> order, depth_q;
     std::vector<uint32_t> slot_of;
 
@@ -336,18 +342,19 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
             e.pre.swap(pending);
             entries.push_back(std::move(e));
         };
+        b.nodes.clear();
         for (size_t j = 0; j < per_out[k].size(); ++j) {
-            b.nodes.clear();
+            const size_t mark = b.nodes.size();
             const int root = b.build(f.root[per_out[k][j]]);
             if (b.nodes[root].leaf) {
                 if (!(std::fabs(b.nodes[root].value) < 1e60)) return "leaf value out of range";
                 if (pending.size() == 255) flush_padding_for_pending();
                 pending.push_back(value_word(f.kind, b.nodes[root].value));
                 out.constants++;
+                b.nodes.resize(mark);       // a folded tree leaves nothing in the pool
                 continue;
             }
             Entry e;
-            e.nodes = b.nodes;
             e.root = root;
             e.depth = b.depth_of(root);
             if (e.depth > kMaxGroupDepth) return "tree deeper than the walk supports (15 levels)";
@@ -392,7 +399,7 @@ inline std::string pack_forest(const HostForest &f, const PackSpec &s, PackedFor
                 slot_of.assign(1, 0xFFFFFFFFu);
                 depth_q.assign(1, 0);
                 for (size_t qi = 0; qi < order.size(); ++qi) {
-                    const PNode &n = e.nodes[order[qi]];
+                    const PNode &n = b.nodes[order[qi]];
                     uint64_t w;
                     bool is_node = true;
                     if (n.leaf) {
