@@ -99,6 +99,35 @@ def _engine_variant(models_s2, **kw):
     return Engine(models_s2, device=0, **kw)
 
 
+@pytest.mark.parametrize("memo", ["on", "off"])
+def test_g6_full_size_digest(models_s2, memo):
+    """Gate G6 at the full size of BASELINE configs[1] (GPU vs host twin on ALL 10 M Philox games): the C
+    oracle played the 10,000,000 games of the headline workload once on host cores (scripts/g6_digest.py, 2.6 hours on 8
+    cores) and recorded the SHA-1 of the score table and its event counters (tests/golden/g6_digest.json); the GPU plays
+    the same games here in one call -- with the exact memo as shipped (`sim_memo_kernel`, 0.9 s) and with every request walked
+    (`sim_kernel`, 3.1 s) -- and must reproduce digest, prefix digests and counters."""
+    import hashlib
+    path = os.path.join(GOLDEN, "g6_digest.json")
+    with open(path) as fh:
+        rec = json.load(fh)
+    n = int(rec["games"])
+    e = _engine_variant(models_s2, stage2="booster", memo=memo)
+    try:
+        e.set_matchups([MatchupSpec("Kansas State", "Iowa State", KSU, ISU, n, 0, n, 0)])
+        got = e.simulate_host(int(rec["seed"]), want_hist=False)
+    finally:
+        e.close()
+    sc = np.ascontiguousarray(got["scores"], dtype=np.int32)
+    assert sc.shape == (n, 2)
+    for g, digest in rec["sha1_of_first_games"].items():
+        assert hashlib.sha1(sc[:int(g)].tobytes()).hexdigest() == digest, f"first {g} games differ from the oracle's"
+    assert hashlib.sha1(sc.tobytes()).hexdigest() == rec["sha1_of_int32_scores"]
+    for k, v in rec["counters"].items():
+        assert got["counters"][k] == v, k
+    assert got["counters"]["games"] == n
+    assert (got["counters"]["memo_hits"] > 0) == (memo == "on")
+
+
 @pytest.mark.parametrize("variant", [
     dict(stage2="booster"),
     dict(policy="play_model"),

@@ -128,3 +128,22 @@ def test_oracle_threads_and_determinism(models, oracle):
     # scores are sums of 7s and 3s
     ok = {7 * i + 3 * j for i in range(20) for j in range(20)}
     assert set(a["scores"].ravel().tolist()) <= ok
+
+
+def test_g6_digest_fixture_is_the_oracles(models_s2, oracle):
+    """tests/golden/g6_digest.json (scripts/g6_digest.py: the oracle's 10,000,000 Philox games of BASELINE configs[1],
+    2.6 hours of host time, recorded once) is what the GPU test `test_g6_full_size_digest` compares against.  Here the
+    oracle replays the first 20,000 of those games: their digest must be the recorded prefix digest, and the record must
+    be complete and agree with the GPU run it quotes."""
+    import hashlib
+    from conftest import ISU, KSU
+    with open(os.path.join(GOLDEN, "g6_digest.json")) as fh:
+        rec = json.load(fh)
+    assert rec["games"] == 10_000_000 and rec["seed"] == 20251018
+    assert rec["sha1_of_first_games"][str(rec["games"])] == rec["sha1_of_int32_scores"]
+    assert rec["gpu_run"]["sha1_of_int32_scores"] == rec["sha1_of_int32_scores"]
+    assert rec["gpu_run"]["plays"] == rec["counters"]["plays"]
+    n = 20_000
+    r = oracle.simulate(oracle.make_config(models_s2, KSU, ISU, stage2="booster"), n, seed=rec["seed"])
+    sc = np.ascontiguousarray(r["scores"], dtype=np.int32)
+    assert hashlib.sha1(sc.tobytes()).hexdigest() == rec["sha1_of_first_games"][str(n)]
