@@ -1,8 +1,8 @@
 """Measurement tooling: one build of libfmc_b200.so (scripts/build_variants.py) on the headline workload, without torch
-(a fresh box pays most of a minute for `import torch`):   python scripts/spec_experiment.py games name [trips,break ...]
+(a fresh box pays most of a minute for `import torch`):   python scripts/spec_experiment.py games name
 1 warm + 3 timed `fmc_simulate_host` calls of `games` games of configs[1] (host wall clock: kernel + the copy of the
-per-game score words), a SHA-1 of the score words (every build must print the same one), then the optional
-(max_trips, break_parked) settings, 2 calls each.  One JSON line per measurement, with the seconds since start."""
+per-game score words), a SHA-1 of the score table (every build must print the same one), then digests of four other code
+paths of the memo kernel.  One JSON line per measurement, with the seconds since start."""
 import hashlib, json, os, sys, time
 T0 = time.perf_counter()
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -76,11 +76,4 @@ eng.set_matchups([MatchupSpec("Kansas State", "Iowa State", (15.6, 35.7, 20.0), 
 r_ = eng.simulate_host(0, stream=stream_of(128, 9), want_trace=True, want_iters=True)
 dig["standin_pm_injected"] = sha(r_["scores"], r_["iters"], r_["trace"])
 print(json.dumps({"lib": name, "digests": dig, "t_done_s": round(time.perf_counter() - T0, 1)}), flush=True)
-sys.exit(0)
-for kb in sys.argv[3:]:
-    a, b = (int(x) for x in kb.split(","))
-    eng.ctx.set_memo("on", 0, a, b)
-    t, res = timed(2)
-    print(json.dumps({"lib": name, "max_trips": a, "break_parked": b, "ms": t,
-                      "sha1": hashlib.sha1(res["scores"].tobytes()).hexdigest()}), flush=True)
 eng.close()
